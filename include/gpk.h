@@ -1,0 +1,161 @@
+/*
+ * gpk.h - C ABI of libgpk.so: the B200 (sm_100a) exact-GP hot path behind the
+ * pyGPs plugin API.
+ *
+ * The reference (marionmari/pyGPs @ 792f3c6) is pure Python and has NO FFI
+ * boundary on this path; native code is entered only inside numpy/scipy.  Each
+ * entry point below therefore names the reference *Python* interface whose work
+ * it takes over (file:line under /root/reference/pyGPs/).  The ctypes binding a
+ * maintainer would add to the reference is shown in INTEGRATION.md; this
+ * repository's own binding is pygps_b200/_lib.py.
+ *
+ * Conventions
+ *   - all functions return int: 0 = ok; > 0 = LAPACK-style `info` (1-based index
+ *     of the first non-positive pivot: the matrix is not positive definite; the
+ *     Python wrapper raises np.linalg.LinAlgError exactly where
+ *     Core/tools.py:67,77 does); < 0 = GPK_ERR_* (bad argument / CUDA failure),
+ *     text from gpk_strerror().  Nothing aborts; NaN/Inf propagate into outputs.
+ *   - every pointer is a HOST pointer to caller-owned, C-contiguous float64
+ *     memory unless the name says otherwise.  The handle owns all device memory,
+ *     streams and events.  A handle is not re-entrant; use one per thread/GPU.
+ *   - hyper-parameters are the reference's LOG values, in the reference's order
+ *     (cov.X.hyp lists, Core/cov.py:793,882,1089; lik.Gauss.hyp[0], Core/lik.py:132).
+ *   - there is no CPU fallback: without a usable CUDA device every call fails
+ *     with GPK_ERR_CUDA.
+ */
+#ifndef GPK_H_
+#define GPK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpk_handle_s* gpk_handle;
+
+/* covariance kinds: cov.RBF (Core/cov.py:786), cov.RBFard (:872), cov.Matern (:1078) */
+enum { GPK_COV_RBF = 0, GPK_COV_RBFARD = 1, GPK_COV_MATERN = 2 };
+/* getCovMatrix modes (Core/cov.py:82-93) */
+enum { GPK_MODE_TRAIN = 0, GPK_MODE_CROSS = 1, GPK_MODE_SELF_TEST = 2 };
+
+enum {
+  GPK_OK = 0,
+  GPK_ERR_ARG = -1,      /* bad argument (NULL, size, kind, der index ...)     */
+  GPK_ERR_CUDA = -2,     /* CUDA runtime error; see gpk_strerror / last_error  */
+  GPK_ERR_STATE = -3,    /* call order: no data / no posterior on the handle   */
+  GPK_ERR_NOMEM = -4     /* device allocation failed                           */
+};
+
+/* per-call device timings (CUDA events on the library's own streams), ms */
+typedef struct gpk_stats {
+  double total_ms;       /* whole call on device, first kernel to last          */
+  double kbuild_ms;      /* covariance-matrix build (cov.*.getCovMatrix)        */
+  double potrf_ms;       /* blocked Cholesky incl. fused forward solve          */
+  double solve_ms;       /* backward solve + nlZ reduction                      */
+  double deriv_ms;       /* inverse + dnlZ reduction (want_der only)            */
+  double syrk_ms;        /* sum of trailing-update launches (when profiled)     */
+  double syrk_flops;     /* algorithmic flops of those launches                 */
+  int64_t launches;      /* kernels launched by the call                        */
+  int64_t h2d_bytes;     /* host->device bytes moved by the call                */
+  int64_t d2h_bytes;     /* device->host bytes moved by the call                */
+} gpk_stats;
+
+/* ---- library / device --------------------------------------------------- */
+int         gpk_version(void);
+const char* gpk_strerror(int code);
+int         gpk_device_count(int* count);
+
+/* One handle = one GPU.  `device` is the CUDA ordinal. */
+int gpk_create(int device, gpk_handle* out);
+int gpk_destroy(gpk_handle h);
+const char* gpk_last_error(gpk_handle h);          /* text of the last CUDA error */
+int gpk_last_stats(gpk_handle h, gpk_stats* out);
+/* profile != 0: time every trailing-update launch with events (serialises the
+ * look-ahead; for roofline measurement only). */
+int gpk_set_profile(gpk_handle h, int profile);
+
+/* ---- cov.*.getCovMatrix / getDerMatrix ---------------------------------- *
+ * Replaces Kernel.getCovMatrix(x,z,mode) (Core/cov.py:796-808, 887-904,
+ * 1124-1148) and getDerMatrix (:811-828, :906-938, :1150-1182) including the
+ * scipy cdist('sqeuclidean') + np.exp they call.
+ *   train:     X (n,D)            -> out (n,n)
+ *   cross:     X (n,D), Z (m,D)   -> out (n,m)
+ *   self_test: Z (m,D)            -> out (m,1)
+ * der < 0: covariance; der >= 0: derivative w.r.t. hyp[der].
+ * matern_d in {1,3,5,7} (ignored for the RBF kinds).                        */
+int gpk_cov_matrix(gpk_handle h, int kind, int matern_d,
+                   const double* hyp, int nhyp,
+                   const double* X, int64_t n, const double* Z, int64_t m, int D,
+                   int mode, int der, double* out);
+
+/* ---- tools.jitchol / tools.solve_chol (Core/tools.py:31-97) ------------- *
+ * gpk_potrf: A (n,n) symmetric (only the lower triangle is read) -> R (n,n)
+ * C-order UPPER factor with an exactly zero strict lower triangle, A = R'R.
+ * This is jitchol(A).T as the reference uses it (Core/inf.py:362).  The factor
+ * stays resident on the handle for gpk_potrs.  logdet_half = sum(log(diag R)).
+ * gpk_potrs: X = (R'R)^-1 B for B (n,nrhs) - solve_chol(R,B).               */
+int gpk_potrf(gpk_handle h, const double* A, int64_t n, double* R_out, double* logdet_half);
+int gpk_potrs(gpk_handle h, const double* B, int64_t nrhs, double* X_out);
+
+/* ---- inf.Exact.evaluate (Core/inf.py:353-384) --------------------------- *
+ * gpk_set_data uploads the training inputs once (GP.setData, Core/gp.py:131). */
+int gpk_set_data(gpk_handle h, const double* X, int64_t n, int D);
+/* One evaluation: K build -> chol(K/sn2+I) -> alpha -> nlZ [-> dnlZ].
+ *   ymm      (n)    y - m(x), the mean-subtracted targets (Core/inf.py:358,363)
+ *   alpha    (n)    out: post.alpha                                (:364)
+ *   nlZ      (1)    out                                            (:370)
+ *   dcov     (nhyp) out if want_der: dnlZ.cov                      (:376-377)
+ *   dlik     (1)    out if want_der: dnlZ.lik                      (:374)
+ * post.sW = 1/sn is formed by the caller (:366); dnlZ.mean = -dm'alpha is an
+ * O(n) host product (:378-381).  The factor stays on the device.            */
+int gpk_exact_eval(gpk_handle h, int kind, int matern_d,
+                   const double* hyp, int nhyp, double log_sn,
+                   const double* ymm, int want_der,
+                   double* nlZ, double* alpha, double* dcov, double* dlik);
+/* post.L: the (n,n) C-order upper factor of K/sn2+I (Core/inf.py:367), copied
+ * out only when the caller touches it. */
+int gpk_get_factor(gpk_handle h, double* R_out);
+
+/* ---- GP.predict solves (Core/gp.py:404-419, Cholesky branch) ------------ *
+ * Uses the posterior left on the handle by gpk_exact_eval.
+ *   Xs (ns,D) -> ks_alpha (ns) = Ks'alpha ;  fs2 (ns) = max(kss - colsum(V*V), 0)
+ * with V = R'^-1 (Ks/sn).  The caller adds the prior mean and lik.Gauss's sn2. */
+int gpk_predict(gpk_handle h, const double* Xs, int64_t ns, double* ks_alpha, double* fs2);
+
+/* ---- inf.FITC_Exact.evaluate (Core/inf.py:398-455) ---------------------- *
+ *   U (M,D) inducing inputs (cov.FITCOfKernel.inducingInput, Core/cov.py:339)
+ *   alpha (M) out: post.alpha ; Lpost (M,M) out: post.L (dense, C-order)
+ *   dcov/dlik as for gpk_exact_eval; al (n) out if want_der: (Kt+sn2 I)^-1 (y-m)
+ *   (needed by the caller for dnlZ.mean, :449-451).                          */
+int gpk_fitc_eval(gpk_handle h, int kind, int matern_d,
+                  const double* hyp, int nhyp, double log_sn,
+                  const double* U, int64_t M, const double* ymm, int want_der,
+                  double* nlZ, double* alpha, double* Lpost,
+                  double* dcov, double* dlik, double* al);
+/* FITC branch of GP.predict (Core/gp.py:418): fs2 = kss + colsum(Ks*(L Ks)). */
+int gpk_fitc_predict(gpk_handle h, const double* Xs, int64_t ns, double* ks_alpha, double* fs2);
+
+/* ---- measurement helpers (bench.py / tests only) ------------------------ */
+/* fp64 tensor-pipe micro-benchmark: shape 0=m8n8k4 1=m16n8k4 2=m16n8k8
+ * 3=m16n8k16 4=DFMA (no tensor pipe); returns TFLOP/s over `iters` inner loops. */
+int gpk_bench_dmma(gpk_handle h, int shape, int warps_per_cta, int iters, double* tflops, double* ms);
+/* device-resident DGEMM-NT (C -= A*B' lower / C = A*B') on random data; returns ms
+ * per launch and TFLOP/s of the hot kernel in isolation.                    */
+int gpk_bench_syrk(gpk_handle h, int64_t n, int k, int reps, double* ms, double* tflops);
+/* stream copy bandwidth GB/s (read+write bytes), for a same-box HBM denominator */
+int gpk_bench_copy(gpk_handle h, int64_t bytes, int reps, double* gbs);
+/* debug: C(M,N) = beta*C + alpha*A(M,K)*B(N,K)' with column-major host arrays,
+ * through the production tile kernel.  mode 0: C=A*B' ; 1: C-=A*B' full;
+ * 2: C-=A*B' lower tiles only (M==N); 3: C=A*B' lower tiles, contraction from
+ * k = 128*tile_row (upper-triangular operands).  M,N multiples of 128, K of 16. */
+int gpk_dbg_gemm_nt(gpk_handle h, int mode, int64_t M, int64_t N, int64_t K,
+                    const double* A, const double* B, double* C);
+/* debug: factor + invert one 128x128 block (column-major): L and inv(L). */
+int gpk_dbg_diag(gpk_handle h, const double* A128, double* L128, double* Linv128,
+                 double* logdet_half, int* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPK_H_ */

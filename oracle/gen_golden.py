@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.  TEST INFRASTRUCTURE.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/gen_golden.py [--big]
+
+The reference (marionmari/pyGPs @ 792f3c6) is imported from /root/reference
+through the three stub modules in oracle/shim/ (past.utils, past.builtins,
+matplotlib.pyplot - SURVEY 8(c)).  Every array written here is an output of the
+reference's own classes (pyGPs.GPR / GPR_FITC / cov.* / inf.*); inputs are stored
+next to the outputs when small, otherwise regenerated from the stated seed.
+`--big` adds the N=8192/16384 C2 runs (minutes of CPU, ~7 GiB).
+"""
+import os
+import sys
+import logging
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("PYGPS_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "shim"))
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+import numpy as np  # noqa: E402
+import pyGPs  # noqa: E402
+
+logging.disable(logging.WARNING)
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def synth(N, D, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, D))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    return X, y
+
+
+def flat_dnlz(d):
+    return (np.array(d.mean, dtype=float), np.array(d.cov, dtype=float),
+            np.array(d.lik, dtype=float))
+
+
+def run_model(model, x, y, xs, tag, store, keep_L=True, ys=None):
+    nlZ, dn, post = model.getPosterior(x, y, der=True)
+    dm, dc, dl = flat_dnlz(dn)
+    store[tag + "_nlZ"] = np.float64(nlZ)
+    store[tag + "_dmean"], store[tag + "_dcov"], store[tag + "_dlik"] = dm, dc, dl
+    store[tag + "_alpha"] = post.alpha
+    store[tag + "_sW0"] = np.float64(post.sW[0, 0])
+    if keep_L:
+        store[tag + "_L"] = post.L
+    if xs is not None:
+        out = model.predict(xs, ys)
+        for name, v in zip(("ym", "ys2", "fm", "fs2"), out[:4]):
+            store[tag + "_" + name] = v
+        if ys is not None:
+            store[tag + "_lp"] = out[4]
+
+
+def kat_regression():
+    """KAT1-KAT4 on the reference's shipped fixture Demo/Regression/regression_data.npz."""
+    d = np.load(os.path.join(REF, "pyGPs/Demo/Regression/regression_data.npz"))
+    x, y, xs = d["x"], d["y"], d["xstar"]
+    s = {"x": x, "y": y, "xs": xs}
+    ys = np.sin(xs) + 0.3
+    s["ys"] = ys
+
+    m = pyGPs.GPR()                                   # KAT1: Zero mean, RBF(0,0), Gauss(log .1)
+    run_model(m, x, y, xs, "kat1", s, ys=ys)
+
+    m = pyGPs.GPR()                                   # KAT2: setData -> mean.Const(mean(y))
+    m.setData(x, y)
+    s["kat2_c"] = np.float64(m.meanfunc.hyp[0])
+    run_model(m, x, y, xs, "kat2", s)
+    m = pyGPs.GPR()
+    m.setData(x, y)
+    m.optimize(x, y)
+    s["kat2_opt_nlZ"] = np.float64(m.nlZ)
+    s["kat2_opt_hyp"] = np.array(m.meanfunc.hyp + m.covfunc.hyp + m.likfunc.hyp)
+
+    m = pyGPs.GPR()                                   # KAT3: other kernels
+    m.setPrior(kernel=pyGPs.cov.RBFard(D=1, log_ell_list=[0.3], log_sigma=0.2))
+    run_model(m, x, y, xs, "kat3_ard", s)
+    for dd in (1, 3, 5, 7):
+        m = pyGPs.GPR()
+        m.setPrior(kernel=pyGPs.cov.Matern(d=dd, log_ell=0.3, log_sigma=0.2))
+        nlZ, post = m.getPosterior(x, y, der=False)   # Matern dnlZ is buggy in the reference
+        s["kat3_mat%d_nlZ" % dd] = np.float64(nlZ)
+        s["kat3_mat%d_alpha" % dd] = post.alpha
+        out = m.predict(xs)
+        s["kat3_mat%d_ym" % dd], s["kat3_mat%d_ys2" % dd] = out[0], out[1]
+    m = pyGPs.GPR()                                   # Linear mean (Core/mean.py:339)
+    m.setPrior(mean=pyGPs.mean.Linear(D=1), kernel=pyGPs.cov.RBF(-0.5, 0.1))
+    m.setNoise(np.log(0.2))
+    run_model(m, x, y, xs, "kat3_lin", s)
+
+    u = np.array([[-1.], [-.8], [-.5], [.3], [1.]])   # KAT4: Testing/unit_test_model.py:33
+    s["u"] = u
+    m = pyGPs.GPR_FITC()
+    m.setPrior(kernel=pyGPs.cov.RBF(), inducing_points=u)
+    run_model(m, x, y, xs, "kat4", s)
+    m = pyGPs.GPR_FITC()
+    m.setData(x, y)                                   # default grid of 5 inducing points + Const mean
+    s["kat4b_u"] = m.u
+    s["kat4b_c"] = np.float64(m.meanfunc.hyp[0])
+    run_model(m, x, y, xs, "kat4b", s)
+    np.savez_compressed(os.path.join(OUT, "kat_regression.npz"), **s)
+    print("kat1 nlZ", s["kat1_nlZ"], "kat4 nlZ", s["kat4_nlZ"], "kat2 opt", s["kat2_opt_nlZ"])
+
+
+def cov_vectors():
+    """Kernel matrices in all three modes + derivatives; inputs like Testing/unit_test_cov.py:24-30
+    but with a spread of length scales so K is not the identity."""
+    rng = np.random.RandomState(0)
+    x = rng.normal(0, 2.0, (20, 3))
+    z = rng.normal(0, 2.0, (10, 3))
+    s = {"x": x, "z": z}
+    kernels = {
+        "rbf": pyGPs.cov.RBF(0.7, -0.3),
+        "ard": pyGPs.cov.RBFard(log_ell_list=[0.5, -0.2, 1.1], log_sigma=0.4),
+        "mat1": pyGPs.cov.Matern(0.6, 1, 0.2),
+        "mat3": pyGPs.cov.Matern(0.6, 3, 0.2),
+        "mat5": pyGPs.cov.Matern(0.6, 5, 0.2),
+        "mat7": pyGPs.cov.Matern(0.6, 7, 0.2),
+    }
+    for name, k in kernels.items():
+        s[name + "_hyp"] = np.array(k.hyp, dtype=float)
+        s[name + "_train"] = k.getCovMatrix(x=x, mode="train")
+        s[name + "_cross"] = k.getCovMatrix(x=x, z=z, mode="cross")
+        s[name + "_self"] = k.getCovMatrix(z=z, mode="self_test")
+        if not name.startswith("mat"):
+            for i in range(len(k.hyp)):
+                s["%s_dtrain%d" % (name, i)] = k.getDerMatrix(x=x, mode="train", der=i)
+                s["%s_dcross%d" % (name, i)] = k.getDerMatrix(x=x, z=z, mode="cross", der=i)
+    u = rng.normal(0, 2.0, (5, 3))
+    s["u"] = u
+    f = pyGPs.cov.RBF(0.7, -0.3).fitc(u)
+    dk, kuu, ku = f.getCovMatrix(x=x, mode="train")
+    s["fitc_diag"], s["fitc_kuu"], s["fitc_ku"] = dk, kuu, ku
+    s["fitc_cross"] = f.getCovMatrix(x=x, z=z, mode="cross")
+    A = kernels["rbf"].getCovMatrix(x=x, mode="train") + 0.01 * np.eye(20)
+    L = pyGPs.Core.tools.jitchol(A)
+    s["chol_A"], s["chol_L"] = A, L
+    B = rng.normal(size=(20, 3))
+    s["chol_B"] = B
+    s["chol_X"] = pyGPs.Core.tools.solve_chol(L.T, B)
+    np.savez_compressed(os.path.join(OUT, "cov_vectors.npz"), **s)
+
+
+def synthetic(big=False):
+    """BASELINE configs at oracle-feasible sizes; inputs come from the seed."""
+    s = {}
+    # C2 family: RBF(log 2, 0), Gauss(log 0.1), Zero mean, D=8
+    for N in (256, 1000, 2048):
+        X, y = synth(N, 8)
+        Xs = np.random.default_rng(1).standard_normal((300, 8))
+        m = pyGPs.GPR()
+        m.setPrior(kernel=pyGPs.cov.RBF(np.log(2.0), 0.0))
+        run_model(m, X, y, Xs, "c2_%d" % N, s, keep_L=False)
+        s["c2_%d_Ldiag" % N] = np.diag(m.posterior.L).copy()
+        print("c2", N, s["c2_%d_nlZ" % N])
+    # C1: N=512, D=2, default GPR via setData (Const mean), np.random.seed(0) recipe of BASELINE.md
+    np.random.seed(0)
+    x1 = np.random.randn(512, 2)
+    y1 = np.sin(x1[:, :1]) + 0.1 * np.random.randn(512, 1)
+    s["c1_x"], s["c1_y"] = x1, y1
+    m = pyGPs.GPR()
+    m.setData(x1, y1)
+    s["c1_c"] = np.float64(m.meanfunc.hyp[0])
+    run_model(m, x1, y1, x1[:50] + 0.1, "c1", s, keep_L=False)
+    print("c1", s["c1_nlZ"])
+    # C3 family: RBFard D=32, ell=3
+    for N in (1024,):
+        X, y = synth(N, 32)
+        m = pyGPs.GPR()
+        m.setPrior(kernel=pyGPs.cov.RBFard(D=32, log_ell_list=[np.log(3.0)] * 32, log_sigma=0.0))
+        Xs = np.random.default_rng(1).standard_normal((200, 32))
+        run_model(m, X, y, Xs, "c3_%d" % N, s, keep_L=False)
+        print("c3", N, s["c3_%d_nlZ" % N])
+    # Matern on synthetic
+    X, y = synth(700, 5)
+    Xs = np.random.default_rng(1).standard_normal((100, 5))
+    for dd in (1, 3, 5, 7):
+        m = pyGPs.GPR()
+        m.setPrior(kernel=pyGPs.cov.Matern(d=dd, log_ell=np.log(1.5), log_sigma=0.1))
+        nlZ, post = m.getPosterior(X, y, der=False)
+        s["mat%d_700_nlZ" % dd] = np.float64(nlZ)
+        s["mat%d_700_alpha" % dd] = post.alpha
+        out = m.predict(Xs)
+        s["mat%d_700_ym" % dd], s["mat%d_700_ys2" % dd] = out[0], out[1]
+    # C4 family: GPR_FITC, RBF(log 2, 0), D=8 (fp64 - the reference has no fp32 path)
+    for N, M in ((4096, 256), (2000, 100)):
+        rng = np.random.default_rng(0)
+        X = rng.standard_normal((N, 8))
+        y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+        U = rng.standard_normal((M, 8))
+        Xs = np.random.default_rng(1).standard_normal((300, 8))
+        m = pyGPs.GPR_FITC()
+        m.setPrior(kernel=pyGPs.cov.RBF(np.log(2.0), 0.0), inducing_points=U)
+        run_model(m, X, y, Xs, "c4_%d_%d" % (N, M), s, keep_L=(M <= 100))
+        print("c4", N, M, s["c4_%d_%d_nlZ" % (N, M)])
+    np.savez_compressed(os.path.join(OUT, "synthetic.npz"), **s)
+
+    if big:
+        b = {}
+        for N in (4096, 8192, 16384):
+            X, y = synth(N, 8)
+            m = pyGPs.GPR()
+            m.setPrior(kernel=pyGPs.cov.RBF(np.log(2.0), 0.0))
+            nlZ, post = m.getPosterior(X, y, der=False)
+            b["c2_%d_nlZ" % N] = np.float64(nlZ)
+            b["c2_%d_alpha" % N] = post.alpha
+            b["c2_%d_Ldiag" % N] = np.diag(post.L).copy()
+            Xs = np.random.default_rng(1).standard_normal((64, 8))
+            out = m.predict(Xs)
+            b["c2_%d_ym" % N], b["c2_%d_ys2" % N] = out[0], out[1]
+            print("c2 big", N, repr(nlZ), flush=True)
+            np.savez_compressed(os.path.join(OUT, "synthetic_big.npz"), **b)
+        X, y = synth(4096, 32)
+        m = pyGPs.GPR()
+        m.setPrior(kernel=pyGPs.cov.RBFard(D=32, log_ell_list=[np.log(3.0)] * 32, log_sigma=0.0))
+        nlZ, post = m.getPosterior(X, y, der=False)
+        b["c3_4096_nlZ"] = np.float64(nlZ)
+        b["c3_4096_alpha"] = post.alpha
+        print("c3 big", repr(nlZ), flush=True)
+        np.savez_compressed(os.path.join(OUT, "synthetic_big.npz"), **b)
+
+
+def housing():
+    """The one published number: doc/source/demoHousing.rst:30 (optimized nlZ 214.46);
+    preprocessing per Demo/Housing/demo_Housing.py:25-40."""
+    path = os.path.join(REF, "pyGPs/Demo/Housing/housing.txt")
+    data = np.genfromtxt(path)
+    N = 25
+    x = np.concatenate((data[:-N, :4], data[:-N, 5:-1]), axis=1)
+    x = (x - np.mean(x, axis=0)) / (np.std(x, axis=0) + 1.e-16)
+    y = np.reshape(data[:-N, -1], (len(data[:-N, -1]), 1))
+    y = (y - np.mean(y)) / (np.std(y) + 1.e-16)
+    x_train, y_train = x, y
+    s = {"x": x_train, "y": y_train}
+    m = pyGPs.GPR()
+    nlZ, dn, post = m.getPosterior(x_train, y_train)
+    s["default_nlZ"] = np.float64(nlZ)
+    s["default_dcov"] = np.array(dn.cov)
+    s["default_dlik"] = np.array(dn.lik)
+    m = pyGPs.GPR()
+    m.optimize(x_train, y_train)
+    s["opt_nlZ"] = np.float64(m.nlZ)
+    s["opt_hyp"] = np.array(m.covfunc.hyp + m.likfunc.hyp)
+    print("housing", s["default_nlZ"], s["opt_nlZ"], s["opt_hyp"])
+    np.savez_compressed(os.path.join(OUT, "housing.npz"), **s)
+
+
+if __name__ == "__main__":
+    kat_regression()
+    cov_vectors()
+    synthetic(big="--big" in sys.argv)
+    housing()

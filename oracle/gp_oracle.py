@@ -1,0 +1,387 @@
+"""CPU oracle for the exact-GP hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is a numpy/scipy restatement of the one path of marionmari/pyGPs
+that this repository accelerates (kernel-matrix build -> Cholesky of K/sn2+I ->
+triangular solves -> nlZ / alpha / dnlZ / predictive mean+variance).  It exists
+so the CUDA path can be checked on a box where `/root/reference` is absent.
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline legs may
+import it; nothing under `pygps_b200/` does, and the product never falls back to
+it.
+
+Parity status: PINNED.  `oracle/gen_golden.py` runs the unmodified reference
+(imported from /root/reference through the stubs in `oracle/shim/`) on the
+reference's own fixtures and on the synthetic BASELINE configurations and
+freezes the outputs into `tests/golden/*.npz`; `tests/test_oracle.py` checks
+every function below against those files (<= 1e-12 relative).
+
+It keeps the reference's *call structure* on purpose (cdist + exp, dpotrf on a
+Fortran copy, two general `np.linalg.solve` on the triangular factor) so that
+timing it is a fair stand-in for timing the reference (`cpu_baseline.kind =
+"port"`).  All citations are to files under /root/reference/pyGPs/.
+
+A covariance function is described by a plain tuple
+    ("rbf",    [log_ell, log_sf])                 Core/cov.py:786-808
+    ("rbfard", [log_ell_1..log_ell_D, log_sf])    Core/cov.py:872-904
+    ("matern", [log_ell, log_sf], d)              Core/cov.py:1078-1148
+and a mean function by
+    ("zero",) | ("one",) | ("const", c) | ("linear", [a_1..a_D])   Core/mean.py:279-369
+"""
+import numpy as np
+import scipy.linalg.lapack as _lapack
+from scipy.spatial.distance import cdist as _cdist
+
+LOG2PI = np.log(2.0 * np.pi)
+
+
+# --------------------------------------------------------------------------
+# mean functions  (Core/mean.py:279-369)
+# --------------------------------------------------------------------------
+def mean_vec(mean, x):
+    """Prior mean m(x) as an (n,1) column.  Core/mean.py:285,303,323,356."""
+    n = x.shape[0]
+    kind = mean[0]
+    if kind == "zero":
+        return np.zeros((n, 1))
+    if kind == "one":
+        return np.ones((n, 1))
+    if kind == "const":
+        return float(mean[1]) * np.ones((n, 1))
+    if kind == "linear":
+        return x @ np.asarray(mean[1], dtype=float).reshape(-1, 1)
+    raise ValueError(kind)
+
+
+def mean_hyp(mean):
+    """Flattened trainable parameters of a mean spec."""
+    if mean[0] == "const":
+        return [float(mean[1])]
+    if mean[0] == "linear":
+        return [float(v) for v in mean[1]]
+    return []
+
+
+def mean_der(mean, x, i):
+    """d m(x) / d hyp_i as an (n,1) column.  Core/mean.py:290,308,328-335,361-369."""
+    n = x.shape[0]
+    if mean[0] == "const" and i == 0:
+        return np.ones((n, 1))
+    if mean[0] == "linear" and i < x.shape[1]:
+        return x[:, i].reshape(n, 1).astype(float)
+    return np.zeros((n, 1))
+
+
+# --------------------------------------------------------------------------
+# covariance functions
+# --------------------------------------------------------------------------
+def _matern_d(d):
+    """Core/cov.py:1128-1136: d is rounded, anything outside {1,3,5,7} becomes 3."""
+    if abs(d - round(d)) < 1e-8:
+        d = int(round(d))
+    d = int(d)
+    return d if d in (1, 3, 5, 7) else 3
+
+
+def _matern_poly(d, t):
+    """Core/cov.py:1094-1104 (func)."""
+    if d == 1:
+        return 1.0 + 0.0 * t
+    if d == 3:
+        return 1.0 + t
+    if d == 5:
+        return 1.0 + t + t * t / 3.0
+    return 1.0 + t + 2.0 * t * t / 5.0 + t * t * t / 15.0
+
+
+def _matern_dpoly(d, t):
+    """Core/cov.py:1106-1116 (dfunc = func - dfunc/dt)."""
+    if d == 1:
+        return 1.0 + 0.0 * t
+    if d == 3:
+        return t
+    if d == 5:
+        return (t + t * t) / 3.0
+    return (t + 3.0 * t * t + t * t * t) / 15.0
+
+
+def _scaled_inputs(cov, x, z):
+    """Inputs after the kernel's own length-scale transform, as the reference
+    forms them before calling cdist (RBF divides, Core/cov.py:804; RBFard
+    multiplies by 1/exp(hyp), :893,899; Matern multiplies by sqrt(d)/ell, :1141)."""
+    kind, hyp = cov[0], cov[1]
+    if kind == "rbf":
+        ell = np.exp(hyp[0])
+        f = lambda a: a / ell
+    elif kind == "rbfard":
+        D = (x if x is not None else z).shape[1]
+        inv = 1.0 / np.exp(np.asarray(hyp[:D], dtype=float))
+        f = lambda a: a * inv[None, :]
+    elif kind == "matern":
+        ell = np.exp(hyp[0])
+        d = _matern_d(cov[2])
+        f = lambda a: np.sqrt(d) * a / ell
+    else:
+        raise ValueError(kind)
+    return (None if x is None else f(x)), (None if z is None else f(z))
+
+
+def _sf2(cov, D):
+    hyp = cov[1]
+    return np.exp(2.0 * (hyp[D] if cov[0] == "rbfard" else hyp[1]))
+
+
+def cov_matrix(cov, x=None, z=None, mode=None):
+    """getCovMatrix for RBF / RBFard / Matern.  Core/cov.py:796-808, 887-904, 1124-1148.
+
+    mode 'train' -> (n,n), 'cross' -> (n,m), 'self_test' -> (m,1)."""
+    if mode is None:
+        raise Exception("Specify the mode: 'train' or 'cross'")
+    if x is None and z is None:
+        raise Exception("Specify at least one: training input (x) or test input (z) or both.")
+    if mode == "cross" and (x is None or z is None):
+        raise Exception("Specify both: training input (x) and test input (z) for cross covariance.")
+    D = (x if x is not None else z).shape[1]
+    sf2 = _sf2(cov, D)
+    if mode == "self_test":
+        A = np.zeros((z.shape[0], 1))
+    else:
+        xs, zs = _scaled_inputs(cov, x, z if mode == "cross" else None)
+        A = _cdist(xs, xs if mode == "train" else zs, "sqeuclidean")
+    if cov[0] == "matern":
+        d = _matern_d(cov[2])
+        t = np.sqrt(A)
+        return sf2 * _matern_poly(d, t) * np.exp(-t)
+    return sf2 * np.exp(-0.5 * A)
+
+
+def cov_der_matrix(cov, x=None, z=None, mode=None, der=None):
+    """getDerMatrix: dK/dhyp_der.  RBF Core/cov.py:811-828, RBFard :906-938.
+
+    For Matern this is the mathematically CORRECT derivative (sf2*dmfunc(t) for
+    the length scale); the reference's Core/cov.py:1173-1177 overwrites the
+    distance with K before using it and is wrong (SURVEY section 7, quirk list),
+    so Matern dnlZ is checked by finite differences, not against the reference."""
+    D = (x if x is not None else z).shape[1]
+    sf2 = _sf2(cov, D)
+    kind = cov[0]
+    nh = D + 1 if kind == "rbfard" else 2
+    if der is None:
+        raise Exception("Specify the index of parameters of the derivatives.")
+    if der < 0 or der >= nh:
+        raise Exception("Wrong derivative index")
+    if mode == "self_test":
+        A = np.zeros((z.shape[0], 1))
+    else:
+        xs, zs = _scaled_inputs(cov, x, z if mode == "cross" else None)
+        A = _cdist(xs, xs if mode == "train" else zs, "sqeuclidean")
+    if kind == "matern":
+        d = _matern_d(cov[2])
+        t = np.sqrt(A)
+        if der == 0:
+            return sf2 * _matern_dpoly(d, t) * t * np.exp(-t)
+        return 2.0 * sf2 * _matern_poly(d, t) * np.exp(-t)
+    K = sf2 * np.exp(-0.5 * A)
+    if kind == "rbf":
+        return K * A if der == 0 else 2.0 * K
+    # rbfard
+    if der == D:
+        return 2.0 * K
+    if mode == "self_test":
+        return K * 0.0
+    inv = 1.0 / np.exp(cov[1][der])
+    a = (x[:, der] * inv).reshape(-1, 1)
+    b = a if mode == "train" else (z[:, der] * inv).reshape(-1, 1)
+    return K * _cdist(a, b, "sqeuclidean")
+
+
+def fitc_cov_matrix(cov, xu, x=None, z=None, mode=None):
+    """FITCOfKernel.getCovMatrix.  Core/cov.py:352-370.
+    'train' -> (diagK (n,1), Kuu (M,M), Ku (M,n)); 'cross' -> K(xu,z); 'self_test' -> diag."""
+    if x is not None and xu.shape[1] != x.shape[1]:
+        raise Exception("Dimensionality of inducing inputs must match training inputs")
+    if mode == "self_test":
+        return cov_matrix(cov, z=z, mode="self_test")
+    if mode == "train":
+        return (cov_matrix(cov, z=x, mode="self_test"),
+                cov_matrix(cov, x=xu, mode="train"),
+                cov_matrix(cov, x=xu, z=x, mode="cross"))
+    if mode == "cross":
+        return cov_matrix(cov, x=xu, z=z, mode="cross")
+    raise Exception("Specify the mode: 'train' or 'cross'")
+
+
+def fitc_cov_der_matrix(cov, xu, x, der):
+    """FITCOfKernel.getDerMatrix(mode='train').  Core/cov.py:372-390."""
+    return (cov_der_matrix(cov, z=x, mode="self_test", der=der),
+            cov_der_matrix(cov, x=xu, mode="train", der=der),
+            cov_der_matrix(cov, x=xu, z=x, mode="cross", der=der))
+
+
+# --------------------------------------------------------------------------
+# dense linear-algebra helpers  (Core/tools.py:31-97)
+# --------------------------------------------------------------------------
+def jitchol(A):
+    """Lower Cholesky factor through LAPACK dpotrf on a Fortran-ordered copy.
+    Core/tools.py:60-77.  The reference's jitter retry is dead code (it calls
+    np.linalg.cholesky with a non-existent `lower=` kwarg inside a bare except),
+    so the observable contract is: not PD -> np.linalg.LinAlgError."""
+    A = np.asfortranarray(A)
+    L, info = _lapack.dpotrf(A, lower=1)
+    if info == 0:
+        return L
+    if np.any(np.diag(A) <= 0.0):
+        raise np.linalg.LinAlgError(
+            "kernel matrix not positive definite: non-positive diagonal elements")
+    raise np.linalg.LinAlgError("kernel matrix not positive definite, even with jitter.")
+
+
+def solve_chol(R, B):
+    """X = (R'R)^-1 B with R upper, done as the reference does it: two GENERAL
+    solves (dgesv) on the triangular factor.  Core/tools.py:92-97."""
+    if not (R.shape[0] == R.shape[1] and R.shape[0] == B.shape[0]):
+        raise Exception("Wrong sizes of matrix arguments in solve_chol.py")
+    return np.linalg.solve(R, np.linalg.solve(R.T, B))
+
+
+# --------------------------------------------------------------------------
+# inference engines
+# --------------------------------------------------------------------------
+def exact_evaluate(mean, cov, log_sn, x, y, nargout=1):
+    """inf.Exact.evaluate.  Core/inf.py:353-384.
+
+    Returns post dict {alpha (n,1), sW (n,1), L (n,n) upper} [, nlZ [, dnlZ dict
+    {mean:[], cov:[], lik:[]}]]."""
+    n = x.shape[0]
+    K = cov_matrix(cov, x=x, mode="train")
+    m = mean_vec(mean, x)
+    sn2 = np.exp(2.0 * log_sn)
+    R = jitchol(K / sn2 + np.eye(n)).T
+    alpha = solve_chol(R, y - m) / sn2
+    post = {"alpha": alpha, "sW": np.ones((n, 1)) / np.sqrt(sn2), "L": R}
+    if nargout == 1:
+        return post
+    nlZ = (np.dot((y - m).T, alpha) / 2.0 + np.log(np.diag(R)).sum()
+           + n * np.log(2.0 * np.pi * sn2) / 2.0)[0, 0]
+    if nargout == 2:
+        return post, nlZ
+    Q = solve_chol(R, np.eye(n)) / sn2 - np.dot(alpha, alpha.T)
+    nh = len(cov[1])
+    dn = {"lik": [sn2 * np.trace(Q)],
+          "cov": [(Q * cov_der_matrix(cov, x=x, mode="train", der=i)).sum() / 2.0
+                  for i in range(nh)],
+          "mean": [np.dot(-mean_der(mean, x, i).T, alpha)[0, 0]
+                   for i in range(len(mean_hyp(mean)))]}
+    return post, nlZ, dn
+
+
+def exact_evaluate_fair(cov, log_sn, x, y):
+    """NOT the reference: the same nlZ through scipy's cho_factor/cho_solve
+    (SURVEY 8(d) 'fair CPU' line), so the reported speed-up is not credited for
+    the reference's LU-on-a-triangular-matrix waste."""
+    import scipy.linalg as sla
+    n = x.shape[0]
+    sn2 = np.exp(2.0 * log_sn)
+    A = cov_matrix(cov, x=x, mode="train")
+    A /= sn2
+    A[np.diag_indices(n)] += 1.0
+    c = sla.cho_factor(A, lower=True, overwrite_a=True, check_finite=False)
+    alpha = sla.cho_solve(c, y, check_finite=False) / sn2
+    return (np.dot(y.T, alpha) / 2.0 + np.log(np.diag(c[0])).sum()
+            + n * np.log(2.0 * np.pi * sn2) / 2.0)[0, 0]
+
+
+def fitc_evaluate(mean, cov, xu, log_sn, x, y, nargout=1):
+    """inf.FITC_Exact.evaluate.  Core/inf.py:398-455."""
+    diagK, Kuu, Ku = fitc_cov_matrix(cov, xu, x=x, mode="train")
+    m = mean_vec(mean, x)
+    n = x.shape[0]
+    nu = Kuu.shape[0]
+    sn2 = np.exp(2.0 * log_sn)
+    snu2 = 1.0e-6 * sn2                                    # :410
+    Ruu = jitchol(Kuu + snu2 * np.eye(nu)).T               # :412
+    V = np.linalg.solve(Ruu.T, Ku)                         # :413
+    g = diagK + sn2 - (V * V).sum(axis=0).reshape(n, 1)    # :415
+    Ru = jitchol(np.eye(nu) + np.dot(V / g.T, V.T)).T      # :417
+    r = (y - m) / np.sqrt(g)
+    be = np.linalg.solve(Ru.T, np.dot(V, r / np.sqrt(g)))  # :419
+    iKuu = solve_chol(Ruu, np.eye(nu))                     # :420
+    post = {"alpha": np.linalg.solve(Ruu, np.linalg.solve(Ru, be)),
+            "L": solve_chol(np.dot(Ru, Ruu), np.eye(nu)) - iKuu,
+            "sW": np.ones((n, 1)) / np.sqrt(sn2)}
+    if nargout == 1:
+        return post
+    nlZ = (np.log(np.diag(Ru)).sum()
+           + (np.log(g).sum() + n * LOG2PI + np.dot(r.T, r) - np.dot(be.T, be)) / 2.0)[0, 0]
+    if nargout == 2:
+        return post, nlZ
+    al = r / np.sqrt(g) - np.dot(V.T, np.linalg.solve(Ru, be)) / g      # :431
+    B = np.dot(iKuu, Ku)
+    w = np.dot(B, al)
+    W = np.linalg.solve(Ru.T, V / g.T)
+    WW = (W * W).sum(axis=0).reshape(1, n)
+    BW = np.dot(B, W.T)
+    dcov = []
+    for i in range(len(cov[1])):
+        ddiag, dKuu, dKu = fitc_cov_der_matrix(cov, xu, x, i)
+        Rm = 2.0 * dKu - np.dot(dKuu, B)
+        v = ddiag - (Rm * B).sum(axis=0).reshape(n, 1)
+        val = (np.dot(ddiag.T, 1.0 / g) + np.dot(w.T, np.dot(dKuu, w) - 2.0 * np.dot(dKu, al))
+               - np.dot(al.T, v * al) - np.dot(WW, v) - (np.dot(Rm, W.T) * BW).sum()) / 2.0
+        dcov.append(val[0, 0])
+    dlik = sn2 * ((1.0 / g).sum() - WW.sum() - np.dot(al.T, al))
+    dKuu_s = 2.0 * snu2
+    Rm = -dKuu_s * B
+    v = -(Rm * B).sum(axis=0).reshape(n, 1)
+    dlik = dlik + (np.dot(w.T, dKuu_s * w) - np.dot(al.T, v * al) - np.dot(WW, v)
+                   - (np.dot(Rm, W.T) * BW).sum()) / 2.0
+    dn = {"cov": dcov, "lik": [dlik[0, 0]],
+          "mean": [np.dot(-mean_der(mean, x, i).T, al)[0, 0]
+                   for i in range(len(mean_hyp(mean)))]}
+    return post, nlZ, dn
+
+
+# --------------------------------------------------------------------------
+# prediction  (Core/gp.py:388-437 with lik.Gauss, Core/lik.py:135-158)
+# --------------------------------------------------------------------------
+def predict(mean, cov, log_sn, x, post, xs, ys=None, xu=None, nperbatch=1000):
+    """GP.predict for a Gaussian likelihood.  Returns (ymu, ys2, fmu, fs2, lp|None).
+    `xu` not None selects the FITC branch (dense post['L'], Core/gp.py:418)."""
+    alpha, R, sW = post["alpha"], post["L"], post["sW"]
+    tri = bool(np.all(np.tril(R, -1) == 0))                 # Core/gp.py:393
+    ns = xs.shape[0]
+    sn2 = np.exp(2.0 * log_sn)
+    fmu = np.zeros((ns, 1))
+    fs2 = np.zeros((ns, 1))
+    for lo in range(0, ns, nperbatch):
+        sl = slice(lo, min(lo + nperbatch, ns))
+        zb = xs[sl]
+        if xu is None:
+            kss = cov_matrix(cov, z=zb, mode="self_test")
+            Ks = cov_matrix(cov, x=x, z=zb, mode="cross")
+        else:
+            kss = fitc_cov_matrix(cov, xu, z=zb, mode="self_test")
+            Ks = fitc_cov_matrix(cov, xu, x=x, z=zb, mode="cross")
+        fmu[sl] = mean_vec(mean, zb) + np.dot(Ks.T, alpha)
+        if tri:
+            V = np.linalg.solve(R.T, sW * Ks)                # Core/gp.py:415
+            fs2[sl] = kss - (V * V).sum(axis=0).reshape(-1, 1)
+        else:
+            fs2[sl] = kss + (Ks * np.dot(R, Ks)).sum(axis=0).reshape(-1, 1)
+        fs2[sl] = np.maximum(fs2[sl], 0.0)
+    ymu = fmu.copy()
+    ys2 = fs2 + sn2                                          # Core/lik.py:150-154
+    lp = None
+    if ys is not None:
+        # Core/lik.py:147-148 -> EP-mode Gauss log partition, :160
+        lp = -(ys - fmu) ** 2 / (sn2 + fs2) / 2.0 - np.log(2.0 * np.pi * (sn2 + fs2)) / 2.0
+    return ymu, ys2, fmu, fs2, lp
+
+
+# --------------------------------------------------------------------------
+# synthetic workloads of BASELINE.json / SURVEY section 8(d)
+# --------------------------------------------------------------------------
+def synth_regression(N, D, seed=0):
+    """`rng=default_rng(seed); X=standard_normal((N,D)); y=sin(X.sum(1))+0.1*standard_normal`."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, D))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    return X, y

@@ -1,0 +1,787 @@
+// api.cu - the extern "C" surface of libgpk.so (include/gpk.h) and the host-side
+// orchestration of the blocked right-looking Cholesky with one-panel look-ahead.
+#include <cmath>
+#include <new>
+#include "gpk_internal.cuh"
+
+namespace gpk {
+
+static const double LOG2PI = 1.8378770664093454835606594728112;
+
+int ensure(Handle* h, double** p, int64_t* cap, int64_t need) {
+  if (*cap >= need && *p) return 0;
+  if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+  GPK_CK(h, cudaMalloc((void**)p, (size_t)need * sizeof(double)));
+  *cap = need;
+  return 0;
+}
+
+static int ensure_events(Handle* h, size_t count) {
+  while (h->ev.size() < count) {
+    cudaEvent_t e;
+    GPK_CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev.push_back(e);
+  }
+  return 0;
+}
+static int ensure_prof_events(Handle* h, size_t count) {
+  while (h->prof_ev.size() < count) {
+    cudaEvent_t e;
+    GPK_CK(h, cudaEventCreate(&e));
+    h->prof_ev.push_back(e);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Blocked right-looking Cholesky, in place on the lower triangle of A (np x np,
+// column-major, np a multiple of NB).  Two streams:
+//   s_panel (high priority): diag(k) -> trsm(k) [-> forward-solve step k]
+//   s_main                 : syrk on block column k+1 (so panel k+1 can start)
+//                            -> syrk on the rest of the trailing matrix
+// Panel k+1 therefore overlaps the bulk of trailing update k (look-ahead 1).
+// ---------------------------------------------------------------------------
+int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info, double* b_fwd,
+                 double* z_out) {
+  const int T = (int)(np / NB);
+  const int64_t lda = np;
+  GPK_TRY(ensure_events(h, 2 * (size_t)T + 4));
+  if (h->profile) GPK_TRY(ensure_prof_events(h, 2 * (size_t)T + 2));
+  cudaEvent_t* ev_panel = h->ev.data();      // [T]
+  cudaEvent_t* ev_col = h->ev.data() + T;    // [T]
+  cudaEvent_t ev_fork = h->ev[2 * T], ev_join = h->ev[2 * T + 1];
+  h->stats.syrk_flops = 0.0;
+
+  GPK_CK(h, cudaEventRecord(ev_fork, h->s_main));
+  GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_fork, 0));
+  for (int k = 0; k < T; ++k) {
+    double* Akk = A + (int64_t)k * NB * (1 + lda);
+    double* Dk = Dinv + (int64_t)k * NB * NB;
+    const int rem = T - k - 1;
+    if (k > 0) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_col[k], 0));
+    GPK_TRY(launch_diag(h, h->s_panel, Akk, lda, Dk, logdet_parts + k, info, k * NB));
+    if (rem > 0) {
+      GemmArgs t{};
+      t.A = Akk + NB; t.B = Dk; t.C = Akk + NB;
+      t.lda = lda; t.ldb = NB; t.ldc = lda; t.K = NB; t.tri = 0;
+      GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, rem, 1));
+    }
+    if (b_fwd) GPK_TRY(launch_trsv_fwd(h, h->s_panel, A, lda, Dinv, b_fwd, z_out, k, T));
+    if (rem > 0) {
+      GPK_CK(h, cudaEventRecord(ev_panel[k], h->s_panel));
+      GPK_CK(h, cudaStreamWaitEvent(h->s_main, ev_panel[k], 0));
+      if (h->profile) GPK_CK(h, cudaEventRecord(h->prof_ev[2 * k], h->s_main));
+      GemmArgs u{};
+      u.A = Akk + NB; u.B = Akk + NB; u.C = A + (int64_t)(k + 1) * NB * (1 + lda);
+      u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = NB; u.tri = 1; u.ti_off = 0; u.tj_off = 0;
+      GPK_TRY(launch_gemm_nt(h, h->s_main, 1, u, rem, 1));
+      GPK_CK(h, cudaEventRecord(ev_col[k + 1], h->s_main));
+      if (rem > 1) {
+        GemmArgs v = u;
+        v.B = u.B + NB; v.C = u.C + (int64_t)NB * lda; v.tj_off = 1;
+        GPK_TRY(launch_gemm_nt(h, h->s_main, 1, v, rem, rem - 1));
+      }
+      if (h->profile) GPK_CK(h, cudaEventRecord(h->prof_ev[2 * k + 1], h->s_main));
+      const double nt = (double)rem * NB;
+      h->stats.syrk_flops += (double)NB * nt * nt;
+    }
+  }
+  GPK_CK(h, cudaEventRecord(ev_join, h->s_panel));
+  GPK_CK(h, cudaStreamWaitEvent(h->s_main, ev_join, 0));
+  return 0;
+}
+
+static int collect_profile(Handle* h, int T) {
+  h->stats.syrk_ms = 0.0;
+  if (!h->profile) return 0;
+  for (int k = 0; k + 1 < T; ++k) {
+    float ms = 0.f;
+    GPK_CK(h, cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]));
+    h->stats.syrk_ms += ms;
+  }
+  return 0;
+}
+
+// per-kind input scaling; returns sf2
+static int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::vector<double>& scale,
+                      int* divide, double* premul, double* sf2) {
+  scale.assign(D, 1.0);
+  *premul = 1.0;
+  if (kind == GPK_COV_RBF) {
+    if (nhyp != 2) return GPK_ERR_ARG;
+    for (int d = 0; d < D; ++d) scale[d] = std::exp(hyp[0]);
+    *divide = 1;
+    *sf2 = std::exp(2.0 * hyp[1]);
+  } else if (kind == GPK_COV_RBFARD) {
+    if (nhyp != D + 1) return GPK_ERR_ARG;
+    for (int d = 0; d < D; ++d) scale[d] = 1.0 / std::exp(hyp[d]);
+    *divide = 0;
+    *sf2 = std::exp(2.0 * hyp[D]);
+  } else if (kind == GPK_COV_MATERN) {
+    if (nhyp != 2) return GPK_ERR_ARG;
+    if (!(matern_d == 1 || matern_d == 3 || matern_d == 5 || matern_d == 7)) return GPK_ERR_ARG;
+    for (int d = 0; d < D; ++d) scale[d] = std::exp(hyp[0]);
+    *divide = 1;
+    *premul = std::sqrt((double)matern_d);
+    *sf2 = std::exp(2.0 * hyp[1]);
+  } else {
+    return GPK_ERR_ARG;
+  }
+  return 0;
+}
+
+static int free_all(Handle* h) {
+  double** ptrs[] = {&h->dX, &h->dXs, &h->dScale, &h->dA, &h->dDinv, &h->dB, &h->dZ, &h->dAlpha, &h->dR, &h->dScal,
+                     &h->dU, &h->dW, &h->dP, &h->dTmp, &h->dUin, &h->dUs, &h->dLpost, &h->dAlphaU};
+  for (auto p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  if (h->dInfo) cudaFree(h->dInfo);
+  h->dInfo = nullptr;
+  h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = 0;
+  return 0;
+}
+
+// (re)allocate everything that depends on the padded problem size
+static int alloc_problem(Handle* h, int64_t n, int D) {
+  const int64_t np = round_up(n, NB);
+  const int T = (int)(np / NB);
+  if (np != h->np || D != h->D || !h->dA) {
+    double** ptrs[] = {&h->dXs, &h->dScale, &h->dDinv, &h->dB, &h->dZ, &h->dAlpha, &h->dR, &h->dScal};
+    for (auto p : ptrs) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+    }
+    GPK_TRY(ensure(h, &h->dA, &h->capA, np * np));
+    GPK_CK(h, cudaMalloc((void**)&h->dXs, (size_t)np * D * sizeof(double)));
+    GPK_CK(h, cudaMalloc((void**)&h->dScale, (size_t)(D + 8) * sizeof(double)));
+    GPK_CK(h, cudaMalloc((void**)&h->dDinv, (size_t)np * NB * sizeof(double)));
+    GPK_CK(h, cudaMalloc((void**)&h->dB, (size_t)np * sizeof(double)));
+    GPK_CK(h, cudaMalloc((void**)&h->dZ, (size_t)np * sizeof(double)));
+    GPK_CK(h, cudaMalloc((void**)&h->dAlpha, (size_t)np * sizeof(double)));
+    GPK_CK(h, cudaMalloc((void**)&h->dR, (size_t)np * sizeof(double)));
+    GPK_CK(h, cudaMalloc((void**)&h->dScal, (size_t)(T + 4 * D + 256) * sizeof(double)));
+    if (!h->dInfo) GPK_CK(h, cudaMalloc((void**)&h->dInfo, 4 * sizeof(int)));
+  }
+  h->n = n; h->np = np; h->D = D;
+  return 0;
+}
+
+static void stats_begin(Handle* h) {
+  std::memset(&h->stats, 0, sizeof(h->stats));
+}
+
+static int check_handle(gpk_handle hh, Handle** out) {
+  if (!hh) return GPK_ERR_ARG;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) { h->last_cuda = e; h->last_msg = cudaGetErrorString(e); return GPK_ERR_CUDA; }
+  *out = h;
+  return 0;
+}
+
+// Solve with many right-hand sides held TRANSPOSED: P is (rows x np) column-major with pitch ldp
+// (one right-hand side per ROW).  Forward: P <- P * L^-T, block column by block column.
+static int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A,
+                         int64_t lda, const double* Dinv, int T) {
+  for (int k = 0; k < T; ++k) {
+    GemmArgs t{};
+    t.A = P + (int64_t)k * NB * ldp; t.B = Dinv + (int64_t)k * NB * NB; t.C = P + (int64_t)k * NB * ldp;
+    t.lda = ldp; t.ldb = NB; t.ldc = ldp; t.K = NB; t.tri = 0;
+    GPK_TRY(launch_gemm_nt(h, st, 0, t, row_tiles, 1));
+    if (k + 1 < T) {
+      GemmArgs u{};
+      u.A = P + (int64_t)k * NB * ldp; u.B = A + (int64_t)(k + 1) * NB + (int64_t)k * NB * lda;
+      u.C = P + (int64_t)(k + 1) * NB * ldp;
+      u.lda = ldp; u.ldb = lda; u.ldc = ldp; u.K = NB; u.tri = 0;
+      GPK_TRY(launch_gemm_nt(h, st, 1, u, row_tiles, T - k - 1));
+    }
+  }
+  return 0;
+}
+
+// U <- L^-T (upper triangular, np x np column-major pitch np) by the same sweep applied to the identity,
+// touching only the tiles on or above the diagonal.
+static int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv) {
+  const int T = (int)(np / NB);
+  GPK_TRY(launch_set_identity(h, st, U, np, np, np));
+  for (int k = 0; k < T; ++k) {
+    GemmArgs t{};
+    t.A = U + (int64_t)k * NB * np; t.B = Dinv + (int64_t)k * NB * NB; t.C = U + (int64_t)k * NB * np;
+    t.lda = np; t.ldb = NB; t.ldc = np; t.K = NB; t.tri = 0;
+    GPK_TRY(launch_gemm_nt(h, st, 0, t, k + 1, 1));
+    if (k + 1 < T) {
+      GemmArgs u{};
+      u.A = U + (int64_t)k * NB * np; u.B = A + (int64_t)(k + 1) * NB + (int64_t)k * NB * np;
+      u.C = U + (int64_t)(k + 1) * NB * np;
+      u.lda = np; u.ldb = np; u.ldc = np; u.K = NB; u.tri = 0;
+      GPK_TRY(launch_gemm_nt(h, st, 1, u, k + 1, T - k - 1));
+    }
+  }
+  return 0;
+}
+
+}  // namespace gpk
+
+using namespace gpk;
+
+extern "C" {
+
+int gpk_version(void) { return 100; }
+
+const char* gpk_strerror(int code) {
+  switch (code) {
+    case GPK_OK: return "ok";
+    case GPK_ERR_ARG: return "invalid argument";
+    case GPK_ERR_CUDA: return "CUDA error (see gpk_last_error)";
+    case GPK_ERR_STATE: return "invalid call order: no data / posterior on the handle";
+    case GPK_ERR_NOMEM: return "device out of memory";
+    default: return code > 0 ? "matrix not positive definite (info = failing pivot)" : "unknown error";
+  }
+}
+
+int gpk_device_count(int* count) {
+  if (!count) return GPK_ERR_ARG;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { *count = 0; return GPK_ERR_CUDA; }
+  *count = c;
+  return 0;
+}
+
+int gpk_create(int device, gpk_handle* out) {
+  if (!out) return GPK_ERR_ARG;
+  *out = nullptr;
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) return GPK_ERR_CUDA;
+  if (device < 0 || device >= cnt) return GPK_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return GPK_ERR_CUDA;
+  Handle* h = new (std::nothrow) Handle();
+  if (!h) return GPK_ERR_NOMEM;
+  h->device = device;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  auto fail = [&](int rc) { delete h; return rc; };
+  if (cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) != cudaSuccess) return fail(GPK_ERR_CUDA);
+  if (cudaStreamCreateWithPriority(&h->s_panel, cudaStreamNonBlocking, hi) != cudaSuccess) return fail(GPK_ERR_CUDA);
+  cudaEvent_t* te[] = {&h->t0, &h->t1, &h->t2, &h->t3, &h->t4};
+  for (auto e : te)
+    if (cudaEventCreate(e) != cudaSuccess) return fail(GPK_ERR_CUDA);
+  if (cudaMallocHost((void**)&h->hPinned, 4096 * sizeof(double)) != cudaSuccess) return fail(GPK_ERR_CUDA);
+  int rc = gemm_init(h);
+  if (rc == 0) rc = diag_init(h);
+  if (rc != 0) return fail(rc);
+  *out = reinterpret_cast<gpk_handle>(h);
+  return 0;
+}
+
+int gpk_destroy(gpk_handle hh) {
+  if (!hh) return GPK_ERR_ARG;
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_all(h);
+  for (auto e : h->ev) cudaEventDestroy(e);
+  for (auto e : h->prof_ev) cudaEventDestroy(e);
+  cudaEvent_t te[] = {h->t0, h->t1, h->t2, h->t3, h->t4};
+  for (auto e : te)
+    if (e) cudaEventDestroy(e);
+  if (h->hPinned) cudaFreeHost(h->hPinned);
+  if (h->s_main) cudaStreamDestroy(h->s_main);
+  if (h->s_panel) cudaStreamDestroy(h->s_panel);
+  delete h;
+  return 0;
+}
+
+const char* gpk_last_error(gpk_handle hh) {
+  if (!hh) return "null handle";
+  return reinterpret_cast<Handle*>(hh)->last_msg.c_str();
+}
+
+int gpk_last_stats(gpk_handle hh, gpk_stats* out) {
+  if (!hh || !out) return GPK_ERR_ARG;
+  *out = reinterpret_cast<Handle*>(hh)->stats;
+  return 0;
+}
+
+int gpk_set_profile(gpk_handle hh, int profile) {
+  if (!hh) return GPK_ERR_ARG;
+  reinterpret_cast<Handle*>(hh)->profile = profile;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int gpk_set_data(gpk_handle hh, const double* X, int64_t n, int D) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!X || n <= 0 || D <= 0) return GPK_ERR_ARG;
+  if (n != h->n || D != h->D || !h->dX) {
+    if (h->dX) cudaFree(h->dX);
+    h->dX = nullptr;
+    GPK_CK(h, cudaMalloc((void**)&h->dX, (size_t)n * D * sizeof(double)));
+  }
+  GPK_TRY(alloc_problem(h, n, D));
+  GPK_CK(h, cudaMemcpyAsync(h->dX, X, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+  GPK_CK(h, cudaStreamSynchronize(h->s_main));
+  h->has_post = false;
+  h->has_fitc = false;
+  h->stats.h2d_bytes = n * D * (int64_t)sizeof(double);
+  return 0;
+}
+
+int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
+                   const double* ymm, int want_der, double* nlZ, double* alpha, double* dcov, double* dlik) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!h->dX || h->n <= 0) return GPK_ERR_STATE;
+  if (!hyp || !ymm || !nlZ || !alpha) return GPK_ERR_ARG;
+  if (want_der && (!dcov || !dlik)) return GPK_ERR_ARG;
+  const int64_t n = h->n, np = h->np;
+  const int D = h->D, T = (int)(np / NB);
+  std::vector<double> scale;
+  int divide = 0;
+  double premul = 1.0, sf2 = 1.0;
+  GPK_TRY(kind_scale(kind, matern_d, hyp, nhyp, D, scale, &divide, &premul, &sf2));
+  if (D > 1900) return GPK_ERR_ARG;  // pinned staging layout
+  const double sn2 = std::exp(2.0 * log_sn);
+  stats_begin(h);
+  h->has_post = false;
+  cudaStream_t st = h->s_main;
+
+  GPK_CK(h, cudaEventRecord(h->t0, st));
+  std::memcpy(h->hPinned, scale.data(), D * sizeof(double));
+  GPK_CK(h, cudaMemcpyAsync(h->dScale, h->hPinned, D * sizeof(double), cudaMemcpyHostToDevice, st));
+  GPK_CK(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), st));
+  GPK_TRY(launch_prescale(h, st, h->dX, n, np, D, h->dScale, divide, premul, h->dXs));
+  {
+    CovArgs c{};
+    c.F = h->dXs; c.S = h->dXs; c.out = h->dA; c.ld = np;
+    c.nF = n; c.nS = n; c.pF = np; c.pS = np; c.D = D;
+    c.kind = kind; c.matern_d = matern_d; c.epi = EPI_COV; c.ard_dim = 0;
+    c.sf2 = sf2; c.scale = 1.0 / sn2; c.diag_add = 1.0;
+    c.same_set = 1; c.lower_only = 1; c.pad_identity = 1;
+    GPK_TRY(launch_cov(h, st, c));
+  }
+  GPK_CK(h, cudaEventRecord(h->t1, st));
+  // right-hand side y - m, zero padded; dB is the forward-solve work copy
+  GPK_CK(h, cudaMemsetAsync(h->dR, 0, (size_t)np * sizeof(double), st));
+  GPK_CK(h, cudaMemcpyAsync(h->dR, ymm, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  GPK_CK(h, cudaMemcpyAsync(h->dB, h->dR, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  h->stats.h2d_bytes += (n + D) * (int64_t)sizeof(double);
+
+  GPK_TRY(potrf_device(h, h->dA, np, h->dDinv, h->dScal, h->dInfo, h->dB, h->dZ));
+  GPK_CK(h, cudaEventRecord(h->t2, st));
+  for (int k = T - 1; k >= 0; --k) GPK_TRY(launch_trsv_bwd(h, st, h->dA, np, h->dDinv, h->dZ, h->dB, k, T));
+  double* res = h->dScal + T;  // [0]=r'alpha [1]=logdet ; [8..] derivative results
+  GPK_TRY(launch_finish_alpha(h, st, h->dB, h->dR, 1.0 / sn2, np, h->dAlpha, h->dScal, T, res));
+  GPK_CK(h, cudaEventRecord(h->t3, st));
+
+  if (want_der) {
+    GPK_TRY(ensure(h, &h->dU, &h->capU, np * np));
+    GPK_TRY(ensure(h, &h->dW, &h->capW, np * np));
+    const int64_t g = (n + 63) / 64;
+    const int64_t part_need = g * g * 34;
+    GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, part_need));
+    GPK_TRY(inverse_factor_T(h, st, h->dU, h->dA, np, h->dDinv));
+    GemmArgs v{};
+    v.A = h->dU; v.B = h->dU; v.C = h->dW; v.lda = np; v.ldb = np; v.ldc = np;
+    v.K = (int)np; v.tri = 2;
+    GPK_TRY(launch_gemm_nt(h, st, 0, v, T, T));
+    GPK_TRY(launch_dnlz(h, st, h->dXs, n, D, h->dW, np, h->dAlpha, 1.0 / sn2, sf2, kind, matern_d, h->dTmp,
+                        h->capTmp, res + 8));
+  }
+  GPK_CK(h, cudaEventRecord(h->t4, st));
+
+  const int nres = 8 + (want_der ? nhyp + 1 : 0);
+  GPK_CK(h, cudaMemcpyAsync(h->hPinned, res, nres * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaMemcpyAsync(h->hPinned + 2048, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaMemcpyAsync(alpha, h->dAlpha, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaStreamSynchronize(st));
+  h->stats.d2h_bytes = (n + nres) * (int64_t)sizeof(double) + 4;
+
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->t0, h->t4); h->stats.total_ms = ms;
+  cudaEventElapsedTime(&ms, h->t0, h->t1); h->stats.kbuild_ms = ms;
+  cudaEventElapsedTime(&ms, h->t1, h->t2); h->stats.potrf_ms = ms;
+  cudaEventElapsedTime(&ms, h->t2, h->t3); h->stats.solve_ms = ms;
+  cudaEventElapsedTime(&ms, h->t3, h->t4); h->stats.deriv_ms = ms;
+  GPK_TRY(collect_profile(h, T));
+
+  const int info = *reinterpret_cast<int*>(h->hPinned + 2048);
+  const double dot = h->hPinned[0], logdet = h->hPinned[1];
+  *nlZ = dot / 2.0 + logdet + (double)n * std::log(2.0 * M_PI * sn2) / 2.0;
+  if (want_der) {
+    for (int i = 0; i < nhyp; ++i) dcov[i] = h->hPinned[8 + i] / 2.0;
+    dlik[0] = sn2 * h->hPinned[8 + nhyp];
+  }
+  h->kind = kind; h->matern_d = matern_d; h->nhyp = nhyp; h->sn2 = sn2; h->sf2 = sf2;
+  h->hyp.assign(hyp, hyp + nhyp);
+  h->pn = 0;
+  if (info != 0) return info;  // not positive definite: outputs are NaN-contaminated, as LAPACK would leave them
+  h->has_post = true;
+  return 0;
+}
+
+int gpk_get_factor(gpk_handle hh, double* R_out) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!R_out) return GPK_ERR_ARG;
+  if (!h->has_post && h->pn == 0) return GPK_ERR_STATE;
+  const int64_t n = h->has_post ? h->n : h->pn;
+  const int64_t np = round_up(n, NB);
+  GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, n * n));
+  GPK_TRY(launch_compact_lower(h, h->s_main, h->dA, np, n, h->dTmp));
+  GPK_CK(h, cudaMemcpyAsync(R_out, h->dTmp, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+  GPK_CK(h, cudaStreamSynchronize(h->s_main));
+  h->stats.d2h_bytes = n * n * (int64_t)sizeof(double);
+  return 0;
+}
+
+int gpk_predict(gpk_handle hh, const double* Xs, int64_t ns, double* ks_alpha, double* fs2) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!h->has_post) return GPK_ERR_STATE;
+  if (!Xs || ns <= 0 || !ks_alpha || !fs2) return GPK_ERR_ARG;
+  const int64_t n = h->n, np = h->np;
+  const int D = h->D, T = (int)(np / NB);
+  cudaStream_t st = h->s_main;
+  stats_begin(h);
+  GPK_CK(h, cudaEventRecord(h->t0, st));
+  const int64_t chunk = 8192;
+  const int nsplit = 16;
+  const int64_t cp_max = round_up(ns < chunk ? ns : chunk, NB);
+  // dP: transposed cross-covariance chunk (cp_max x np); dTmp: raw + scaled test inputs, partial sums, outputs
+  GPK_TRY(ensure(h, &h->dP, &h->capP, cp_max * np));
+  const int64_t tmp_need = 2 * cp_max * D + (int64_t)nsplit * cp_max + 2 * cp_max;
+  GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, tmp_need));
+  double* dXraw = h->dTmp;
+  double* dXsc = dXraw + cp_max * D;
+  double* dPart = dXsc + cp_max * D;
+  double* dOut = dPart + (int64_t)nsplit * cp_max;
+  // same input scaling as the posterior's kernel
+  std::vector<double> scale;
+  int divide = 0;
+  double premul = 1.0, sf2 = 1.0;
+  GPK_TRY(kind_scale(h->kind, h->matern_d, h->hyp.data(), h->nhyp, D, scale, &divide, &premul, &sf2));
+  const double sn = std::sqrt(h->sn2);
+  for (int64_t lo = 0; lo < ns; lo += chunk) {
+    const int64_t m = (ns - lo < chunk) ? ns - lo : chunk;
+    const int64_t mp = round_up(m, NB);
+    GPK_CK(h, cudaMemcpyAsync(dXraw, Xs + lo * D, (size_t)m * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    GPK_TRY(launch_prescale(h, st, dXraw, m, mp, D, h->dScale, divide, premul, dXsc));
+    CovArgs c{};
+    c.F = dXsc; c.S = h->dXs; c.out = h->dP; c.ld = mp;
+    c.nF = m; c.nS = n; c.pF = mp; c.pS = np; c.D = D;
+    c.kind = h->kind; c.matern_d = h->matern_d; c.epi = EPI_COV;
+    c.sf2 = sf2; c.scale = 1.0 / sn; c.diag_add = 0.0; c.same_set = 0; c.lower_only = 0; c.pad_identity = 0;
+    GPK_TRY(launch_cov(h, st, c));
+    // Ks' alpha  (undo the 1/sn scaling)
+    GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, h->dAlpha, 0, sn, 0.0, dPart, nsplit, dOut, m));
+    GPK_TRY(sweep_forward(h, st, h->dP, mp, (int)(mp / NB), h->dA, np, h->dDinv, T));
+    GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, nullptr, 1, 1.0, sf2, dPart, nsplit, dOut + mp, m));
+    GPK_CK(h, cudaMemcpyAsync(ks_alpha + lo, dOut, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GPK_CK(h, cudaMemcpyAsync(fs2 + lo, dOut + mp, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GPK_CK(h, cudaStreamSynchronize(st));
+  }
+  GPK_CK(h, cudaEventRecord(h->t1, st));
+  GPK_CK(h, cudaEventSynchronize(h->t1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->t0, h->t1);
+  h->stats.total_ms = ms;
+  h->stats.h2d_bytes = ns * D * (int64_t)sizeof(double);
+  h->stats.d2h_bytes = 2 * ns * (int64_t)sizeof(double);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int gpk_cov_matrix(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, const double* X, int64_t n,
+                   const double* Z, int64_t m, int D, int mode, int der, double* out) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!hyp || !out || D <= 0) return GPK_ERR_ARG;
+  std::vector<double> scale;
+  int divide = 0;
+  double premul = 1.0, sf2 = 1.0;
+  GPK_TRY(kind_scale(kind, matern_d, hyp, nhyp, D, scale, &divide, &premul, &sf2));
+  if (der >= nhyp) return GPK_ERR_ARG;
+  int epi = EPI_COV, ard_dim = 0;
+  if (der >= 0) {
+    if (kind == GPK_COV_RBFARD) {
+      if (der < D) { epi = EPI_DER_ARD; ard_dim = der; } else epi = EPI_DER_SF;
+    } else {
+      epi = (der == 0) ? EPI_DER_ELL : EPI_DER_SF;
+    }
+  }
+  stats_begin(h);
+  if (mode == GPK_MODE_SELF_TEST) {
+    if (!Z || m <= 0) return GPK_ERR_ARG;
+    // k(z,z) at zero distance: sf2 for all three kinds; derivatives: 2*sf2 w.r.t. log sf, 0 otherwise
+    const double v = (epi == EPI_COV) ? sf2 : (epi == EPI_DER_SF ? 2.0 * sf2 : 0.0);
+    for (int64_t i = 0; i < m; ++i) out[i] = v;
+    return 0;
+  }
+  const bool train = (mode == GPK_MODE_TRAIN);
+  if (!train && mode != GPK_MODE_CROSS) return GPK_ERR_ARG;
+  if (!X || n <= 0) return GPK_ERR_ARG;
+  if (!train && (!Z || m <= 0)) return GPK_ERR_ARG;
+  const int64_t mm = train ? n : m;
+  cudaStream_t st = h->s_main;
+  double *dXr = nullptr, *dXq = nullptr, *dZq = nullptr, *dOut = nullptr, *dSc = nullptr;
+  auto cleanup = [&]() {
+    if (dXr) cudaFree(dXr);
+    if (dXq) cudaFree(dXq);
+    if (dZq) cudaFree(dZq);
+    if (dOut) cudaFree(dOut);
+    if (dSc) cudaFree(dSc);
+  };
+#define CKC(call)                                                          \
+  do {                                                                     \
+    cudaError_t e__ = (call);                                              \
+    if (e__ != cudaSuccess) {                                              \
+      h->last_cuda = e__;                                                  \
+      h->last_msg = std::string(#call) + ": " + cudaGetErrorString(e__);   \
+      cleanup();                                                           \
+      return (e__ == cudaErrorMemoryAllocation) ? GPK_ERR_NOMEM : GPK_ERR_CUDA; \
+    }                                                                      \
+  } while (0)
+  const int64_t big = (n > mm ? n : mm);
+  CKC(cudaMalloc((void**)&dXr, (size_t)big * D * sizeof(double)));
+  CKC(cudaMalloc((void**)&dXq, (size_t)n * D * sizeof(double)));
+  if (!train) CKC(cudaMalloc((void**)&dZq, (size_t)m * D * sizeof(double)));
+  CKC(cudaMalloc((void**)&dOut, (size_t)n * mm * sizeof(double)));
+  CKC(cudaMalloc((void**)&dSc, (size_t)D * sizeof(double)));
+  CKC(cudaMemcpyAsync(dSc, scale.data(), D * sizeof(double), cudaMemcpyHostToDevice, st));
+  CKC(cudaMemcpyAsync(dXr, X, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = launch_prescale(h, st, dXr, n, n, D, dSc, divide, premul, dXq);
+  if (rc == 0 && !train) {
+    CKC(cudaMemcpyAsync(dXr, Z, (size_t)m * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = launch_prescale(h, st, dXr, m, m, D, dSc, divide, premul, dZq);
+  }
+  if (rc == 0) {
+    CovArgs c{};
+    // C-order (n, mm) output: fast index = column j (second point set), slow = row i
+    c.F = train ? dXq : dZq; c.S = dXq; c.out = dOut; c.ld = mm;
+    c.nF = mm; c.nS = n; c.pF = mm; c.pS = n; c.D = D;
+    c.kind = kind; c.matern_d = matern_d; c.epi = epi; c.ard_dim = ard_dim;
+    c.sf2 = sf2; c.scale = 1.0; c.diag_add = 0.0; c.same_set = train ? 1 : 0; c.lower_only = 0; c.pad_identity = 0;
+    rc = launch_cov(h, st, c);
+  }
+  if (rc != 0) { cleanup(); return rc; }
+  CKC(cudaMemcpyAsync(out, dOut, (size_t)n * mm * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CKC(cudaStreamSynchronize(st));
+#undef CKC
+  cleanup();
+  h->stats.h2d_bytes = (n + (train ? 0 : m)) * D * (int64_t)sizeof(double);
+  h->stats.d2h_bytes = n * mm * (int64_t)sizeof(double);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int gpk_potrf(gpk_handle hh, const double* A, int64_t n, double* R_out, double* logdet_half) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!A || n <= 0) return GPK_ERR_ARG;
+  const int64_t pn = round_up(n, NB);
+  const int T = (int)(pn / NB);
+  cudaStream_t st = h->s_main;
+  stats_begin(h);
+  h->has_post = false; h->has_fitc = false;
+  // the standalone factor reuses the posterior's storage; sizes follow this call
+  if (pn != h->np || !h->dA) {
+    h->n = 0;
+    GPK_TRY(alloc_problem(h, n, h->D > 0 ? h->D : 1));
+    h->n = 0;
+  }
+  GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, n * n));
+  GPK_CK(h, cudaMemcpyAsync(h->dTmp, A, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  GPK_CK(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), st));
+  GPK_CK(h, cudaEventRecord(h->t0, st));
+  GPK_TRY(launch_pad_sym(h, st, h->dTmp, n, h->dA, pn));
+  GPK_TRY(potrf_device(h, h->dA, pn, h->dDinv, h->dScal, h->dInfo, nullptr, nullptr));
+  GPK_TRY(launch_sum_parts(h, st, h->dScal, T, h->dScal + T));
+  GPK_CK(h, cudaEventRecord(h->t1, st));
+  GPK_CK(h, cudaMemcpyAsync(h->hPinned, h->dScal + T, sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaMemcpyAsync(h->hPinned + 2048, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->t0, h->t1);
+  h->stats.total_ms = ms; h->stats.potrf_ms = ms;
+  GPK_TRY(collect_profile(h, T));
+  const int info = *reinterpret_cast<int*>(h->hPinned + 2048);
+  if (logdet_half) *logdet_half = h->hPinned[0];
+  h->pn = n;
+  if (R_out) GPK_TRY(gpk_get_factor(hh, R_out));
+  if (info != 0) { h->pn = 0; return info; }
+  return 0;
+}
+
+int gpk_potrs(gpk_handle hh, const double* B, int64_t nrhs, double* X_out) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (h->pn <= 0) return GPK_ERR_STATE;
+  if (!B || !X_out || nrhs <= 0) return GPK_ERR_ARG;
+  const int64_t n = h->pn, pn = round_up(n, NB);
+  const int T = (int)(pn / NB);
+  cudaStream_t st = h->s_main;
+  stats_begin(h);
+  // B (n,nrhs) C-order == (nrhs x n) column-major with pitch nrhs: exactly the transposed layout the sweeps use.
+  // X = A^-1 B = B' * (U U') row-wise, with U = L^-T:  Xt = Bt * U * U'.
+  const int64_t rp = round_up(nrhs, NB);
+  GPK_TRY(ensure(h, &h->dU, &h->capU, pn * pn));
+  GPK_TRY(ensure(h, &h->dW, &h->capW, pn * pn));
+  GPK_TRY(ensure(h, &h->dP, &h->capP, 2 * rp * pn));
+  double* P0 = h->dP;
+  double* P1 = h->dP + rp * pn;
+  GPK_CK(h, cudaMemsetAsync(P0, 0, (size_t)rp * pn * sizeof(double), st));
+  GPK_CK(h, cudaMemcpy2DAsync(P0, (size_t)rp * sizeof(double), B, (size_t)nrhs * sizeof(double),
+                              (size_t)nrhs * sizeof(double), (size_t)n, cudaMemcpyHostToDevice, st));
+  // Ainv (lower) = U U'
+  GPK_TRY(inverse_factor_T(h, st, h->dU, h->dA, pn, h->dDinv));
+  GemmArgs v{};
+  v.A = h->dU; v.B = h->dU; v.C = h->dW; v.lda = pn; v.ldb = pn; v.ldc = pn; v.K = (int)pn; v.tri = 2;
+  GPK_TRY(launch_gemm_nt(h, st, 0, v, T, T));
+  // symmetrise into dU (full), then Xt = Bt * Ainv' (= Bt * Ainv)
+  GPK_TRY(launch_compact_sym(h, st, h->dW, pn, pn, h->dU));
+  GemmArgs x{};
+  x.A = P0; x.B = h->dU; x.C = P1; x.lda = rp; x.ldb = pn; x.ldc = rp; x.K = (int)pn; x.tri = 0;
+  GPK_TRY(launch_gemm_nt(h, st, 0, x, (int)(rp / NB), T));
+  GPK_CK(h, cudaMemcpy2DAsync(X_out, (size_t)nrhs * sizeof(double), P1, (size_t)rp * sizeof(double),
+                              (size_t)nrhs * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int gpk_fitc_eval(gpk_handle, int, int, const double*, int, double, const double*, int64_t, const double*, int,
+                  double*, double*, double*, double*, double*, double*) {
+  return GPK_ERR_STATE;
+}
+int gpk_fitc_predict(gpk_handle, const double*, int64_t, double*, double*) { return GPK_ERR_STATE; }
+
+// ---------------------------------------------------------------------------
+int gpk_bench_dmma(gpk_handle hh, int shape, int warps_per_cta, int iters, double* tflops, double* ms) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!tflops || !ms) return GPK_ERR_ARG;
+  return bench_dmma(h, shape, warps_per_cta, iters, tflops, ms);
+}
+
+int gpk_bench_syrk(gpk_handle hh, int64_t n, int k, int reps, double* ms_out, double* tflops) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (n <= 0 || n % NB != 0 || k <= 0 || k % GEMM_BK != 0 || reps <= 0 || !ms_out || !tflops) return GPK_ERR_ARG;
+  cudaStream_t st = h->s_main;
+  double *C = nullptr, *P = nullptr;
+  GPK_CK(h, cudaMalloc((void**)&C, (size_t)n * n * sizeof(double)));
+  if (cudaMalloc((void**)&P, (size_t)n * k * sizeof(double)) != cudaSuccess) { cudaFree(C); return GPK_ERR_NOMEM; }
+  launch_fill_random(h, st, C, n * n, 1u);
+  launch_fill_random(h, st, P, n * k, 2u);
+  GemmArgs u{};
+  u.A = P; u.B = P; u.C = C; u.lda = n; u.ldb = n; u.ldc = n; u.K = k; u.tri = 1;
+  const int T = (int)(n / NB);
+  int rc = launch_gemm_nt(h, st, 1, u, T, T);  // warm-up
+  cudaStreamSynchronize(st);
+  float best = 1e30f, sum = 0.f;
+  for (int r = 0; r < reps && rc == 0; ++r) {
+    cudaEventRecord(h->t0, st);
+    rc = launch_gemm_nt(h, st, 1, u, T, T);
+    cudaEventRecord(h->t1, st);
+    cudaEventSynchronize(h->t1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->t0, h->t1);
+    sum += ms;
+    if (ms < best) best = ms;
+  }
+  cudaFree(C);
+  cudaFree(P);
+  if (rc != 0) return rc;
+  GPK_CK(h, cudaGetLastError());
+  const double avg = sum / reps;
+  *ms_out = avg;
+  *tflops = (double)k * (double)n * (double)n / (avg * 1e-3) / 1e12;  // algorithmic: k*n^2 for the lower triangle
+  (void)best;
+  return 0;
+}
+
+int gpk_bench_copy(gpk_handle hh, int64_t bytes, int reps, double* gbs) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (bytes < 1024 || reps <= 0 || !gbs) return GPK_ERR_ARG;
+  const int64_t n = bytes / 8 / 4 * 4;
+  double *a = nullptr, *b = nullptr;
+  GPK_CK(h, cudaMalloc((void**)&a, (size_t)n * 8));
+  if (cudaMalloc((void**)&b, (size_t)n * 8) != cudaSuccess) { cudaFree(a); return GPK_ERR_NOMEM; }
+  cudaStream_t st = h->s_main;
+  launch_fill_random(h, st, a, n, 3u);
+  launch_copy(h, st, a, b, n);
+  cudaStreamSynchronize(st);
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    cudaEventRecord(h->t0, st);
+    launch_copy(h, st, a, b, n);
+    cudaEventRecord(h->t1, st);
+    cudaEventSynchronize(h->t1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->t0, h->t1);
+    if (ms < best) best = ms;
+  }
+  cudaFree(a);
+  cudaFree(b);
+  GPK_CK(h, cudaGetLastError());
+  *gbs = 2.0 * n * 8 / (best * 1e-3) / 1e9;
+  return 0;
+}
+
+int gpk_dbg_gemm_nt(gpk_handle hh, int mode, int64_t M, int64_t N, int64_t K, const double* A, const double* B,
+                    double* C) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!A || !B || !C || M % NB || N % NB || K % GEMM_BK || mode < 0 || mode > 3) return GPK_ERR_ARG;
+  if ((mode >= 2) && M != N) return GPK_ERR_ARG;
+  cudaStream_t st = h->s_main;
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  GPK_CK(h, cudaMalloc((void**)&dA, (size_t)M * K * 8));
+  GPK_CK(h, cudaMalloc((void**)&dB, (size_t)N * K * 8));
+  GPK_CK(h, cudaMalloc((void**)&dC, (size_t)M * N * 8));
+  cudaMemcpyAsync(dA, A, (size_t)M * K * 8, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dB, B, (size_t)N * K * 8, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dC, C, (size_t)M * N * 8, cudaMemcpyHostToDevice, st);
+  GemmArgs u{};
+  u.A = dA; u.B = dB; u.C = dC; u.lda = M; u.ldb = N; u.ldc = M; u.K = (int)K;
+  u.tri = (mode == 2) ? 1 : (mode == 3 ? 2 : 0);
+  int rc = launch_gemm_nt(h, st, (mode == 0 || mode == 3) ? 0 : 1, u, (int)(M / NB), (int)(N / NB));
+  cudaMemcpyAsync(C, dC, (size_t)M * N * 8, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  if (rc != 0) return rc;
+  GPK_CK(h, e);
+  return 0;
+}
+
+int gpk_dbg_diag(gpk_handle hh, const double* A128, double* L128, double* Linv128, double* logdet_half, int* info) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!A128 || !L128 || !Linv128 || !logdet_half || !info) return GPK_ERR_ARG;
+  cudaStream_t st = h->s_main;
+  double *dA = nullptr, *dI = nullptr, *dS = nullptr;
+  int* dInfo = nullptr;
+  GPK_CK(h, cudaMalloc((void**)&dA, NB * NB * 8));
+  GPK_CK(h, cudaMalloc((void**)&dI, NB * NB * 8));
+  GPK_CK(h, cudaMalloc((void**)&dS, 64));
+  GPK_CK(h, cudaMalloc((void**)&dInfo, 16));
+  cudaMemcpyAsync(dA, A128, NB * NB * 8, cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(dInfo, 0, 16, st);
+  int rc = launch_diag(h, st, dA, NB, dI, dS, dInfo, 0);
+  cudaMemcpyAsync(L128, dA, NB * NB * 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(Linv128, dI, NB * NB * 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(logdet_half, dS, 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(info, dInfo, 4, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(dA); cudaFree(dI); cudaFree(dS); cudaFree(dInfo);
+  if (rc != 0) return rc;
+  GPK_CK(h, e);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// Internal declarations shared by the libgpk translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/gpk.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libgpk is written for sm_100a (B200) only"
+#endif
+
+namespace gpk {
+
+constexpr int NB = 128;          // tile edge == panel width of the blocked Cholesky
+constexpr int GEMM_BK = 16;      // k-slab per pipeline stage
+constexpr int GEMM_LDS = NB + 4; // smem column pitch (doubles); == 4 mod 16 -> conflict-free DMMA fragment loads
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 256;
+constexpr size_t GEMM_SMEM = size_t(2) * GEMM_STAGES * GEMM_BK * GEMM_LDS * sizeof(double);
+
+constexpr int DIAG_THREADS = 256;
+constexpr int DIAG_IB = 32;
+constexpr int DIAG_LDT = DIAG_IB + 1;
+constexpr size_t DIAG_SMEM = (size_t(NB) * NB + 4 * DIAG_IB * DIAG_LDT) * sizeof(double);
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ---- argument blocks ------------------------------------------------------
+// C(tile ti,tj) (+)= A(rows ti) * B(rows tj)^T ; all column-major, all tile-aligned.
+struct GemmArgs {
+  const double* A; const double* B; double* C;
+  int64_t lda, ldb, ldc;
+  int K;            // contraction length (multiple of GEMM_BK)
+  int ti_off;       // global tile index of grid row 0   (triangular tests)
+  int tj_off;       // global tile index of grid column 0
+  int tri;          // 0: all tiles; 1: only gi>=gj, diagonal tiles store row>=col;
+                    // 2: as 1, and the contraction starts at k = gi*NB (U*U^T of an upper-triangular U)
+};
+
+enum CovEpi { EPI_COV = 0, EPI_DER_ELL = 1, EPI_DER_SF = 2, EPI_DER_ARD = 3 };
+
+struct CovArgs {
+  const double* F;  // scaled inputs indexed by the FAST output index (nF, D) row-major
+  const double* S;  // scaled inputs indexed by the SLOW output index (nS, D)
+  double* out;      // out[f + s*ld]
+  int64_t ld;
+  int64_t nF, nS;   // valid extents
+  int64_t pF, pS;   // padded extents actually written (>= nF/nS)
+  int D;
+  int kind;         // GPK_COV_*
+  int matern_d;
+  int epi;          // CovEpi
+  int ard_dim;      // for EPI_DER_ARD
+  double sf2;
+  double scale;     // out = value*scale (+ diag_add on f==s)
+  double diag_add;
+  int same_set;     // F and S are the same point set (train mode): f==s is the diagonal
+  int lower_only;   // skip tiles entirely above the diagonal (f-tile < s-tile); zero strict upper inside diagonal tiles
+  int pad_identity; // padded diagonal entries (f==s>=nF) get 1.0 instead of 0.0
+};
+
+// ---- handle ---------------------------------------------------------------
+struct Handle {
+  int device = 0;
+  cudaStream_t s_main = nullptr, s_panel = nullptr;
+  std::vector<cudaEvent_t> ev;          // dependency events (no timing)
+  cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr, t4 = nullptr;
+  cudaError_t last_cuda = cudaSuccess;
+  std::string last_msg;
+  gpk_stats stats{};
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_ev;
+
+  // training data
+  int64_t n = 0, np = 0; int D = 0;
+  double* dX = nullptr;      // (n,D) as given
+  double* dXs = nullptr;     // (np,D) scaled by the kernel's length scales, zero padded
+  double* dScale = nullptr;  // (D) per-dimension multipliers
+  // factor storage
+  double* dA = nullptr; int64_t capA = 0;    // (np,np) column-major, lower = L
+  double* dDinv = nullptr;   // (np,NB): inverses of the diagonal blocks, block k at rows k*NB
+  double* dB = nullptr;      // (np) forward-solve work vector
+  double* dZ = nullptr;      // (np) z = L^-1 r
+  double* dAlpha = nullptr;  // (np) alpha
+  double* dR = nullptr;      // (np) y - m
+  double* dScal = nullptr;   // scalars: [0..T) logdet parts, then results
+  int* dInfo = nullptr;
+  double* hPinned = nullptr; // small pinned staging
+  // posterior state
+  bool has_post = false; int kind = 0, matern_d = 3, nhyp = 0; double sn2 = 1.0, sf2 = 1.0;
+  std::vector<double> hyp;
+  // derivative / predict / fitc work buffers (lazy)
+  double* dU = nullptr; int64_t capU = 0;
+  double* dW = nullptr; int64_t capW = 0;
+  double* dP = nullptr; int64_t capP = 0;
+  double* dTmp = nullptr; int64_t capTmp = 0;
+  // standalone potrf state
+  int64_t pn = 0;
+  // fitc state
+  bool has_fitc = false; int64_t M = 0, Mp = 0;
+  double* dUin = nullptr; double* dUs = nullptr; double* dLpost = nullptr; double* dAlphaU = nullptr;
+  int64_t capUin = 0;
+};
+
+#define GPK_CK(h, call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      (h)->last_cuda = e__;                                                    \
+      (h)->last_msg = std::string(#call) + ": " + cudaGetErrorString(e__);     \
+      return (e__ == cudaErrorMemoryAllocation) ? GPK_ERR_NOMEM : GPK_ERR_CUDA; \
+    }                                                                          \
+  } while (0)
+
+#define GPK_TRY(expr)                 \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != 0) return rc__;       \
+  } while (0)
+
+// ---- launchers (defined in the .cu files) ----------------------------------
+int launch_gemm_nt(Handle* h, cudaStream_t st, int mode /*0 set, 1 sub*/, const GemmArgs& a, int tiles_m, int tiles_n);
+int launch_cov(Handle* h, cudaStream_t st, const CovArgs& a);
+int launch_prescale(Handle* h, cudaStream_t st, const double* X, int64_t n, int64_t np, int D,
+                    const double* scale, int divide, double premul, double* out);
+int launch_diag(Handle* h, cudaStream_t st, double* Ablk, int64_t lda, double* Dinv, double* logdet_slot,
+                int* info, int gidx0);
+int launch_trsv_fwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* b,
+                    double* z, int k, int T);
+int launch_trsv_bwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* z,
+                    double* x, int k, int T);
+int launch_finish_alpha(Handle* h, cudaStream_t st, const double* x, const double* r, double inv_sn2, int64_t np,
+                        double* alpha, const double* parts, int T, double* res);
+int launch_sum_parts(Handle* h, cudaStream_t st, const double* parts, int T, double* res);
+int launch_pad_sym(Handle* h, cudaStream_t st, const double* src, int64_t n, double* dst, int64_t pn);
+int launch_compact_lower(Handle* h, cudaStream_t st, const double* src, int64_t ld, int64_t n, double* dst);
+int launch_compact_sym(Handle* h, cudaStream_t st, const double* src, int64_t ld, int64_t n, double* dst);
+int launch_set_identity(Handle* h, cudaStream_t st, double* M, int64_t ld, int64_t rows, int64_t cols);
+int launch_rowdot(Handle* h, cudaStream_t st, const double* P, int64_t ld, int64_t rows, int64_t cols, const double* v,
+                  int mode, double scale, double kss, double* part, int nsplit, double* out, int64_t nvalid);
+int launch_dnlz(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
+                const double* alpha, double inv_sn2, double sf2, int kind, int matern_d, double* part,
+                int64_t part_cap, double* res);
+int launch_copy(Handle* h, cudaStream_t st, const double* src, double* dst, int64_t n);
+int launch_fill_random(Handle* h, cudaStream_t st, double* p, int64_t n, unsigned seed);
+int bench_dmma(Handle* h, int shape, int warps, int iters, double* tflops, double* ms_out);
+int gemm_init(Handle* h);
+int diag_init(Handle* h);
+
+int ensure(Handle* h, double** p, int64_t* cap, int64_t need_elems);
+int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info,
+                 double* b_fwd /*nullable: fused forward solve in/out*/, double* z_out);
+
+}  // namespace gpk
