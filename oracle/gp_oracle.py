@@ -93,14 +93,16 @@ def _matern_poly(d, t):
 
 
 def _matern_dpoly(d, t):
-    """Core/cov.py:1106-1116 (dfunc = func - dfunc/dt)."""
+    """func - dfunc/dt, the factor of the length-scale derivative (Core/cov.py:1106-1116).
+    For d=7 the reference has (t + 3t^2 + t^3)/15; the true value of func - func' is
+    (3t + 3t^2 + t^3)/15 (finite-difference checked in tests/test_oracle.py), used here."""
     if d == 1:
         return 1.0 + 0.0 * t
     if d == 3:
         return t
     if d == 5:
         return (t + t * t) / 3.0
-    return (t + 3.0 * t * t + t * t * t) / 15.0
+    return (3.0 * t + 3.0 * t * t + t * t * t) / 15.0
 
 
 def _scaled_inputs(cov, x, z):

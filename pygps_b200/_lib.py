@@ -1,0 +1,327 @@
+"""ctypes binding of libgpk.so (include/gpk.h) - the only door to the GPU.
+
+There is deliberately no CPU fallback here: if the shared library is missing or
+no CUDA device is usable, every entry point raises.  The oracle under `oracle/`
+is test infrastructure and is never imported from this package.
+"""
+import ctypes
+import os
+import threading
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libgpk.so")
+
+COV_RBF, COV_RBFARD, COV_MATERN = 0, 1, 2
+MODE_TRAIN, MODE_CROSS, MODE_SELF_TEST = 0, 1, 2
+_MODES = {"train": MODE_TRAIN, "cross": MODE_CROSS, "self_test": MODE_SELF_TEST}
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+
+class GpkStats(ctypes.Structure):
+    _fields_ = [("total_ms", ctypes.c_double), ("kbuild_ms", ctypes.c_double),
+                ("potrf_ms", ctypes.c_double), ("solve_ms", ctypes.c_double),
+                ("deriv_ms", ctypes.c_double), ("syrk_ms", ctypes.c_double),
+                ("syrk_flops", ctypes.c_double), ("launches", ctypes.c_int64),
+                ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class GpkError(RuntimeError):
+    pass
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+# every symbol include/gpk.h declares: (name, restype, argtypes)
+_H = ctypes.c_void_p
+_I, _L, _D = ctypes.c_int, ctypes.c_int64, ctypes.c_double
+PROTOTYPES = [
+    ("gpk_version", _I, []),
+    ("gpk_strerror", ctypes.c_char_p, [_I]),
+    ("gpk_device_count", _I, [c_int_p]),
+    ("gpk_create", _I, [_I, ctypes.POINTER(_H)]),
+    ("gpk_destroy", _I, [_H]),
+    ("gpk_last_error", ctypes.c_char_p, [_H]),
+    ("gpk_last_stats", _I, [_H, ctypes.POINTER(GpkStats)]),
+    ("gpk_set_profile", _I, [_H, _I]),
+    ("gpk_cov_matrix", _I, [_H, _I, _I, c_double_p, _I, c_double_p, _L, c_double_p, _L, _I, _I, _I, c_double_p]),
+    ("gpk_potrf", _I, [_H, c_double_p, _L, c_double_p, c_double_p]),
+    ("gpk_potrs", _I, [_H, c_double_p, _L, c_double_p]),
+    ("gpk_set_data", _I, [_H, c_double_p, _L, _I]),
+    ("gpk_exact_eval", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, _I,
+                            c_double_p, c_double_p, c_double_p, c_double_p]),
+    ("gpk_get_factor", _I, [_H, c_double_p]),
+    ("gpk_predict", _I, [_H, c_double_p, _L, c_double_p, c_double_p]),
+    ("gpk_fitc_eval", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, _L, c_double_p, _I,
+                           c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    ("gpk_fitc_predict", _I, [_H, c_double_p, _L, c_double_p, c_double_p]),
+    ("gpk_bench_dmma", _I, [_H, _I, _I, _I, c_double_p, c_double_p]),
+    ("gpk_bench_syrk", _I, [_H, _L, _I, _I, c_double_p, c_double_p]),
+    ("gpk_bench_copy", _I, [_H, _L, _I, c_double_p]),
+    ("gpk_dbg_gemm_nt", _I, [_H, _I, _L, _L, _L, c_double_p, c_double_p, c_double_p]),
+    ("gpk_dbg_diag", _I, [_H, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
+]
+
+
+def lib_path():
+    return _LIBPATH
+
+
+def load():
+    """Load libgpk.so and attach prototypes.  Raises GpkError when it has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIBPATH):
+            raise GpkError(
+                "libgpk.so is not built (%s). Run `python -m pygps_b200.build`; "
+                "this package has no CPU fallback." % _LIBPATH)
+        lib = ctypes.CDLL(_LIBPATH)
+        for name, res, args in PROTOTYPES:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def as_f64(a, name="array"):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.ndim != 2:
+        raise Exception("%s must be a 2-d array" % name)
+    return a
+
+
+class Engine(object):
+    """One GPU handle.  Not re-entrant; one in-flight call at a time."""
+
+    def __init__(self, device=None):
+        self._lib = load()
+        if device is None:
+            device = int(os.environ.get("PYGPS_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            cnt = ctypes.c_int(0)
+            self._lib.gpk_device_count(ctypes.byref(cnt))
+            if cnt.value > 0:
+                device %= cnt.value
+        self.device = device
+        h = _H()
+        rc = self._lib.gpk_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise GpkError("gpk_create(device=%d) failed: %s - a CUDA device is required, there is no CPU fallback"
+                           % (device, self._lib.gpk_strerror(rc).decode()))
+        self._h = h
+        self.epoch = 0              # bumped whenever the resident factor changes
+        self._live_posts = weakref.WeakSet()   # postStructs whose lazy L points at this handle
+        self._finalizer = weakref.finalize(self, self._lib.gpk_destroy, h)
+
+    # -- helpers ------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc == 0:
+            return
+        if rc > 0:
+            # LAPACK-style info: same exception type and text as Core/tools.py:77
+            raise np.linalg.LinAlgError("kernel matrix not positive definite, even with jitter.")
+        msg = self._lib.gpk_strerror(rc).decode()
+        if rc == -2:
+            msg += ": " + self._lib.gpk_last_error(self._h).decode()
+        raise GpkError("%s failed (%d): %s" % (what, rc, msg))
+
+    def stats(self):
+        s = GpkStats()
+        self._lib.gpk_last_stats(self._h, ctypes.byref(s))
+        return s.as_dict()
+
+    def set_profile(self, on):
+        self._lib.gpk_set_profile(self._h, int(bool(on)))
+
+    def _retire_factor(self):
+        """Called before the resident factor is overwritten: a posterior that still
+        holds a lazy reference to it gets its L materialised first."""
+        live = list(self._live_posts)
+        self._live_posts = weakref.WeakSet()
+        for post in live:
+            post._materialize()
+        self.epoch += 1
+
+    # -- covariance -----------------------------------------------------------
+    def cov_matrix(self, kind, matern_d, hyp, x, z, mode, der=-1):
+        hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+        m = _MODES[mode]
+        if m == MODE_SELF_TEST:
+            z = as_f64(z, "z")
+            out = np.empty((z.shape[0], 1))
+            rc = self._lib.gpk_cov_matrix(self._h, kind, matern_d, _dp(hyp), hyp.size, None, 0, _dp(z),
+                                          z.shape[0], z.shape[1], m, der, _dp(out))
+        elif m == MODE_TRAIN:
+            x = as_f64(x, "x")
+            out = np.empty((x.shape[0], x.shape[0]))
+            rc = self._lib.gpk_cov_matrix(self._h, kind, matern_d, _dp(hyp), hyp.size, _dp(x), x.shape[0],
+                                          None, 0, x.shape[1], m, der, _dp(out))
+        else:
+            x = as_f64(x, "x")
+            z = as_f64(z, "z")
+            if x.shape[1] != z.shape[1]:
+                raise Exception("x and z must have the same number of columns")
+            out = np.empty((x.shape[0], z.shape[0]))
+            rc = self._lib.gpk_cov_matrix(self._h, kind, matern_d, _dp(hyp), hyp.size, _dp(x), x.shape[0],
+                                          _dp(z), z.shape[0], x.shape[1], m, der, _dp(out))
+        self._check(rc, "gpk_cov_matrix")
+        return out
+
+    # -- jitchol / solve_chol -------------------------------------------------
+    def potrf(self, A, want_factor=True):
+        A = as_f64(A, "A")
+        n = A.shape[0]
+        self._retire_factor()
+        R = np.empty((n, n)) if want_factor else None
+        ld = ctypes.c_double(0.0)
+        rc = self._lib.gpk_potrf(self._h, _dp(A), n, _dp(R), ctypes.byref(ld))
+        if rc > 0:
+            if np.any(np.diag(A) <= 0.0):
+                raise np.linalg.LinAlgError(
+                    "kernel matrix not positive definite: non-positive diagonal elements")
+        self._check(rc, "gpk_potrf")
+        return R, ld.value
+
+    def potrs(self, B):
+        B = as_f64(B, "B")
+        X = np.empty_like(B)
+        rc = self._lib.gpk_potrs(self._h, _dp(B), B.shape[1], _dp(X))
+        self._check(rc, "gpk_potrs")
+        return X
+
+    # -- exact inference ------------------------------------------------------
+    def set_data(self, x):
+        x = as_f64(x, "x")
+        self._retire_factor()
+        rc = self._lib.gpk_set_data(self._h, _dp(x), x.shape[0], x.shape[1])
+        self._check(rc, "gpk_set_data")
+        self.n, self.D = x.shape
+
+    def exact_eval(self, kind, matern_d, hyp, log_sn, ymm, want_der):
+        hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+        ymm = np.ascontiguousarray(ymm, dtype=np.float64).reshape(-1)
+        n = ymm.size
+        self._retire_factor()
+        alpha = np.empty((n, 1))
+        nlZ = ctypes.c_double(0.0)
+        dcov = np.zeros(max(hyp.size, 1))
+        dlik = np.zeros(1)
+        rc = self._lib.gpk_exact_eval(self._h, kind, matern_d, _dp(hyp), hyp.size, float(log_sn), _dp(ymm),
+                                      1 if want_der else 0, ctypes.byref(nlZ), _dp(alpha), _dp(dcov), _dp(dlik))
+        self._check(rc, "gpk_exact_eval")
+        return np.float64(nlZ.value), alpha, dcov[:hyp.size], dlik
+
+    def get_factor(self, n):
+        R = np.empty((n, n))
+        rc = self._lib.gpk_get_factor(self._h, _dp(R))
+        self._check(rc, "gpk_get_factor")
+        return R
+
+    def predict(self, xs):
+        xs = as_f64(xs, "xs")
+        ns = xs.shape[0]
+        ka = np.empty((ns, 1))
+        fs2 = np.empty((ns, 1))
+        rc = self._lib.gpk_predict(self._h, _dp(xs), ns, _dp(ka), _dp(fs2))
+        self._check(rc, "gpk_predict")
+        return ka, fs2
+
+    # -- FITC -----------------------------------------------------------------
+    def fitc_eval(self, kind, matern_d, hyp, log_sn, u, ymm, want_der):
+        hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+        u = as_f64(u, "inducing inputs")
+        ymm = np.ascontiguousarray(ymm, dtype=np.float64).reshape(-1)
+        M, n = u.shape[0], ymm.size
+        self._retire_factor()
+        alpha = np.empty((M, 1))
+        Lp = np.empty((M, M))
+        nlZ = ctypes.c_double(0.0)
+        dcov = np.zeros(max(hyp.size, 1))
+        dlik = np.zeros(1)
+        al = np.zeros((n, 1))
+        rc = self._lib.gpk_fitc_eval(self._h, kind, matern_d, _dp(hyp), hyp.size, float(log_sn), _dp(u), M,
+                                     _dp(ymm), 1 if want_der else 0, ctypes.byref(nlZ), _dp(alpha), _dp(Lp),
+                                     _dp(dcov), _dp(dlik), _dp(al))
+        self._check(rc, "gpk_fitc_eval")
+        return np.float64(nlZ.value), alpha, Lp, dcov[:hyp.size], dlik, al
+
+    def fitc_predict(self, xs):
+        xs = as_f64(xs, "xs")
+        ns = xs.shape[0]
+        ka = np.empty((ns, 1))
+        fs2 = np.empty((ns, 1))
+        rc = self._lib.gpk_fitc_predict(self._h, _dp(xs), ns, _dp(ka), _dp(fs2))
+        self._check(rc, "gpk_fitc_predict")
+        return ka, fs2
+
+    # -- measurement ----------------------------------------------------------
+    def bench_dmma(self, shape, warps=8, iters=20000):
+        tf, ms = ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self._lib.gpk_bench_dmma(self._h, shape, warps, iters, ctypes.byref(tf), ctypes.byref(ms)),
+                    "gpk_bench_dmma")
+        return tf.value, ms.value
+
+    def bench_syrk(self, n, k=128, reps=5):
+        tf, ms = ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self._lib.gpk_bench_syrk(self._h, n, k, reps, ctypes.byref(ms), ctypes.byref(tf)),
+                    "gpk_bench_syrk")
+        return ms.value, tf.value
+
+    def bench_copy(self, nbytes=1 << 30, reps=5):
+        g = ctypes.c_double(0)
+        self._check(self._lib.gpk_bench_copy(self._h, nbytes, reps, ctypes.byref(g)), "gpk_bench_copy")
+        return g.value
+
+    def dbg_gemm_nt(self, mode, A, B, C):
+        """Column-major (Fortran-ordered) A (M,K), B (N,K), C (M,N); returns the new C."""
+        A = np.asfortranarray(A, dtype=np.float64)
+        B = np.asfortranarray(B, dtype=np.float64)
+        C = np.array(C, dtype=np.float64, order="F", copy=True)
+        M, K = A.shape
+        N = B.shape[0]
+        rc = self._lib.gpk_dbg_gemm_nt(self._h, mode, M, N, K, A.ctypes.data_as(c_double_p),
+                                       B.ctypes.data_as(c_double_p), C.ctypes.data_as(c_double_p))
+        self._check(rc, "gpk_dbg_gemm_nt")
+        return C
+
+    def dbg_diag(self, A):
+        A = np.asfortranarray(A, dtype=np.float64)
+        L = np.zeros((128, 128), order="F")
+        Li = np.zeros((128, 128), order="F")
+        ld = ctypes.c_double(0)
+        info = ctypes.c_int(0)
+        rc = self._lib.gpk_dbg_diag(self._h, A.ctypes.data_as(c_double_p), L.ctypes.data_as(c_double_p),
+                                    Li.ctypes.data_as(c_double_p), ctypes.byref(ld), ctypes.byref(info))
+        self._check(rc, "gpk_dbg_diag")
+        return L, Li, ld.value, info.value
+
+
+_shared = {}
+_shared_lock = threading.Lock()
+
+
+def shared_engine(device=None):
+    """Process-wide engine used by the stateless entry points (getCovMatrix, jitchol, solve_chol)."""
+    key = device
+    with _shared_lock:
+        e = _shared.get(key)
+        if e is None:
+            e = Engine(device)
+            _shared[key] = e
+        return e

@@ -44,11 +44,12 @@ __device__ __forceinline__ double cov_value(const CovArgs& a, double d2, double 
       case 1: f = 1.0; df = 1.0; break;
       case 3: f = 1.0 + t; df = t; break;
       case 5: f = 1.0 + t + t * t / 3.0; df = (t + t * t) / 3.0; break;
-      default: f = 1.0 + t + 2.0 * t * t / 5.0 + t * t * t / 15.0; df = (t + 3.0 * t * t + t * t * t) / 15.0; break;
+      default: f = 1.0 + t + 2.0 * t * t / 5.0 + t * t * t / 15.0; df = (3.0 * t + 3.0 * t * t + t * t * t) / 15.0; break;
     }
     if (a.epi == EPI_COV) return a.sf2 * f * e;
     if (a.epi == EPI_DER_SF) return 2.0 * a.sf2 * f * e;
-    return a.sf2 * df * t * e;  // d/dlog(ell): the mathematically correct form (reference :1173-1177 is buggy)
+    return a.sf2 * df * t * e;  // d/dlog(ell), mathematically correct: the reference reuses K as the distance
+                              // (:1173-1177) and its d=7 polynomial (:1114) has t where 3t belongs
   }
   const double k = a.sf2 * exp(-0.5 * d2);
   switch (a.epi) {

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) dnlz_kernel(const DnlzArgs a) {
           case 1: f = 1.0; df = 1.0; break;
           case 3: f = 1.0 + t; df = t; break;
           case 5: f = 1.0 + t + t * t / 3.0; df = (t + t * t) / 3.0; break;
-          default: f = 1.0 + t + 2.0 * t * t / 5.0 + t * t * t / 15.0; df = (t + 3.0 * t * t + t * t * t) / 15.0; break;
+          default: f = 1.0 + t + 2.0 * t * t / 5.0 + t * t * t / 15.0; df = (3.0 * t + 3.0 * t * t + t * t * t) / 15.0; break;
         }
         acc[0] = fma(w * q, a.sf2 * df * t * e, acc[0]);
         acc[1] = fma(w * q, 2.0 * a.sf2 * f * e, acc[1]);

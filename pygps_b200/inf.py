@@ -1,0 +1,229 @@
+"""Inference engines on the accelerated path: Exact and FITC_Exact.
+
+Mirror of pyGPs.Core.inf (/root/reference/pyGPs/Core/inf.py): same
+`evaluate(meanfunc, covfunc, likfunc, x, y, nargout)` contract (:140-172), same
+result containers postStruct (:59-89) and dnlZStruct (:93-128), same exceptions.
+One evaluation is ONE foreign call (gpk_exact_eval / gpk_fitc_eval): the kernel
+matrix, its factor and the solves never leave the GPU; post.L is fetched lazily.
+"""
+import logging
+from copy import copy
+
+import numpy as np
+
+from . import _lib, cov, lik
+from .tools import jitchol, solve_chol
+
+np.seterr(all='ignore')          # the reference does this at import (Core/inf.py:56)
+
+
+class postStruct(object):
+    """Posterior parameters alpha, sW, L (Core/inf.py:59-89).
+
+    L is device-backed: it is copied out of GPU memory the first time it is read
+    (an (n,n) upper-triangular C-ordered array, exactly what the reference stores)."""
+
+    def __init__(self):
+        self.alpha = np.array([])
+        self.sW = np.array([])
+        self._L = np.array([])
+        self._engine = None      # engine that holds the factor this posterior describes
+        self._epoch = -1
+        self._n = 0
+        self._spec = None        # what the resident factor was built from (for predict)
+
+    # -- lazy factor ----------------------------------------------------------
+    def _resident(self):
+        return self._engine is not None and self._engine.epoch == self._epoch
+
+    def _materialize(self):
+        if self._L is None:
+            if not self._resident():
+                raise RuntimeError("posterior factor is no longer resident on the GPU")
+            self._L = self._engine.get_factor(self._n)
+        return self._L
+
+    def _getL(self):
+        return self._materialize()
+
+    def _setL(self, value):
+        self._L = value
+        self._engine = None
+    L = property(_getL, _setL)
+
+    def __deepcopy__(self, memo):
+        # GP.getPosterior deep-copies the posterior every call (Core/gp.py:338,344); copying a
+        # lazy handle instead of an N x N matrix keeps that cheap.
+        other = postStruct()
+        other.alpha = np.array(self.alpha, copy=True)
+        other.sW = np.array(self.sW, copy=True)
+        other._L = None if self._L is None else np.array(self._L, copy=True)
+        other._engine, other._epoch, other._n, other._spec = self._engine, self._epoch, self._n, self._spec
+        if other._L is None and other._engine is not None:
+            other._engine._live_posts.add(other)
+        return other
+
+    def __repr__(self):
+        return ("posterior: to get the parameters of the posterior distribution use:\n"
+                "model.posterior.alpha\nmodel.posterior.L\nmodel.posterior.sW\n"
+                "See documentation and gpml book chapter 2.3 and chapter 3.4.3 for these parameters.")
+
+    def __str__(self):
+        return ("posterior distribution described by alpha, sW and L\n"
+                "See documentation and gpml book chapter 2.3 and chapter 3.4.3 for these parameters\n"
+                "alpha:\n" + str(self.alpha) + "\nL:\n" + str(self.L) + "\nsW:\n" + str(self.sW))
+
+
+class dnlZStruct(object):
+    """Derivatives of nlZ w.r.t. mean / cov / lik hyper-parameters (Core/inf.py:93-128)."""
+
+    def __init__(self, m, c, l):
+        self.mean = []
+        self.cov = []
+        self.lik = []
+        if m.hyp is not None:
+            self.mean = [0 for i in range(len(m.hyp))]
+        if c.hyp is not None:
+            self.cov = [0 for i in range(len(c.hyp))]
+        if l.hyp is not None:
+            self.lik = [0 for i in range(len(l.hyp))]
+
+    def __str__(self):
+        return ("Derivatives of mean, cov and lik functions:\nmean:" + str(self.mean) + "\ncov:"
+                + str(self.cov) + "\nlik:" + str(self.lik))
+
+    def __repr__(self):
+        return ("dnlZ: to get the derivatives of mean, cov and lik functions use:\n"
+                "model.dnlZ.mean\nmodel.dnlZ.cov\nmodel.dnlZ.lik")
+
+    def accumulateDnlZ(self, dnlZObject):
+        self.mean = [a + b for a, b in zip(self.mean, dnlZObject.mean)]
+        self.cov = [a + b for a, b in zip(self.cov, dnlZObject.cov)]
+        self.lik = [a + b for a, b in zip(self.lik, dnlZObject.lik)]
+        return self
+
+
+class Inference(object):
+    """Base class (Core/inf.py:133-172)."""
+
+    def __init__(self):
+        self.logger = logging.getLogger(__name__)
+        self._engine = None
+
+    def _get_engine(self):
+        if getattr(self, '_engine', None) is None:
+            self._engine = _lib.Engine()
+        return self._engine
+
+    def evaluate(self, meanfunc, covfunc, likfunc, x, y, nargout=1):
+        pass
+
+
+def _mean_derivs(meanfunc, x, vec, dnlZ):
+    """dnlZ.mean[i] = -dm_i' vec (Core/inf.py:378-381, :449-451): O(n) host products."""
+    for i in range(len(meanfunc.hyp)):
+        dnlZ.mean[i] = np.float64(np.dot(-meanfunc.getDerMatrix(x, i).T, vec)[0, 0])
+
+
+class Exact(Inference):
+    """Exact inference for a GP with Gaussian likelihood (Core/inf.py:345-384)."""
+
+    def __init__(self):
+        self.name = "Exact inference"
+        self._engine = None
+
+    def evaluate(self, meanfunc, covfunc, likfunc, x, y, nargout=1):
+        if not isinstance(likfunc, lik.Gauss):
+            raise Exception('Exact inference only possible with Gaussian likelihood')
+        n, D = x.shape
+        m = meanfunc.getMean(x)
+        sn2 = np.exp(2 * likfunc.hyp[0])
+        spec = covfunc._device_spec() if not isinstance(covfunc, cov.FITCOfKernel) else None
+        if spec is None:
+            return self._evaluate_generic(meanfunc, covfunc, likfunc, x, y, m, sn2, nargout)
+        kind, md, hyp = spec
+        eng = self._get_engine()
+        eng.set_data(x)
+        nlZ, alpha, dcov, dlik = eng.exact_eval(kind, md, hyp, likfunc.hyp[0], y - m, nargout > 2)
+        post = postStruct()
+        post.alpha = alpha
+        post.sW = np.ones((n, 1)) / np.sqrt(sn2)
+        post._L = None
+        post._engine, post._epoch, post._n = eng, eng.epoch, n
+        post._spec = ('exact', kind, md, tuple(hyp), float(likfunc.hyp[0]))
+        eng._live_posts.add(post)
+        if nargout > 1:
+            if nargout > 2:
+                dnlZ = dnlZStruct(meanfunc, covfunc, likfunc)
+                dnlZ.lik = [np.float64(dlik[0])]
+                dnlZ.cov = [np.float64(v) for v in dcov]
+                _mean_derivs(meanfunc, x, alpha, dnlZ)
+                return post, nlZ, dnlZ
+            return post, nlZ
+        return post
+
+    def _evaluate_generic(self, meanfunc, covfunc, likfunc, x, y, m, sn2, nargout):
+        """Composite kernels: K is assembled from device-built pieces on the host, the
+        factorisation and solves still run on the GPU (gpk_potrf / gpk_potrs)."""
+        n = x.shape[0]
+        K = covfunc.getCovMatrix(x=x, mode='train')
+        L = jitchol(K / sn2 + np.eye(n)).T
+        alpha = solve_chol(L, y - m) / sn2
+        post = postStruct()
+        post.alpha = alpha
+        post.sW = np.ones((n, 1)) / np.sqrt(sn2)
+        post.L = np.ascontiguousarray(L)
+        if nargout > 1:
+            nlZ = (np.dot((y - m).T, alpha) / 2. + np.log(np.diag(L)).sum() + n * np.log(2 * np.pi * sn2) / 2.)[0, 0]
+            if nargout > 2:
+                dnlZ = dnlZStruct(meanfunc, covfunc, likfunc)
+                Q = solve_chol(L, np.eye(n)) / sn2 - np.dot(alpha, alpha.T)
+                dnlZ.lik = [sn2 * np.trace(Q)]
+                for ii in range(len(covfunc.hyp)):
+                    dnlZ.cov[ii] = (Q * covfunc.getDerMatrix(x=x, mode='train', der=ii)).sum() / 2.
+                _mean_derivs(meanfunc, x, alpha, dnlZ)
+                return post, nlZ, dnlZ
+            return post, nlZ
+        return post
+
+
+class FITC_Exact(Inference):
+    """FITC approximation with Gaussian likelihood (Core/inf.py:387-455)."""
+
+    def __init__(self):
+        self.name = 'FICT exact inference'
+        self._engine = None
+
+    def evaluate(self, meanfunc, covfunc, likfunc, x, y, nargout=1):
+        if not isinstance(likfunc, lik.Gauss):
+            raise Exception('Exact inference only possible with Gaussian likelihood')
+        if not isinstance(covfunc, cov.FITCOfKernel):
+            raise Exception('Only covFITC supported.')
+        spec = covfunc._device_spec()
+        if spec is None:
+            raise Exception('FITC on the GPU path needs cov.RBF, cov.RBFard or cov.Matern')
+        kind, md, hyp = spec
+        xu = covfunc.inducingInput
+        if xu.shape[1] != x.shape[1]:
+            raise Exception('Dimensionality of inducing inputs must match training inputs')
+        n, D = x.shape
+        m = meanfunc.getMean(x)
+        sn2 = np.exp(2 * likfunc.hyp[0])
+        eng = self._get_engine()
+        eng.set_data(x)
+        nlZ, alpha, Lp, dcov, dlik, al = eng.fitc_eval(kind, md, hyp, likfunc.hyp[0], xu, y - m, nargout > 2)
+        post = postStruct()
+        post.alpha = alpha
+        post.sW = np.ones((n, 1)) / np.sqrt(sn2)
+        post.L = Lp
+        post._engine, post._epoch, post._n = eng, eng.epoch, xu.shape[0]
+        post._spec = ('fitc', kind, md, tuple(hyp), float(likfunc.hyp[0]))
+        if nargout > 1:
+            if nargout > 2:
+                dnlZ = dnlZStruct(meanfunc, covfunc, likfunc)
+                dnlZ.cov = [np.float64(v) for v in dcov]
+                dnlZ.lik = [np.float64(dlik[0])]
+                _mean_derivs(meanfunc, x, al, dnlZ)
+                return post, nlZ, dnlZ
+            return post, nlZ
+        return post

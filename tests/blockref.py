@@ -1,0 +1,173 @@
+"""numpy model of the DEVICE algorithms (block level), for CPU tests of the host logic.
+
+Every function mirrors one launcher/kernel of pygps_b200/csrc with the same
+argument meaning, so the orchestration in api.cu (look-ahead Cholesky, the
+transposed multi-right-hand-side sweeps, the inverse through U = L^-T, the
+in-block inversion of potrf_diag_kernel) can be checked against scipy without a
+GPU.  Matrices are Fortran-ordered numpy arrays == the device's column-major.
+"""
+import numpy as np
+
+NB = 128
+IB = 32
+
+
+def gemm_nt(mode, C, A, B, K, tiles_m, tiles_n, tri=0, ti_off=0, tj_off=0):
+    """dgemm_nt_kernel: C(ti,tj) = A(ti)·B(tj)' (mode 0) or C -= A·B' (mode 1).
+    A, B, C are views whose [0,0] is the tile-grid origin (like the device pointers)."""
+    for tj in range(tiles_n):
+        for ti in range(tiles_m):
+            gi, gj = ti + ti_off, tj + tj_off
+            if tri and gi < gj:
+                continue
+            kbeg = gi * NB if tri == 2 else 0
+            a = A[ti * NB:(ti + 1) * NB, kbeg:K]
+            b = B[tj * NB:(tj + 1) * NB, kbeg:K]
+            p = a @ b.T
+            c = C[ti * NB:(ti + 1) * NB, tj * NB:(tj + 1) * NB]
+            new = p if mode == 0 else c - p
+            if tri and gi == gj:
+                mask = np.tril(np.ones((NB, NB), dtype=bool))
+                c[mask] = new[mask]
+            else:
+                c[...] = new
+
+
+def diag_block(Ablk):
+    """potrf_diag_kernel: returns (L, inv(L), sum log diag, info) for one 128x128 block,
+    following the kernel's 32-wide inner blocking and its in-place inversion order."""
+    S = np.tril(Ablk).copy(order="F")
+    T = []
+    logdet = 0.0
+    info = 0
+    nblk = NB // IB
+    for jb in range(nblk):
+        j0 = jb * IB
+        a = S[j0:j0 + IB, j0:j0 + IB].copy()
+        for j in range(IB):            # the warp-shuffle column loop
+            d = a[j, j]
+            if not d > 0 and info == 0:
+                info = j0 + j + 1
+            l = np.sqrt(d)
+            a[j:, j] = a[j:, j] / l
+            a[j, j] = l
+            a[:j, j] = 0.0
+            logdet += np.log(l)
+            for c in range(j + 1, IB):
+                a[:, c] -= a[:, j] * a[c, j]
+        a = np.tril(a)
+        S[j0:j0 + IB, j0:j0 + IB] = a
+        W = np.zeros((IB, IB))
+        for col in range(IB):          # per-lane forward substitution
+            for i in range(IB):
+                s = (1.0 if i == col else 0.0) - a[i, :i] @ W[:i, col]
+                W[i, col] = s / a[i, i]
+        T.append(W)
+        if jb < nblk - 1:
+            r0 = j0 + IB
+            S[r0:, j0:j0 + IB] = S[r0:, j0:j0 + IB] @ W.T
+            P = S[r0:, j0:j0 + IB]
+            upd = P @ P.T
+            nrb = nblk - 1 - jb
+            for ib in range(nrb):
+                for cb in range(ib + 1):
+                    S[r0 + ib * IB:r0 + (ib + 1) * IB, r0 + cb * IB:r0 + (cb + 1) * IB] -= \
+                        upd[ib * IB:(ib + 1) * IB, cb * IB:(cb + 1) * IB]
+    L = np.tril(S).copy(order="F")
+    # phase 3: in-place inverse, last block column first
+    S = np.tril(S)                      # the kernel never reads the garbage above sub-block diagonals
+    for jb in range(nblk - 1, -1, -1):
+        j0 = jb * IB
+        r0 = j0 + IB
+        if jb < nblk - 1:
+            Y = S[r0:, j0:j0 + IB] @ T[jb]
+            S[r0:, j0:j0 + IB] = -(np.tril(S[r0:, r0:]) @ Y)
+        S[j0:j0 + IB, j0:j0 + IB] = T[jb]
+    return L, S.copy(order="F"), logdet, info
+
+
+def trsv_fwd(A, Dinv, b, z, k, T):
+    zk = Dinv[k] @ b[k * NB:(k + 1) * NB]
+    z[k * NB:(k + 1) * NB] = zk
+    for i in range(1, T - k):
+        r = (k + i) * NB
+        b[r:r + NB] -= A[r:r + NB, k * NB:(k + 1) * NB] @ zk
+
+
+def trsv_bwd(A, Dinv, z, x, k, T):
+    xk = Dinv[k].T @ z[k * NB:(k + 1) * NB]
+    x[k * NB:(k + 1) * NB] = xk
+    for j in range(k):
+        z[j * NB:(j + 1) * NB] -= A[k * NB:(k + 1) * NB, j * NB:(j + 1) * NB].T @ xk
+
+
+def potrf_device(A, b=None):
+    """api.cu potrf_device (stream order flattened).  A: padded (np,np) F-order, lower
+    triangle valid; factor overwrites it.  Returns Dinv list, logdet parts, info, z."""
+    np_ = A.shape[0]
+    T = np_ // NB
+    Dinv = [None] * T
+    parts = np.zeros(T)
+    info = 0
+    z = np.zeros(np_) if b is not None else None
+    for k in range(T):
+        s = slice(k * NB, (k + 1) * NB)
+        L, Li, ld, inf_k = diag_block(A[s, s])
+        A[s, s] = L
+        Dinv[k], parts[k] = Li, ld
+        if inf_k and not info:
+            info = k * NB + inf_k
+        rem = T - k - 1
+        if rem > 0:
+            pan = A[(k + 1) * NB:, s]
+            gemm_nt(0, pan, pan.copy(), Li, NB, rem, 1)
+        if b is not None:
+            trsv_fwd(A, Dinv, b, z, k, T)
+        if rem > 0:
+            pan = A[(k + 1) * NB:, s]
+            Ct = A[(k + 1) * NB:, (k + 1) * NB:]
+            gemm_nt(1, Ct, pan, pan, NB, rem, 1, tri=1)
+            if rem > 1:
+                gemm_nt(1, Ct[:, NB:], pan, pan[NB:], NB, rem, rem - 1, tri=1, tj_off=1)
+    return Dinv, parts, info, z
+
+
+def sweep_forward(P, A, Dinv, T):
+    """api.cu sweep_forward: P (rows x np) <- P · L^-T."""
+    rt = P.shape[0] // NB
+    for k in range(T):
+        blk = P[:, k * NB:(k + 1) * NB]
+        gemm_nt(0, blk, blk.copy(), Dinv[k], NB, rt, 1)
+        if k + 1 < T:
+            gemm_nt(1, P[:, (k + 1) * NB:], blk, A[(k + 1) * NB:, k * NB:(k + 1) * NB], NB, rt, T - k - 1)
+
+
+def inverse_factor_T(A, Dinv):
+    """api.cu inverse_factor_T: U = L^-T, touching only tiles on/above the diagonal."""
+    np_ = A.shape[0]
+    T = np_ // NB
+    U = np.asfortranarray(np.eye(np_))
+    for k in range(T):
+        blk = U[:(k + 1) * NB, k * NB:(k + 1) * NB]
+        gemm_nt(0, blk, blk.copy(), Dinv[k], NB, k + 1, 1)
+        if k + 1 < T:
+            gemm_nt(1, U[:(k + 1) * NB, (k + 1) * NB:], blk, A[(k + 1) * NB:, k * NB:(k + 1) * NB],
+                    NB, k + 1, T - k - 1)
+    return U
+
+
+def inverse_lower(U):
+    """Ainv (lower tiles) = U·U' with the trapezoidal contraction start (tri=2)."""
+    np_ = U.shape[0]
+    T = np_ // NB
+    W = np.asfortranarray(np.full((np_, np_), np.nan))
+    gemm_nt(0, W, U, U, np_, T, T, tri=2)
+    return W
+
+
+def pad_spd(Amat):
+    n = Amat.shape[0]
+    np_ = (n + NB - 1) // NB * NB
+    P = np.asfortranarray(np.eye(np_))
+    P[:n, :n] = Amat
+    return P

@@ -1,0 +1,158 @@
+"""Kernel-level parity on the B200: each CUDA kernel through the C ABI against numpy/scipy."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pygps_b200 import _lib, build
+    build.build()
+    return _lib.Engine(0)
+
+
+def _report(name, got, ref):
+    err = np.abs(got - ref)
+    i = np.unravel_index(np.nanargmax(err), err.shape)
+    return "%s: max abs err %.3e at %s (got %r ref %r), nan=%d" % (
+        name, err[i], i, got[i], ref[i], int(np.isnan(got).sum()))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", [(128, 128, 16), (256, 384, 128), (512, 128, 256)])
+def test_gemm_nt_full(eng, mode, shape):
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K + mode)
+    A = rng.standard_normal((M, K)); B = rng.standard_normal((N, K)); C = rng.standard_normal((M, N))
+    got = eng.dbg_gemm_nt(mode, A, B, C)
+    ref = A @ B.T if mode == 0 else C - A @ B.T
+    assert np.allclose(got, ref, rtol=1e-12, atol=1e-11), _report("gemm mode %d" % mode, got, ref)
+
+
+def test_gemm_nt_lower_only_leaves_upper_untouched(eng):
+    n, K = 384, 128
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((n, K)); C = rng.standard_normal((n, n))
+    got = eng.dbg_gemm_nt(2, A, A, C)
+    ref = C - A @ A.T
+    lo = np.tril(np.ones((n, n), bool))
+    assert np.allclose(got[lo], ref[lo], rtol=1e-12, atol=1e-11), _report("syrk lower", np.where(lo, got, 0), np.where(lo, ref, 0))
+    assert np.array_equal(got[~lo], C[~lo]), "strict upper triangle was written"
+
+
+def test_gemm_nt_trapezoid(eng):
+    n = 384
+    rng = np.random.default_rng(6)
+    U = np.triu(rng.standard_normal((n, n)))
+    C = np.full((n, n), 7.0)
+    got = eng.dbg_gemm_nt(3, U, U, C)
+    ref = U @ U.T
+    lo = np.tril(np.ones((n, n), bool))
+    assert np.allclose(got[lo], ref[lo], rtol=1e-12, atol=1e-11), _report("U U^T", np.where(lo, got, 0), np.where(lo, ref, 0))
+
+
+def _spd128(seed):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((128, 3))
+    d = ((X[:, None] - X[None]) ** 2).sum(-1)
+    return np.exp(-0.5 * d / 4.0) / 0.01 + np.eye(128)
+
+
+def test_diag_block_factor_and_inverse(eng):
+    A = _spd128(1)
+    L, Li, ld, info = eng.dbg_diag(A)
+    Lref = np.linalg.cholesky(A)
+    assert info == 0
+    assert np.allclose(L, Lref, rtol=1e-10, atol=1e-10), _report("diag L", L, Lref)
+    assert np.all(np.triu(L, 1) == 0) and np.all(np.triu(Li, 1) == 0)
+    assert np.allclose(Li @ Lref, np.eye(128), atol=1e-8), _report("Linv*L", Li @ Lref, np.eye(128))
+    assert abs(ld - np.log(np.diag(Lref)).sum()) < 1e-10 * abs(ld)
+
+
+def test_diag_block_flags_first_bad_pivot(eng):
+    A = _spd128(2)
+    A[70, 70] = -3.0
+    _, _, _, info = eng.dbg_diag(A)
+    assert info == 71
+
+
+def test_cov_matrices_against_reference_vectors(eng, golden):
+    from pygps_b200 import _lib
+    g = golden("cov_vectors")
+    x, z = g["x"], g["z"]
+    kinds = {"rbf": (_lib.COV_RBF, 3), "ard": (_lib.COV_RBFARD, 3), "mat1": (_lib.COV_MATERN, 1),
+             "mat3": (_lib.COV_MATERN, 3), "mat5": (_lib.COV_MATERN, 5), "mat7": (_lib.COV_MATERN, 7)}
+    for name, (kind, d) in kinds.items():
+        hyp = g[name + "_hyp"]
+        for mode, key, args in (("train", "_train", (x, None)), ("cross", "_cross", (x, z)), ("self_test", "_self", (None, z))):
+            got = eng.cov_matrix(kind, d, hyp, args[0], args[1], mode)
+            ref = g[name + key]
+            assert got.shape == ref.shape
+            assert np.allclose(got, ref, rtol=1e-12, atol=1e-14), _report(name + key, got, ref)
+        K = eng.cov_matrix(kind, d, hyp, x, None, "train")
+        assert np.array_equal(K, K.T), "train matrix must be bit-symmetric like cdist's"
+        assert np.all(np.diag(K) == np.exp(2 * hyp[-1] if kind != _lib.COV_RBFARD else 2 * hyp[-1]))
+    for name in ("rbf", "ard"):
+        kind, d = kinds[name]
+        hyp = g[name + "_hyp"]
+        for i in range(len(hyp)):
+            got = eng.cov_matrix(kind, d, hyp, x, None, "train", i)
+            assert np.allclose(got, g["%s_dtrain%d" % (name, i)], rtol=1e-12, atol=1e-14), _report("d%s%d" % (name, i), got, g["%s_dtrain%d" % (name, i)])
+            got = eng.cov_matrix(kind, d, hyp, x, z, "cross", i)
+            assert np.allclose(got, g["%s_dcross%d" % (name, i)], rtol=1e-12, atol=1e-14)
+
+
+def test_cov_matrix_ragged_sizes(eng):
+    from pygps_b200 import _lib
+    from oracle import gp_oracle as go
+    rng = np.random.default_rng(3)
+    for n, m, D in ((1, 1, 1), (65, 130, 5), (200, 63, 17), (129, 1, 33)):
+        x = rng.standard_normal((n, D)); z = rng.standard_normal((m, D))
+        hyp = [0.3, -0.2]
+        got = eng.cov_matrix(_lib.COV_RBF, 3, hyp, x, z, "cross")
+        ref = go.cov_matrix(("rbf", hyp), x=x, z=z, mode="cross")
+        assert np.allclose(got, ref, rtol=1e-12, atol=1e-15), _report("ragged %s" % ((n, m, D),), got, ref)
+
+
+@pytest.mark.parametrize("n", [20, 128, 300, 1000])
+def test_potrf_potrs_match_lapack(eng, n):
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((n, 4))
+    d = ((X[:, None] - X[None]) ** 2).sum(-1)
+    A = np.exp(-0.5 * d / 4.0) / 0.01 + np.eye(n)
+    R, ld = eng.potrf(A)
+    Rref = np.linalg.cholesky(A).T
+    assert np.all(np.tril(R, -1) == 0), "strict lower triangle of the upper factor must be exactly zero"
+    assert np.allclose(R, Rref, rtol=1e-9, atol=1e-9), _report("potrf n=%d" % n, R, Rref)
+    assert abs(ld - np.log(np.diag(Rref)).sum()) < 1e-10 * max(1.0, abs(ld))
+    B = rng.standard_normal((n, 3))
+    Xs = eng.potrs(B)
+    ref = sla.cho_solve((Rref, False), B)
+    assert np.allclose(Xs, ref, rtol=1e-7, atol=1e-9), _report("potrs n=%d" % n, Xs, ref)
+
+
+def test_potrf_not_positive_definite_raises(eng):
+    A = np.eye(200)
+    A[150, 150] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.potrf(A)
+    A = np.ones((140, 140)) + 1e-3 * np.eye(140)      # PD diagonal, indefinite after elimination? no: rank-1 + eps, PD
+    A[100, 130] = A[130, 100] = 5.0                   # breaks positive definiteness with positive diagonal
+    with pytest.raises(np.linalg.LinAlgError) as ei:
+        eng.potrf(A)
+    assert "even with jitter" in str(ei.value)
+
+
+def test_tools_jitchol_solve_chol_drop_in(eng, golden):
+    import pygps_b200 as pg
+    g = golden("cov_vectors")
+    L = pg.tools.jitchol(g["chol_A"])
+    assert np.allclose(L, g["chol_L"], rtol=1e-11, atol=1e-12)
+    X = pg.tools.solve_chol(L.T, g["chol_B"])
+    assert np.allclose(X, g["chol_X"], rtol=1e-8, atol=1e-10)
+    X2 = pg.tools.solve_chol(np.array(L.T), g["chol_B"])          # factor not resident: still correct
+    assert np.allclose(X2, g["chol_X"], rtol=1e-8, atol=1e-10)
+    with pytest.raises(Exception):
+        pg.tools.solve_chol(L.T, np.zeros((3, 1)))

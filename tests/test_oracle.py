@@ -1,0 +1,157 @@
+"""The CPU oracle (oracle/gp_oracle.py) pinned against outputs of the UNMODIFIED reference
+frozen in tests/golden/*.npz by oracle/gen_golden.py.  No GPU needed."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as go
+
+RT = 1e-11
+
+
+def close(a, b, rtol=RT, atol=1e-12):
+    np.testing.assert_allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float), rtol=rtol, atol=atol)
+
+
+def test_cov_matrices_all_modes(golden):
+    g = golden("cov_vectors")
+    x, z = g["x"], g["z"]
+    specs = {"rbf": ("rbf", list(g["rbf_hyp"])), "ard": ("rbfard", list(g["ard_hyp"]))}
+    for d in (1, 3, 5, 7):
+        specs["mat%d" % d] = ("matern", list(g["mat%d_hyp" % d]), d)
+    for name, cov in specs.items():
+        close(go.cov_matrix(cov, x=x, mode="train"), g[name + "_train"])
+        close(go.cov_matrix(cov, x=x, z=z, mode="cross"), g[name + "_cross"])
+        close(go.cov_matrix(cov, z=z, mode="self_test"), g[name + "_self"])
+    for name in ("rbf", "ard"):
+        cov = specs[name]
+        for i in range(len(cov[1])):
+            close(go.cov_der_matrix(cov, x=x, mode="train", der=i), g["%s_dtrain%d" % (name, i)])
+            close(go.cov_der_matrix(cov, x=x, z=z, mode="cross", der=i), g["%s_dcross%d" % (name, i)])
+    dk, kuu, ku = go.fitc_cov_matrix(specs["rbf"], g["u"], x=x, mode="train")
+    close(dk, g["fitc_diag"]); close(kuu, g["fitc_kuu"]); close(ku, g["fitc_ku"])
+    close(go.fitc_cov_matrix(specs["rbf"], g["u"], x=x, z=z, mode="cross"), g["fitc_cross"])
+
+
+def test_matern_derivative_is_the_true_gradient(golden):
+    """The reference's Matern.getDerMatrix is wrong; ours is checked by finite differences."""
+    g = golden("cov_vectors")
+    x = g["x"]
+    for d in (1, 3, 5, 7):
+        hyp = list(g["mat%d_hyp" % d])
+        for i in range(2):
+            hp, hm = list(hyp), list(hyp)
+            hp[i] += 1e-6; hm[i] -= 1e-6
+            fd = (go.cov_matrix(("matern", hp, d), x=x, mode="train")
+                  - go.cov_matrix(("matern", hm, d), x=x, mode="train")) / 2e-6
+            np.testing.assert_allclose(go.cov_der_matrix(("matern", hyp, d), x=x, mode="train", der=i), fd,
+                                       rtol=1e-5, atol=1e-8)
+
+
+def test_jitchol_solve_chol(golden):
+    g = golden("cov_vectors")
+    L = go.jitchol(g["chol_A"])
+    close(L, g["chol_L"])
+    close(go.solve_chol(L.T, g["chol_B"]), g["chol_X"], rtol=1e-9)
+    bad = g["chol_A"].copy()
+    bad[3, 3] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        go.jitchol(bad)
+    with pytest.raises(Exception):
+        go.solve_chol(L.T, np.zeros((3, 1)))
+
+
+def _check_exact(g, tag, mean, cov, log_sn, x, y, xs, ys=None, der=True):
+    post, nlZ, dn = go.exact_evaluate(mean, cov, log_sn, x, y, 3)
+    close(nlZ, g[tag + "_nlZ"])
+    close(post["alpha"], g[tag + "_alpha"], rtol=1e-8)
+    close(post["sW"][0, 0], g[tag + "_sW0"])
+    if tag + "_L" in g.files:
+        close(post["L"], g[tag + "_L"], rtol=1e-9)
+    if der:
+        close(dn["cov"], g[tag + "_dcov"], rtol=1e-7)
+        close(dn["lik"], g[tag + "_dlik"], rtol=1e-7)
+        close(dn["mean"], g[tag + "_dmean"], rtol=1e-7)
+    out = go.predict(mean, cov, log_sn, x, post, xs, ys)
+    for name, v in zip(("ym", "ys2", "fm", "fs2"), out[:4]):
+        close(v, g[tag + "_" + name], rtol=1e-7, atol=1e-10)
+    if ys is not None:
+        close(out[4], g[tag + "_lp"], rtol=1e-7)
+
+
+def test_exact_kats_on_reference_fixture(golden):
+    g = golden("kat_regression")
+    x, y, xs = g["x"], g["y"], g["xs"]
+    _check_exact(g, "kat1", ("zero",), ("rbf", [0., 0.]), np.log(0.1), x, y, xs, ys=g["ys"])
+    assert abs(float(g["kat1_nlZ"]) - 154.068967070743) < 1e-9
+    _check_exact(g, "kat2", ("const", float(g["kat2_c"])), ("rbf", [0., 0.]), np.log(0.1), x, y, xs)
+    _check_exact(g, "kat3_ard", ("zero",), ("rbfard", [0.3, 0.2]), np.log(0.1), x, y, xs)
+    _check_exact(g, "kat3_lin", ("linear", [0.5]), ("rbf", [-0.5, 0.1]), np.log(0.2), x, y, xs)
+    for d in (1, 3, 5, 7):
+        post, nlZ = go.exact_evaluate(("zero",), ("matern", [0.3, 0.2], d), np.log(0.1), x, y, 2)
+        close(nlZ, g["kat3_mat%d_nlZ" % d])
+        close(post["alpha"], g["kat3_mat%d_alpha" % d], rtol=1e-8)
+        out = go.predict(("zero",), ("matern", [0.3, 0.2], d), np.log(0.1), x, post, xs)
+        close(out[0], g["kat3_mat%d_ym" % d], rtol=1e-7)
+        close(out[1], g["kat3_mat%d_ys2" % d], rtol=1e-7)
+
+
+def test_fitc_kats(golden):
+    g = golden("kat_regression")
+    x, y, xs = g["x"], g["y"], g["xs"]
+    for tag, mean, u in (("kat4", ("zero",), g["u"]), ("kat4b", ("const", float(g["kat4b_c"])), g["kat4b_u"])):
+        cov = ("rbf", [0., 0.])
+        post, nlZ, dn = go.fitc_evaluate(mean, cov, u, np.log(0.1), x, y, 3)
+        close(nlZ, g[tag + "_nlZ"], rtol=1e-9)
+        close(post["alpha"], g[tag + "_alpha"], rtol=1e-6)
+        close(post["L"], g[tag + "_L"], rtol=1e-5, atol=1e-6)
+        close(dn["cov"], g[tag + "_dcov"], rtol=1e-6)
+        close(dn["lik"], g[tag + "_dlik"], rtol=1e-6)
+        close(dn["mean"], g[tag + "_dmean"], rtol=1e-6)
+        out = go.predict(mean, cov, np.log(0.1), x, post, xs, xu=u)
+        close(out[0], g[tag + "_ym"], rtol=1e-6)
+        close(out[1], g[tag + "_ys2"], rtol=1e-6)
+    assert abs(float(g["kat4_nlZ"]) - 179.399011418159) < 1e-8
+
+
+def test_synthetic_baseline_configs(golden):
+    g = golden("synthetic")
+    for N in (256, 1000):
+        X, y = go.synth_regression(N, 8)
+        Xs = np.random.default_rng(1).standard_normal((300, 8))
+        _check_exact(g, "c2_%d" % N, ("zero",), ("rbf", [np.log(2.0), 0.0]), np.log(0.1), X, y, Xs)
+    X, y = go.synth_regression(2048, 8)
+    assert abs(go.exact_evaluate_fair(("rbf", [np.log(2.0), 0.0]), np.log(0.1), X, y) - float(g["c2_2048_nlZ"])) \
+        < 1e-7 * abs(float(g["c2_2048_nlZ"]))
+    _check_exact(g, "c1", ("const", float(g["c1_c"])), ("rbf", [0., 0.]), np.log(0.1), g["c1_x"], g["c1_y"],
+                 g["c1_x"][:50] + 0.1)
+    assert abs(float(g["c1_nlZ"]) - (-379.2688218267)) < 1e-8
+    X, y = go.synth_regression(1024, 32)
+    Xs = np.random.default_rng(1).standard_normal((200, 32))
+    _check_exact(g, "c3_1024", ("zero",), ("rbfard", [np.log(3.0)] * 32 + [0.0]), np.log(0.1), X, y, Xs)
+
+
+def test_fitc_synthetic(golden):
+    g = golden("synthetic")
+    N, M = 2000, 100
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((N, 8))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    U = rng.standard_normal((M, 8))
+    post, nlZ, dn = go.fitc_evaluate(("zero",), ("rbf", [np.log(2.0), 0.0]), U, np.log(0.1), X, y, 3)
+    tag = "c4_%d_%d" % (N, M)
+    close(nlZ, g[tag + "_nlZ"], rtol=1e-9)
+    close(dn["cov"], g[tag + "_dcov"], rtol=1e-5)
+    close(dn["lik"], g[tag + "_dlik"], rtol=1e-5)
+
+
+def test_housing_published_value(golden):
+    """doc/source/demoHousing.rst:30 publishes the optimised nlZ 214.46; the frozen run reproduces it."""
+    g = golden("housing")
+    assert abs(float(g["opt_nlZ"]) - 214.46) < 5e-3
+    post, nlZ, dn = go.exact_evaluate(("zero",), ("rbf", [0., 0.]), np.log(0.1), g["x"], g["y"], 3)
+    close(nlZ, g["default_nlZ"])
+    close(dn["cov"], g["default_dcov"], rtol=1e-7)
+    close(dn["lik"], g["default_dlik"], rtol=1e-7)
+    h = g["opt_hyp"]
+    _, nlZo = go.exact_evaluate(("zero",), ("rbf", [h[0], h[1]]), h[2], g["x"], g["y"], 2)
+    close(nlZo, g["opt_nlZ"], rtol=1e-9)
