@@ -148,7 +148,8 @@ int gpk_bench_copy(gpk_handle h, int64_t bytes, int reps, double* gbs);
 /* debug: C(M,N) = beta*C + alpha*A(M,K)*B(N,K)' with column-major host arrays,
  * through the production tile kernel.  mode 0: C=A*B' ; 1: C-=A*B' full;
  * 2: C-=A*B' lower tiles only (M==N); 3: C=A*B' lower tiles, contraction from
- * k = 128*tile_row (upper-triangular operands).  M,N multiples of 128, K of 16. */
+ * k = 128*tile_row (upper-triangular operands); 4: A <- A*B' in place (N==K), the
+ * panel-TRSM form.  M,N multiples of 128, K of 32.                              */
 int gpk_dbg_gemm_nt(gpk_handle h, int mode, int64_t M, int64_t N, int64_t K,
                     const double* A, const double* B, double* C);
 /* debug: factor + invert one 128x128 block (column-major): L and inv(L). */

@@ -126,7 +126,6 @@ class Engine(object):
                            % (device, self._lib.gpk_strerror(rc).decode()))
         self._h = h
         self.epoch = 0              # bumped whenever the resident factor changes
-        self._live_posts = weakref.WeakSet()   # postStructs whose lazy L points at this handle
         self._finalizer = weakref.finalize(self, self._lib.gpk_destroy, h)
 
     # -- helpers ------------------------------------------------------------
@@ -150,12 +149,8 @@ class Engine(object):
         self._lib.gpk_set_profile(self._h, int(bool(on)))
 
     def _retire_factor(self):
-        """Called before the resident factor is overwritten: a posterior that still
-        holds a lazy reference to it gets its L materialised first."""
-        live = list(self._live_posts)
-        self._live_posts = weakref.WeakSet()
-        for post in live:
-            post._materialize()
+        """Called before the resident factor is overwritten.  Posteriors that still point at it
+        notice through the epoch and rebuild their factor on demand (inf.postStruct._materialize)."""
         self.epoch += 1
 
     # -- covariance -----------------------------------------------------------

@@ -1,6 +1,7 @@
 // api.cu - the extern "C" surface of libgpk.so (include/gpk.h) and the host-side
 // orchestration of the blocked right-looking Cholesky with one-panel look-ahead.
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include "gpk_internal.cuh"
 
@@ -34,67 +35,102 @@ static int ensure_prof_events(Handle* h, size_t count) {
 }
 
 // ---------------------------------------------------------------------------
-// Blocked right-looking Cholesky, in place on the lower triangle of A (np x np,
-// column-major, np a multiple of NB).  Two streams:
-//   s_panel (high priority): diag(k) -> trsm(k) [-> forward-solve step k]
-//   s_main                 : syrk on block column k+1 (so panel k+1 can start)
-//                            -> syrk on the rest of the trailing matrix
-// Panel k+1 therefore overlaps the bulk of trailing update k (look-ahead 1).
+// Blocked right-looking Cholesky, in place on the lower triangle of A (np x np, column-major, np a multiple
+// of NB), two-level: an OUTER block of W panels (W*128 columns) is factored panel by panel on the
+// high-priority stream, then the trailing matrix gets ONE update with contraction length W*128 (fewer
+// passes over the trailing matrix than W separate rank-128 updates).  Streams:
+//   s_panel (high priority): for each panel p of the block: diag(p) -> trsm(p) -> rank-128 update of the
+//                            remaining columns of the block
+//   s_main                 : rank-(W*128) update of the next block's columns (so its panels can start)
+//                            -> update of the rest of the trailing matrix
+//   s_aux                  : single-right-hand-side forward substitution step p, off the critical path
+// Outer block j+1 therefore overlaps the bulk of trailing update j (look-ahead 1).
 // ---------------------------------------------------------------------------
+static int g_potrf_w = 2;
+
 int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info, double* b_fwd,
                  double* z_out) {
   const int T = (int)(np / NB);
   const int64_t lda = np;
+  if (const char* e = getenv("GPK_POTRF_W")) { g_potrf_w = atoi(e); }
+  const int W = (g_potrf_w < 1) ? 1 : (g_potrf_w > 8 ? 8 : g_potrf_w);
+  const int nblk = (T + W - 1) / W;
   GPK_TRY(ensure_events(h, 2 * (size_t)T + 4));
   if (h->profile) GPK_TRY(ensure_prof_events(h, 2 * (size_t)T + 2));
-  cudaEvent_t* ev_panel = h->ev.data();      // [T]
-  cudaEvent_t* ev_col = h->ev.data() + T;    // [T]
-  cudaEvent_t ev_fork = h->ev[2 * T], ev_join = h->ev[2 * T + 1];
+  cudaEvent_t* ev_panel = h->ev.data();      // [T]   panel p factored and solved
+  cudaEvent_t* ev_col = h->ev.data() + T;    // [T]   columns of outer block j up to date
+  cudaEvent_t ev_fork = h->ev[2 * T], ev_join = h->ev[2 * T + 1], ev_aux = h->ev[2 * T + 2];
   h->stats.syrk_flops = 0.0;
+  h->prof_pairs = 0;
 
   GPK_CK(h, cudaEventRecord(ev_fork, h->s_main));
   GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_fork, 0));
-  for (int k = 0; k < T; ++k) {
-    double* Akk = A + (int64_t)k * NB * (1 + lda);
-    double* Dk = Dinv + (int64_t)k * NB * NB;
-    const int rem = T - k - 1;
-    if (k > 0) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_col[k], 0));
-    GPK_TRY(launch_diag(h, h->s_panel, Akk, lda, Dk, logdet_parts + k, info, k * NB));
-    if (rem > 0) {
-      GemmArgs t{};
-      t.A = Akk + NB; t.B = Dk; t.C = Akk + NB;
-      t.lda = lda; t.ldb = NB; t.ldc = lda; t.K = NB; t.tri = 0;
-      GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, rem, 1));
-    }
-    if (b_fwd) GPK_TRY(launch_trsv_fwd(h, h->s_panel, A, lda, Dinv, b_fwd, z_out, k, T));
-    if (rem > 0) {
-      GPK_CK(h, cudaEventRecord(ev_panel[k], h->s_panel));
-      GPK_CK(h, cudaStreamWaitEvent(h->s_main, ev_panel[k], 0));
-      if (h->profile) GPK_CK(h, cudaEventRecord(h->prof_ev[2 * k], h->s_main));
-      GemmArgs u{};
-      u.A = Akk + NB; u.B = Akk + NB; u.C = A + (int64_t)(k + 1) * NB * (1 + lda);
-      u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = NB; u.tri = 1; u.ti_off = 0; u.tj_off = 0;
-      GPK_TRY(launch_gemm_nt(h, h->s_main, 1, u, rem, 1));
-      GPK_CK(h, cudaEventRecord(ev_col[k + 1], h->s_main));
-      if (rem > 1) {
-        GemmArgs v = u;
-        v.B = u.B + NB; v.C = u.C + (int64_t)NB * lda; v.tj_off = 1;
-        GPK_TRY(launch_gemm_nt(h, h->s_main, 1, v, rem, rem - 1));
+  if (b_fwd) GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_fork, 0));
+  for (int j = 0; j < nblk; ++j) {
+    const int pb = j * W;                              // first panel of the block
+    const int pe = (pb + W < T) ? pb + W : T;          // one past its last panel
+    if (j > 0) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_col[j], 0));
+    for (int p = pb; p < pe; ++p) {
+      double* App = A + (int64_t)p * NB * (1 + lda);
+      double* Dp = Dinv + (int64_t)p * NB * NB;
+      const int rem = T - p - 1;                       // tile rows below panel p
+      GPK_TRY(launch_diag(h, h->s_panel, App, lda, Dp, logdet_parts + p, info, p * NB));
+      if (rem > 0) {
+        GemmArgs t{};
+        t.A = App + NB; t.B = Dp; t.C = App + NB;
+        t.lda = lda; t.ldb = NB; t.ldc = lda; t.K = NB; t.tri = 0;
+        GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, rem, 1));
       }
-      if (h->profile) GPK_CK(h, cudaEventRecord(h->prof_ev[2 * k + 1], h->s_main));
+      GPK_CK(h, cudaEventRecord(ev_panel[p], h->s_panel));
+      if (b_fwd) {
+        GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_panel[p], 0));
+        GPK_TRY(launch_trsv_fwd(h, h->s_aux, A, lda, Dinv, b_fwd, z_out, p, T));
+      }
+      const int inner = pe - p - 1;                    // remaining columns of this block
+      if (inner > 0) {
+        GemmArgs u{};
+        u.A = App + NB; u.B = App + NB; u.C = A + (int64_t)(p + 1) * NB * (1 + lda);
+        u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = NB; u.tri = 1;
+        GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, u, rem, inner));
+      }
+    }
+    const int rem = T - pe;                            // trailing tiles after the block
+    if (rem > 0) {
+      GPK_CK(h, cudaEventRecord(ev_join, h->s_panel));
+      GPK_CK(h, cudaStreamWaitEvent(h->s_main, ev_join, 0));
+      if (h->profile) GPK_CK(h, cudaEventRecord(h->prof_ev[2 * h->prof_pairs], h->s_main));
+      const int kw = (pe - pb) * NB;
+      const int first = (W < rem) ? W : rem;           // the next block's columns go first
+      GemmArgs u{};
+      u.A = A + (int64_t)pe * NB + (int64_t)pb * NB * lda; u.B = u.A;
+      u.C = A + (int64_t)pe * NB * (1 + lda);
+      u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = kw; u.tri = 1; u.ti_off = 0; u.tj_off = 0;
+      GPK_TRY(launch_gemm_nt(h, h->s_main, 1, u, rem, first));
+      GPK_CK(h, cudaEventRecord(ev_col[j + 1], h->s_main));
+      if (rem > first) {
+        GemmArgs v = u;
+        v.B = u.B + (int64_t)first * NB; v.C = u.C + (int64_t)first * NB * lda; v.tj_off = first;
+        GPK_TRY(launch_gemm_nt(h, h->s_main, 1, v, rem, rem - first));
+      }
+      if (h->profile) { GPK_CK(h, cudaEventRecord(h->prof_ev[2 * h->prof_pairs + 1], h->s_main)); h->prof_pairs++; }
       const double nt = (double)rem * NB;
-      h->stats.syrk_flops += (double)NB * nt * nt;
+      h->stats.syrk_flops += (double)kw * nt * nt;
     }
   }
   GPK_CK(h, cudaEventRecord(ev_join, h->s_panel));
   GPK_CK(h, cudaStreamWaitEvent(h->s_main, ev_join, 0));
+  if (b_fwd) {
+    GPK_CK(h, cudaEventRecord(ev_aux, h->s_aux));
+    GPK_CK(h, cudaStreamWaitEvent(h->s_main, ev_aux, 0));
+  }
   return 0;
 }
 
 static int collect_profile(Handle* h, int T) {
   h->stats.syrk_ms = 0.0;
+  (void)T;
   if (!h->profile) return 0;
-  for (int k = 0; k + 1 < T; ++k) {
+  for (int k = 0; k < h->prof_pairs; ++k) {
     float ms = 0.f;
     GPK_CK(h, cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]));
     h->stats.syrk_ms += ms;
@@ -265,6 +301,8 @@ int gpk_create(int device, gpk_handle* out) {
   auto fail = [&](int rc) { delete h; return rc; };
   if (cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) != cudaSuccess) return fail(GPK_ERR_CUDA);
   if (cudaStreamCreateWithPriority(&h->s_panel, cudaStreamNonBlocking, hi) != cudaSuccess) return fail(GPK_ERR_CUDA);
+  if (cudaStreamCreateWithPriority(&h->s_aux, cudaStreamNonBlocking, (hi < lo) ? hi + 1 : lo) != cudaSuccess)
+    return fail(GPK_ERR_CUDA);
   cudaEvent_t* te[] = {&h->t0, &h->t1, &h->t2, &h->t3, &h->t4};
   for (auto e : te)
     if (cudaEventCreate(e) != cudaSuccess) return fail(GPK_ERR_CUDA);
@@ -290,6 +328,7 @@ int gpk_destroy(gpk_handle hh) {
   if (h->hPinned) cudaFreeHost(h->hPinned);
   if (h->s_main) cudaStreamDestroy(h->s_main);
   if (h->s_panel) cudaStreamDestroy(h->s_panel);
+  if (h->s_aux) cudaStreamDestroy(h->s_aux);
   delete h;
   return 0;
 }
@@ -670,7 +709,7 @@ int gpk_bench_dmma(gpk_handle hh, int shape, int warps_per_cta, int iters, doubl
 int gpk_bench_syrk(gpk_handle hh, int64_t n, int k, int reps, double* ms_out, double* tflops) {
   Handle* h;
   GPK_TRY(check_handle(hh, &h));
-  if (n <= 0 || n % NB != 0 || k <= 0 || k % GEMM_BK != 0 || reps <= 0 || !ms_out || !tflops) return GPK_ERR_ARG;
+  if (n <= 0 || n % NB != 0 || k <= 0 || k % 32 != 0 || reps <= 0 || !ms_out || !tflops) return GPK_ERR_ARG;
   cudaStream_t st = h->s_main;
   double *C = nullptr, *P = nullptr;
   GPK_CK(h, cudaMalloc((void**)&C, (size_t)n * n * sizeof(double)));
@@ -737,8 +776,9 @@ int gpk_dbg_gemm_nt(gpk_handle hh, int mode, int64_t M, int64_t N, int64_t K, co
                     double* C) {
   Handle* h;
   GPK_TRY(check_handle(hh, &h));
-  if (!A || !B || !C || M % NB || N % NB || K % GEMM_BK || mode < 0 || mode > 3) return GPK_ERR_ARG;
-  if ((mode >= 2) && M != N) return GPK_ERR_ARG;
+  if (!A || !B || !C || M % NB || N % NB || K % 32 || mode < 0 || mode > 4) return GPK_ERR_ARG;
+  if ((mode == 2 || mode == 3) && M != N) return GPK_ERR_ARG;
+  if (mode == 4 && N != K) return GPK_ERR_ARG;
   cudaStream_t st = h->s_main;
   double *dA = nullptr, *dB = nullptr, *dC = nullptr;
   GPK_CK(h, cudaMalloc((void**)&dA, (size_t)M * K * 8));
@@ -750,8 +790,9 @@ int gpk_dbg_gemm_nt(gpk_handle hh, int mode, int64_t M, int64_t N, int64_t K, co
   GemmArgs u{};
   u.A = dA; u.B = dB; u.C = dC; u.lda = M; u.ldb = N; u.ldc = M; u.K = (int)K;
   u.tri = (mode == 2) ? 1 : (mode == 3 ? 2 : 0);
-  int rc = launch_gemm_nt(h, st, (mode == 0 || mode == 3) ? 0 : 1, u, (int)(M / NB), (int)(N / NB));
-  cudaMemcpyAsync(C, dC, (size_t)M * N * 8, cudaMemcpyDeviceToHost, st);
+  if (mode == 4) u.C = dA;   // in place over A, as the panel TRSM runs
+  int rc = launch_gemm_nt(h, st, (mode == 0 || mode >= 3) ? 0 : 1, u, (int)(M / NB), (int)(N / NB));
+  cudaMemcpyAsync(C, (mode == 4) ? dA : dC, (size_t)M * N * 8, cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(dA); cudaFree(dB); cudaFree(dC);
   if (rc != 0) return rc;
@@ -768,11 +809,20 @@ int gpk_dbg_diag(gpk_handle hh, const double* A128, double* L128, double* Linv12
   int* dInfo = nullptr;
   GPK_CK(h, cudaMalloc((void**)&dA, NB * NB * 8));
   GPK_CK(h, cudaMalloc((void**)&dI, NB * NB * 8));
-  GPK_CK(h, cudaMalloc((void**)&dS, 64));
+  GPK_CK(h, cudaMalloc((void**)&dS, 64 * 8));
   GPK_CK(h, cudaMalloc((void**)&dInfo, 16));
   cudaMemcpyAsync(dA, A128, NB * NB * 8, cudaMemcpyHostToDevice, st);
   cudaMemsetAsync(dInfo, 0, 16, st);
-  int rc = launch_diag(h, st, dA, NB, dI, dS, dInfo, 0);
+  cudaMemsetAsync(dS, 0, 64 * 8, st);
+  int rc = launch_diag(h, st, dA, NB, dI, dS, dInfo, 0, reinterpret_cast<long long*>(dS + 8));
+  if (getenv("GPK_DBG_DIAG_CLK")) {
+    long long clk[32] = {0};
+    cudaStreamSynchronize(st);
+    cudaMemcpy(clk, dS + 8, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "diag clk deltas:");
+    for (int i = 1; i < 32 && clk[i]; ++i) fprintf(stderr, " %lld", clk[i] - clk[i - 1]);
+    fprintf(stderr, "  total %lld\n", clk[0] ? 0LL : 0LL);
+  }
   cudaMemcpyAsync(L128, dA, NB * NB * 8, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(Linv128, dI, NB * NB * 8, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(logdet_half, dS, 8, cudaMemcpyDeviceToHost, st);

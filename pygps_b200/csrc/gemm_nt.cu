@@ -13,8 +13,10 @@
 // global one (column-major slabs of BK=16 columns) with a pitch of 132 doubles,
 // which makes every A/B fragment load bank-conflict free (pitch == 4 mod 16).
 //
-// Tile: 128x128 per CTA, 8 warps as 4(M) x 2(N), warp tile 32x64 = 2x8 MMA
-// tiles, 64 fp64 accumulators (128 registers) per thread, one CTA per SM.
+// Tile: 128x64 per CTA (default), 8 warps as 4(M) x 2(N), warp tile 32x32 = 2x4
+// MMA tiles, 32 fp64 accumulators per thread, two CTAs per SM; a 128x128 /
+// one-CTA-per-SM variant is kept for comparison (GPK_GEMM_BN=128).
+#include <cstdlib>
 #include "gpk_internal.cuh"
 
 namespace gpk {
@@ -41,55 +43,74 @@ __device__ __forceinline__ void dmma_16x8x8(double (&c)[4], const double (&a)[4]
 
 // MODE 0: C = A*B^T          (C is not read)
 // MODE 1: C = C - A*B^T      (accumulators start at -C, result is negated on store)
-template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(const GemmArgs p) {
+// Variants (template parameters; picked at run time by GPK_GEMM_VARIANT for A/B measurements):
+//   BN   column width of the CTA tile (rows are always 128)
+//   WN   warps along N (4 along M): CTA = 128*WN threads, warp tile 32 x BN/WN
+//   BK   k-slab per pipeline stage, ST stages, MINB CTAs per SM the register budget is sized for
+template <int MODE, int BN, int WN, int BK, int ST, int MINB>
+__global__ void __launch_bounds__(128 * WN, MINB) dgemm_nt_kernel(const GemmArgs p) {
+  constexpr int THREADS = 128 * WN;
+  constexpr int WTN = BN / WN;           // warp tile width
+  constexpr int NT = WTN / 8;            // 8-wide MMA tiles per warp along N
+  constexpr int LDB = BN + 4;            // == 4 mod 16 for 64 and 128
+  constexpr int A_STAGE = BK * GEMM_LDS;
+  constexpr int B_STAGE = BK * LDB;
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
-  double* Bs = smem + GEMM_STAGES * GEMM_BK * GEMM_LDS;
+  double* Bs = smem + ST * A_STAGE;
 
-  const int ti = blockIdx.x, tj = blockIdx.y;
-  const int gi = ti + p.ti_off, gj = tj + p.tj_off;
-  if (p.tri && gi < gj) return;
-  const bool diag_tile = (p.tri != 0) && (gi == gj);
+  const int ti = blockIdx.x, tjs = blockIdx.y;          // tjs counts BN-wide column tiles
+  const int gi = ti + p.ti_off;
+  const int gcol0 = tjs * BN + p.tj_off * NB;           // first global column (relative to the tile grid origin)
+  const int grow0 = gi * NB;
+  if (p.tri && grow0 + NB - 1 < gcol0) return;          // tile entirely above the diagonal
+  const bool diag_tile = (p.tri != 0) && (gcol0 + BN - 1 > grow0);   // crosses the diagonal
+  const int dshift = gcol0 - grow0;                     // store (r,c) iff r >= c + dshift
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 3, wn = warp >> 2;
   const int g = lane >> 2, t = lane & 3;
 
   const double* __restrict__ Ag = p.A + (int64_t)ti * NB;
-  const double* __restrict__ Bg = p.B + (int64_t)tj * NB;
-  double* __restrict__ Cg = p.C + (int64_t)ti * NB + (int64_t)tj * NB * p.ldc;
+  const double* __restrict__ Bg = p.B + (int64_t)tjs * BN;
+  double* __restrict__ Cg = p.C + (int64_t)ti * NB + (int64_t)tjs * BN * p.ldc;
 
   const int kbeg = (p.tri == 2) ? gi * NB : 0;
-  const int nkt = (p.K - kbeg) / GEMM_BK;
+  const int nkt = (p.K - kbeg) / BK;
 
   auto load_stage = [&](int slot, int kt) {
-    const int k0 = kbeg + kt * GEMM_BK;
+    const int k0 = kbeg + kt * BK;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = tid + i * GEMM_THREADS;  // 0..1023 16-byte chunks per operand
-      const int col = c >> 6;                // 0..15
-      const int r = (c & 63) * 2;            // 0..126
-      cp_async16(As + (slot * GEMM_BK + col) * GEMM_LDS + r, Ag + r + (int64_t)(k0 + col) * p.lda);
-      cp_async16(Bs + (slot * GEMM_BK + col) * GEMM_LDS + r, Bg + r + (int64_t)(k0 + col) * p.ldb);
+    for (int i = 0; i < (BK * 64) / THREADS; ++i) {
+      const int c = tid + i * THREADS;       // BK*64 16-byte chunks of A (64 per column)
+      const int col = c >> 6;
+      const int r = (c & 63) * 2;
+      cp_async16(As + slot * A_STAGE + col * GEMM_LDS + r, Ag + r + (int64_t)(k0 + col) * p.lda);
+    }
+#pragma unroll
+    for (int i = 0; i < (BK * BN / 2) / THREADS; ++i) {
+      const int c = tid + i * THREADS;       // BN/2 chunks per column of B
+      const int col = c / (BN / 2);
+      const int r = (c % (BN / 2)) * 2;
+      cp_async16(Bs + slot * B_STAGE + col * LDB + r, Bg + r + (int64_t)(k0 + col) * p.ldb);
     }
   };
 
   // start the pipeline before touching C so the loads overlap
 #pragma unroll
-  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+  for (int s = 0; s < ST - 1; ++s) {
     if (s < nkt) load_stage(s, s);
     cp_async_commit();
   }
 
-  double acc[2][8][4];
+  double acc[2][NT][4];
   const int row_base = wm * 32 + g;
-  const int col_base = wn * 64 + 2 * t;
+  const int col_base = wn * WTN + 2 * t;
   if (MODE == 1) {
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 8; ++ni) {
+      for (int ni = 0; ni < NT; ++ni) {
         const int r = row_base + mi * 16, c = col_base + ni * 8;
         const double* cp = Cg + r + (int64_t)c * p.ldc;
         acc[mi][ni][0] = -cp[0];
@@ -101,23 +122,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(const GemmArg
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 8; ++ni)
+      for (int ni = 0; ni < NT; ++ni)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.0;
   }
 
   for (int kt = 0; kt < nkt; ++kt) {
-    cp_async_wait<GEMM_STAGES - 2>();
+    cp_async_wait<ST - 2>();
     __syncthreads();
     {
-      const int nk = kt + GEMM_STAGES - 1;
-      if (nk < nkt) load_stage(nk % GEMM_STAGES, nk);
+      const int nk = kt + ST - 1;
+      if (nk < nkt) load_stage(nk % ST, nk);
       cp_async_commit();
     }
-    const double* as = As + (kt % GEMM_STAGES) * GEMM_BK * GEMM_LDS;
-    const double* bs = Bs + (kt % GEMM_STAGES) * GEMM_BK * GEMM_LDS;
+    const double* as = As + (kt % ST) * A_STAGE;
+    const double* bs = Bs + (kt % ST) * B_STAGE;
 #pragma unroll
-    for (int kk = 0; kk < GEMM_BK / 8; ++kk) {
+    for (int kk = 0; kk < BK / 8; ++kk) {
       double a[2][4];
       const double* a_lo = as + (kk * 8 + t) * GEMM_LDS + wm * 32 + g;
       const double* a_hi = a_lo + 4 * GEMM_LDS;
@@ -128,10 +149,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(const GemmArg
         a[mi][2] = a_hi[mi * 16];
         a[mi][3] = a_hi[mi * 16 + 8];
       }
-      const double* b_lo = bs + (kk * 8 + t) * GEMM_LDS + wn * 64 + g;
-      const double* b_hi = b_lo + 4 * GEMM_LDS;
+      const double* b_lo = bs + (kk * 8 + t) * LDB + wn * WTN + g;
+      const double* b_hi = b_lo + 4 * LDB;
 #pragma unroll
-      for (int ni = 0; ni < 8; ++ni) {
+      for (int ni = 0; ni < NT; ++ni) {
         const double b0 = b_lo[ni * 8], b1 = b_hi[ni * 8];
         dmma_16x8x8(acc[0][ni], a[0], b0, b1);
         dmma_16x8x8(acc[1][ni], a[1], b0, b1);
@@ -145,7 +166,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(const GemmArg
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 8; ++ni) {
+    for (int ni = 0; ni < NT; ++ni) {
       const int r = row_base + mi * 16, c = col_base + ni * 8;
       double* cp = Cg + r + (int64_t)c * p.ldc;
       if (!diag_tile) {
@@ -154,28 +175,72 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(const GemmArg
         cp[8] = sgn * acc[mi][ni][2];
         cp[8 + p.ldc] = sgn * acc[mi][ni][3];
       } else {
-        if (r >= c) cp[0] = sgn * acc[mi][ni][0];
-        if (r >= c + 1) cp[p.ldc] = sgn * acc[mi][ni][1];
-        if (r + 8 >= c) cp[8] = sgn * acc[mi][ni][2];
-        if (r + 8 >= c + 1) cp[8 + p.ldc] = sgn * acc[mi][ni][3];
+        const int cc = c + dshift;
+        if (r >= cc) cp[0] = sgn * acc[mi][ni][0];
+        if (r >= cc + 1) cp[p.ldc] = sgn * acc[mi][ni][1];
+        if (r + 8 >= cc) cp[8] = sgn * acc[mi][ni][2];
+        if (r + 8 >= cc + 1) cp[8 + p.ldc] = sgn * acc[mi][ni][3];
       }
     }
 }
 
+template <int BN, int BK, int ST>
+constexpr size_t gemm_smem() {
+  return size_t(ST) * BK * (GEMM_LDS + BN + 4) * sizeof(double);
+}
+
+// variant table:      BN   WN  BK  ST  MINB
+#define GPK_V0 64, 2, 16, 4, 2      /* 128x64, 8 warps, two CTAs per SM (default)        */
+#define GPK_V1 128, 2, 16, 4, 1     /* 128x128, 8 warps, one CTA per SM (round-1 first cut) */
+#define GPK_V2 128, 4, 16, 4, 1     /* 128x128, 16 warps, one CTA per SM                  */
+#define GPK_V3 128, 4, 32, 3, 1     /* 128x128, 16 warps, 32-deep k-slabs, 3 stages       */
+#define GPK_V4 64, 2, 32, 2, 2      /* 128x64, 8 warps, two CTAs per SM, 32-deep k-slabs  */
+
+static int g_gemm_variant = 0;
+
+template <int BN, int WN, int BK, int ST, int MINB>
+static int variant_init(Handle* h) {
+  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<0, BN, WN, BK, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)gemm_smem<BN, BK, ST>()));
+  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<1, BN, WN, BK, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)gemm_smem<BN, BK, ST>()));
+  return 0;
+}
+
+template <int BN, int WN, int BK, int ST, int MINB>
+static void variant_launch(cudaStream_t st, int mode, const GemmArgs& a, int tiles_m, int tiles_n) {
+  dim3 grid((unsigned)tiles_m, (unsigned)(tiles_n * (NB / BN)));
+  if (mode == 0)
+    dgemm_nt_kernel<0, BN, WN, BK, ST, MINB><<<grid, 128 * WN, gemm_smem<BN, BK, ST>(), st>>>(a);
+  else
+    dgemm_nt_kernel<1, BN, WN, BK, ST, MINB><<<grid, 128 * WN, gemm_smem<BN, BK, ST>(), st>>>(a);
+}
+
 int gemm_init(Handle* h) {
-  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  if (const char* e = getenv("GPK_GEMM_VARIANT")) g_gemm_variant = atoi(e);
+  if (g_gemm_variant < 0 || g_gemm_variant > 4) g_gemm_variant = 0;
+  GPK_TRY((variant_init<GPK_V0>(h)));
+  GPK_TRY((variant_init<GPK_V1>(h)));
+  GPK_TRY((variant_init<GPK_V2>(h)));
+  GPK_TRY((variant_init<GPK_V3>(h)));
+  GPK_TRY((variant_init<GPK_V4>(h)));
   return 0;
 }
 
 int launch_gemm_nt(Handle* h, cudaStream_t st, int mode, const GemmArgs& a, int tiles_m, int tiles_n) {
   if (tiles_m <= 0 || tiles_n <= 0) return 0;
-  if (a.K % GEMM_BK != 0 || tiles_n > 65535) return GPK_ERR_ARG;
-  dim3 grid((unsigned)tiles_m, (unsigned)tiles_n);
-  if (mode == 0)
-    dgemm_nt_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
-  else
-    dgemm_nt_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+  if (a.K % 32 != 0 || tiles_n > 32000) return GPK_ERR_ARG;
+  // In-place products (C overwrites A: the panel TRSM and the first step of the multi-right-hand-side sweeps)
+  // are only safe when ONE CTA owns a whole 128-row tile of A: it finishes reading the tile before its
+  // epilogue writes it.  Column-split tiles (BN=64) would let a sibling CTA overwrite columns still being read.
+  const bool inplace = (static_cast<const double*>(a.C) == a.A);
+  switch (inplace ? 1 : g_gemm_variant) {
+    case 1: variant_launch<GPK_V1>(st, mode, a, tiles_m, tiles_n); break;
+    case 2: variant_launch<GPK_V2>(st, mode, a, tiles_m, tiles_n); break;
+    case 3: variant_launch<GPK_V3>(st, mode, a, tiles_m, tiles_n); break;
+    case 4: variant_launch<GPK_V4>(st, mode, a, tiles_m, tiles_n); break;
+    default: variant_launch<GPK_V0>(st, mode, a, tiles_m, tiles_n); break;
+  }
   h->stats.launches++;
   GPK_CK(h, cudaGetLastError());
   return 0;

@@ -15,16 +15,13 @@
 namespace gpk {
 
 constexpr int NB = 128;          // tile edge == panel width of the blocked Cholesky
-constexpr int GEMM_BK = 16;      // k-slab per pipeline stage
 constexpr int GEMM_LDS = NB + 4; // smem column pitch (doubles); == 4 mod 16 -> conflict-free DMMA fragment loads
-constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 256;
-constexpr size_t GEMM_SMEM = size_t(2) * GEMM_STAGES * GEMM_BK * GEMM_LDS * sizeof(double);
 
 constexpr int DIAG_THREADS = 256;
 constexpr int DIAG_IB = 32;
-constexpr int DIAG_LDT = DIAG_IB + 1;
-constexpr size_t DIAG_SMEM = (size_t(NB) * NB + 4 * DIAG_IB * DIAG_LDT) * sizeof(double);
+constexpr int DIAG_LDS = NB + 4;
+constexpr int DIAG_LDT = DIAG_IB + 4;
+constexpr size_t DIAG_SMEM = (size_t(NB) * DIAG_LDS + 4 * DIAG_IB * DIAG_LDT + NB) * sizeof(double);
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
@@ -33,7 +30,7 @@ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 struct GemmArgs {
   const double* A; const double* B; double* C;
   int64_t lda, ldb, ldc;
-  int K;            // contraction length (multiple of GEMM_BK)
+  int K;            // contraction length (multiple of 32)
   int ti_off;       // global tile index of grid row 0   (triangular tests)
   int tj_off;       // global tile index of grid column 0
   int tri;          // 0: all tiles; 1: only gi>=gj, diagonal tiles store row>=col;
@@ -65,7 +62,7 @@ struct CovArgs {
 // ---- handle ---------------------------------------------------------------
 struct Handle {
   int device = 0;
-  cudaStream_t s_main = nullptr, s_panel = nullptr;
+  cudaStream_t s_main = nullptr, s_panel = nullptr, s_aux = nullptr;
   std::vector<cudaEvent_t> ev;          // dependency events (no timing)
   cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr, t4 = nullptr;
   cudaError_t last_cuda = cudaSuccess;
@@ -73,6 +70,7 @@ struct Handle {
   gpk_stats stats{};
   int profile = 0;
   std::vector<cudaEvent_t> prof_ev;
+  int prof_pairs = 0;
 
   // training data
   int64_t n = 0, np = 0; int D = 0;
@@ -127,7 +125,7 @@ int launch_cov(Handle* h, cudaStream_t st, const CovArgs& a);
 int launch_prescale(Handle* h, cudaStream_t st, const double* X, int64_t n, int64_t np, int D,
                     const double* scale, int divide, double premul, double* out);
 int launch_diag(Handle* h, cudaStream_t st, double* Ablk, int64_t lda, double* Dinv, double* logdet_slot,
-                int* info, int gidx0);
+                int* info, int gidx0, long long* dbg_clk = nullptr);
 int launch_trsv_fwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* b,
                     double* z, int k, int T);
 int launch_trsv_bwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* z,

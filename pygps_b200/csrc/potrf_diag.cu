@@ -25,20 +25,83 @@ namespace gpk {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int DB = NB;            // 128
 constexpr int IB = DIAG_IB;       // 32
-constexpr int LDT = DIAG_LDT;     // 33
+constexpr int LDS_ = DIAG_LDS;    // 132: == 4 mod 16 -> DMMA fragment loads from S are bank-conflict free
+constexpr int LDT = DIAG_LDT;     // 36:  same property for the 32x32 inverses
 constexpr int DW = DIAG_THREADS / 32;
-constexpr int NRD = (3 * (IB / 4) + DW - 1) / DW;  // register-staging rounds for a 96x32 sub-panel
 
-// S: DBxDB column-major (pitch DB).  T: 4 blocks of IBxIB, column-major, pitch LDT.
-#define S_(r, c) S[(r) + (c) * DB]
+// S: DBxDB column-major (pitch LDS_).  T: 4 blocks W_jj = inv(L_jj), 32x32 column-major, pitch LDT.
+#define S_(r, c) S[(r) + (c) * LDS_]
 #define T_(b, r, c) T[(b) * IB * LDT + (r) + (c) * LDT]
+
+__device__ __forceinline__ void dmma8(double (&c)[4], const double (&a)[4], double b0, double b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b0), "d"(b1));
+}
+
+// One warp: acc(32 x 8*NT) += A(32 x K) * Bop(K x 8*NT), operands in shared memory.
+//   A(r,k)   = A[r + k*lda]                       (column-major rows of S)
+//   Bop(k,n) = B[n*sbn + k*sbk]                   (sbn=1,sbk=ld: B^T of a column-major matrix; sbn=ld,sbk=1: B itself)
+template <int NT>
+__device__ __forceinline__ void warp_mma32(double (&acc)[2][NT][4], const double* A, int lda, const double* B, int sbn,
+                                           int sbk, int K, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    double a[2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      a[mi][0] = A[(mi * 16 + g) + (k0 + t) * lda];
+      a[mi][1] = A[(mi * 16 + g + 8) + (k0 + t) * lda];
+      a[mi][2] = A[(mi * 16 + g) + (k0 + t + 4) * lda];
+      a[mi][3] = A[(mi * 16 + g + 8) + (k0 + t + 4) * lda];
+    }
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+      const double b0 = B[(ni * 8 + g) * sbn + (k0 + t) * sbk];
+      const double b1 = B[(ni * 8 + g) * sbn + (k0 + t + 4) * sbk];
+      dmma8(acc[0][ni], a[0], b0, b1);
+      dmma8(acc[1][ni], a[1], b0, b1);
+    }
+  }
+}
+
+// C fragment <-> shared memory: element (mi*16+g(+8), ni*8+2t(+1)) of a 32 x 8*NT block at C[r + c*LDS_]
+template <int NT>
+__device__ __forceinline__ void frag_apply(double (&acc)[2][NT][4], double* C, int lane, double alpha, double beta) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+      double* p = C + (mi * 16 + g) + (ni * 8 + 2 * t) * LDS_;
+      p[0] = alpha * acc[mi][ni][0] + (beta != 0.0 ? beta * p[0] : 0.0);
+      p[LDS_] = alpha * acc[mi][ni][1] + (beta != 0.0 ? beta * p[LDS_] : 0.0);
+      p[8] = alpha * acc[mi][ni][2] + (beta != 0.0 ? beta * p[8] : 0.0);
+      p[8 + LDS_] = alpha * acc[mi][ni][3] + (beta != 0.0 ? beta * p[8 + LDS_] : 0.0);
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void frag_zero(double (&acc)[2][NT][4]) {
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.0;
+}
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ Dinv,
-                  double* __restrict__ logdet_slot, int* __restrict__ info, int gidx0) {
+                  double* __restrict__ logdet_slot, int* __restrict__ info, int gidx0, long long* dbg_clk) {
   extern __shared__ __align__(16) double dsm[];
-  double* S = dsm;
-  double* T = dsm + DB * DB;
+  int dbg_i = 0;
+#define DBG_T() do { if (dbg_clk && threadIdx.x == 0) dbg_clk[dbg_i++] = clock64(); } while (0)
+  DBG_T();
+  double* S = dsm;                    // DB x LDS_
+  double* T = dsm + DB * LDS_;        // 4 x (IB x LDT)
+  double* rdiag = T + 4 * IB * LDT;   // DB reciprocals of the diagonal of L
   __shared__ double s_logdet;
   __shared__ int s_info;
 
@@ -46,27 +109,33 @@ potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ D
 
   for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
     const int r = idx % DB, c = idx / DB;
-    S[idx] = (r >= c) ? Ablk[r + (int64_t)c * lda] : 0.0;
+    S_(r, c) = (r >= c) ? Ablk[r + (int64_t)c * lda] : 0.0;
   }
   if (tid == 0) { s_logdet = 0.0; s_info = 0; }
   __syncthreads();
+  DBG_T();
 
   // ---------------- phase 1: blocked Cholesky, inner block 32 ----------------
   for (int jb = 0; jb < DB / IB; ++jb) {
     const int j0 = jb * IB;
-    if (warp == 0) {
+    {
+      // 32x32 diagonal block: one matrix row per lane, pivots and multipliers by warp shuffle.
+      // EVERY warp runs it (redundantly) so the shuffles sit in uniform control flow; warp 0 publishes.
       double a[IB];
 #pragma unroll
       for (int c = 0; c < IB; ++c) a[c] = S_(j0 + lane, j0 + c);
-      double lsum = 0.0;
+      __syncthreads();               // everyone has read the block before warp 0 overwrites it
+      double lsum = 0.0, prod = 1.0;
       int bad = 0;
 #pragma unroll
       for (int j = 0; j < IB; ++j) {
         const double d = __shfl_sync(FULL, a[j], j);
         if (!(d > 0.0) && bad == 0) bad = j + 1;
-        const double l = sqrt(d);
-        const double rinv = 1.0 / l;
-        lsum += log(l);
+        const double rinv = rsqrt(d);
+        const double l = d * rinv;
+        prod *= l;
+        if ((j & 7) == 7) { lsum += log(prod); prod = 1.0; }
+        if (tid == j) rdiag[j0 + j] = rinv;
         const double v = (lane == j) ? l : a[j] * rinv;
         a[j] = (lane >= j) ? v : 0.0;
 #pragma unroll
@@ -75,275 +144,251 @@ potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ D
           a[c] = fma(-a[j], lc, a[c]);
         }
       }
+      if (warp == 0) {
 #pragma unroll
-      for (int c = 0; c < IB; ++c) S_(j0 + lane, j0 + c) = (lane >= c) ? a[c] : 0.0;
-      __syncwarp();
-      // inverse of the 32x32 factor: lane owns column `lane` of W = L^-1
-      double w[IB];
-#pragma unroll
-      for (int i = 0; i < IB; ++i) {
-        double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k) {
-          const double lik = S_(j0 + i, j0 + k);
-          if ((k & 3) == 0) s0 = fma(-lik, w[k], s0);
-          else if ((k & 3) == 1) s1 = fma(-lik, w[k], s1);
-          else if ((k & 3) == 2) s2 = fma(-lik, w[k], s2);
-          else s3 = fma(-lik, w[k], s3);
+        for (int c = 0; c < IB; ++c) S_(j0 + lane, j0 + c) = (lane >= c) ? a[c] : 0.0;
+        if (lane == 0) {
+          s_logdet += lsum;
+          if (bad != 0 && s_info == 0) s_info = gidx0 + j0 + bad;
         }
-        w[i] = ((s0 + s1) + (s2 + s3)) / S_(j0 + i, j0 + i);
-      }
-#pragma unroll
-      for (int i = 0; i < IB; ++i) T_(jb, i, lane) = w[i];
-      if (lane == 0) {
-        s_logdet += lsum;
-        if (bad != 0 && s_info == 0) s_info = gidx0 + j0 + bad;
       }
     }
     __syncthreads();
+    DBG_T();
     const int nrb = DB / IB - 1 - jb;  // 32-row blocks below the diagonal block
     if (nrb > 0) {
-      // sub-panel: S[r, j0+c] <- sum_{k<=c} S[r, j0+k] * W(c,k)   (row-wise in place -> stage in registers)
-      double outv[NRD][4];
-      const int ntile = nrb * (IB / 4);
+      // sub-panel: X * L_jj^T = Y by forward substitution, one row per thread, row kept in registers
+      if (tid < nrb * IB) {
+        const int r = j0 + IB + tid;
+        double x[IB];
 #pragma unroll
-      for (int rd = 0; rd < NRD; ++rd) {
-        const int wt = warp + rd * DW;
-        if (wt < ntile) {
-          const int r = j0 + IB + (wt / (IB / 4)) * IB + lane;
-          const int c0 = (wt % (IB / 4)) * 4;
-          double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-          for (int k = 0; k < c0 + 4; ++k) {
-            const double x = S_(r, j0 + k);
-            acc0 = fma(x, T_(jb, c0 + 0, k), acc0);
-            acc1 = fma(x, T_(jb, c0 + 1, k), acc1);
-            acc2 = fma(x, T_(jb, c0 + 2, k), acc2);
-            acc3 = fma(x, T_(jb, c0 + 3, k), acc3);
+        for (int c = 0; c < IB; ++c) {
+          double s0 = S_(r, j0 + c), s1 = 0.0;
+#pragma unroll
+          for (int k = 0; k < c; ++k) {
+            const double lck = S_(j0 + c, j0 + k);      // warp-uniform address: broadcast
+            if (k & 1) s1 = fma(-x[k], lck, s1);
+            else s0 = fma(-x[k], lck, s0);
           }
-          outv[rd][0] = acc0; outv[rd][1] = acc1; outv[rd][2] = acc2; outv[rd][3] = acc3;
+          x[c] = (s0 + s1) * rdiag[j0 + c];
         }
+#pragma unroll
+        for (int c = 0; c < IB; ++c) S_(r, j0 + c) = x[c];
       }
       __syncthreads();
-#pragma unroll
-      for (int rd = 0; rd < NRD; ++rd) {
-        const int wt = warp + rd * DW;
-        if (wt < ntile) {
-          const int r = j0 + IB + (wt / (IB / 4)) * IB + lane;
-          const int c0 = (wt % (IB / 4)) * 4;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) S_(r, j0 + c0 + q) = outv[rd][q];
-        }
-      }
-      __syncthreads();
-      // trailing update of the lower block triangle: S[ib,cb] -= S[ib,jb] * S[cb,jb]^T
+      // trailing update of the lower block triangle on the tensor pipe: S[ib,cb] -= S[ib,jb] * S[cb,jb]^T
       const int npair = nrb * (nrb + 1) / 2;
-      for (int wt = warp; wt < npair * (IB / 4); wt += DW) {
-        const int pr = wt / (IB / 4);
-        const int cg = wt % (IB / 4);
+      for (int pr = warp; pr < npair; pr += DW) {
         int ib = 0, cb = 0;  // decode pair index -> (ib >= cb), both in [0,nrb)
         {
           int q = pr;
           while (q > ib) { q -= (ib + 1); ++ib; }
           cb = q;
         }
-        const int r = j0 + IB + ib * IB + lane;
-        const int c0 = j0 + IB + cb * IB + cg * 4;
-        double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-#pragma unroll 8
-        for (int k = 0; k < IB; ++k) {
-          const double x = S_(r, j0 + k);
-          acc0 = fma(x, S_(c0 + 0, j0 + k), acc0);
-          acc1 = fma(x, S_(c0 + 1, j0 + k), acc1);
-          acc2 = fma(x, S_(c0 + 2, j0 + k), acc2);
-          acc3 = fma(x, S_(c0 + 3, j0 + k), acc3);
-        }
-        S_(r, c0 + 0) -= acc0;
-        S_(r, c0 + 1) -= acc1;
-        S_(r, c0 + 2) -= acc2;
-        S_(r, c0 + 3) -= acc3;
+        double acc[2][4][4];
+        frag_zero<4>(acc);
+        const int rr = j0 + IB + ib * IB, cc = j0 + IB + cb * IB;
+        warp_mma32<4>(acc, &S_(rr, j0), LDS_, &S_(cc, j0), 1, LDS_, IB, lane);
+        frag_apply<4>(acc, &S_(rr, cc), lane, -1.0, 1.0);
       }
       __syncthreads();
     }
+    DBG_T();
   }
 
-  // ---------------- phase 2: L back to global (strict upper of the block = 0) ----
-  for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
-    const int r = idx % DB, c = idx / DB;
-    Ablk[r + (int64_t)c * lda] = (r >= c) ? S[idx] : 0.0;
+  // ---------------- phase 2: 32x32 inverses (warps 0-3) || L back to global (warps 4-7) ----------
+  if (warp < 4) {
+    // lane owns column `lane` of W = inv(L_ww) : forward substitution in registers
+    const int j0 = warp * IB;
+    double w[IB];
+#pragma unroll
+    for (int i = 0; i < IB; ++i) {
+      double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) {
+        const double lik = S_(j0 + i, j0 + k);
+        if ((k & 3) == 0) s0 = fma(-lik, w[k], s0);
+        else if ((k & 3) == 1) s1 = fma(-lik, w[k], s1);
+        else if ((k & 3) == 2) s2 = fma(-lik, w[k], s2);
+        else s3 = fma(-lik, w[k], s3);
+      }
+      w[i] = ((s0 + s1) + (s2 + s3)) * rdiag[j0 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < IB; ++i) T_(warp, i, lane) = w[i];
+  } else {
+    for (int idx = tid - 4 * 32; idx < DB * DB; idx += DIAG_THREADS - 4 * 32) {
+      const int r = idx % DB, c = idx / DB;
+      Ablk[r + (int64_t)c * lda] = (r >= c) ? S_(r, c) : 0.0;
+    }
   }
   if (tid == 0) {
     *logdet_slot = s_logdet;
     if (s_info != 0) atomicCAS(info, 0, s_info);
   }
   __syncthreads();
+  DBG_T();
 
   // ---------------- phase 3: in-place inverse of the block factor ----------------
-  // W[>j, j] = -W22 * L[>j, j] * W_jj, from the last block column to the first.
-  for (int jb = DB / IB - 1; jb >= 0; --jb) {
+  // diagonal blocks <- W_jj ; then W[>j, j] = -W22 * (L[>j, j] * W_jj), last block column first.
+  for (int idx = tid; idx < 4 * IB * IB; idx += DIAG_THREADS) {
+    const int b = idx / (IB * IB), e = idx % (IB * IB);
+    const int r = e % IB, c = e / IB;
+    S_(b * IB + r, b * IB + c) = T_(b, r, c);
+  }
+  __syncthreads();
+  for (int jb = DB / IB - 2; jb >= 0; --jb) {
     const int j0 = jb * IB;
     const int nrb = DB / IB - 1 - jb;
     const int r0 = j0 + IB;
-    if (nrb > 0) {
-      const int ntile = nrb * (IB / 4);
-      double outv[NRD][4];
-      // (i) Y <- Y * W_jj :  Y(r,c) = sum_{k>=c} Y(r,k) * W_jj(k,c)
-#pragma unroll
-      for (int rd = 0; rd < NRD; ++rd) {
-        const int wt = warp + rd * DW;
-        if (wt < ntile) {
-          const int r = r0 + (wt / (IB / 4)) * IB + lane;
-          const int c0 = (wt % (IB / 4)) * 4;
-          double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-          for (int k = c0; k < IB; ++k) {
-            const double x = S_(r, j0 + k);
-            acc0 = fma(x, T_(jb, k, c0 + 0), acc0);
-            acc1 = fma(x, T_(jb, k, c0 + 1), acc1);
-            acc2 = fma(x, T_(jb, k, c0 + 2), acc2);
-            acc3 = fma(x, T_(jb, k, c0 + 3), acc3);
-          }
-          outv[rd][0] = acc0; outv[rd][1] = acc1; outv[rd][2] = acc2; outv[rd][3] = acc3;
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int rd = 0; rd < NRD; ++rd) {
-        const int wt = warp + rd * DW;
-        if (wt < ntile) {
-          const int r = r0 + (wt / (IB / 4)) * IB + lane;
-          const int c0 = (wt % (IB / 4)) * 4;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) S_(r, j0 + c0 + q) = outv[rd][q];
-        }
-      }
-      __syncthreads();
-      // (ii) X <- -W22 * Y : X(r,c) = -sum_{r0<=k<=r} S(r,k) * Y(k,c)   (S upper entries are exact zeros)
-#pragma unroll
-      for (int rd = 0; rd < NRD; ++rd) {
-        const int wt = warp + rd * DW;
-        if (wt < ntile) {
-          const int rb = wt / (IB / 4);
-          const int r = r0 + rb * IB + lane;
-          const int c0 = j0 + (wt % (IB / 4)) * 4;
-          double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-          const int kend = r0 + (rb + 1) * IB;
-#pragma unroll 8
-          for (int k = r0; k < kend; ++k) {
-            const double x = S_(r, k);
-            acc0 = fma(x, S_(k, c0 + 0), acc0);
-            acc1 = fma(x, S_(k, c0 + 1), acc1);
-            acc2 = fma(x, S_(k, c0 + 2), acc2);
-            acc3 = fma(x, S_(k, c0 + 3), acc3);
-          }
-          outv[rd][0] = -acc0; outv[rd][1] = -acc1; outv[rd][2] = -acc2; outv[rd][3] = -acc3;
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int rd = 0; rd < NRD; ++rd) {
-        const int wt = warp + rd * DW;
-        if (wt < ntile) {
-          const int r = r0 + (wt / (IB / 4)) * IB + lane;
-          const int c0 = j0 + (wt % (IB / 4)) * 4;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) S_(r, c0 + q) = outv[rd][q];
-        }
-      }
+    // Work items are (row block rb, 16-column half): up to 6 warps busy.  Results are staged in registers
+    // across a barrier because the products are formed in place.
+    const int rb = warp >> 1, half = warp & 1;
+    const bool active = rb < nrb;
+    double acc[2][2][4];
+    // (i) Y <- Y * W_jj
+    if (active) {
+      frag_zero<2>(acc);
+      warp_mma32<2>(acc, &S_(r0 + rb * IB, j0), LDS_, &T_(jb, 0, half * 16), LDT, 1, IB, lane);
     }
-    // (iii) diagonal block <- W_jj
-    for (int idx = tid; idx < IB * IB; idx += DIAG_THREADS) {
-      const int r = idx % IB, c = idx / IB;
-      S_(j0 + r, j0 + c) = T_(jb, r, c);
+    __syncthreads();
+    if (active) frag_apply<2>(acc, &S_(r0 + rb * IB, j0 + half * 16), lane, 1.0, 0.0);
+    __syncthreads();
+    // (ii) X <- -W22 * Y : row block rb needs Y blocks 0..rb
+    if (active) {
+      frag_zero<2>(acc);
+      warp_mma32<2>(acc, &S_(r0 + rb * IB, r0), LDS_, &S_(r0, j0 + half * 16), LDS_, 1, (rb + 1) * IB, lane);
     }
+    __syncthreads();
+    if (active) frag_apply<2>(acc, &S_(r0 + rb * IB, j0 + half * 16), lane, -1.0, 0.0);
     __syncthreads();
   }
 
+  DBG_T();
   // ---------------- phase 4: inverse to global (dense 128x128, pitch 128) --------
-  for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) Dinv[idx] = S[idx];
+  for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
+    const int r = idx % DB, c = idx / DB;
+    Dinv[idx] = S_(r, c);
+  }
+  __syncthreads();
+  DBG_T();
+#undef DBG_T
+}
+
+// ---------------------------------------------------------------------------
+// single right-hand-side substitution steps.  512 threads; each 128x128 tile is pulled into shared
+// memory with cp.async (all 128 KB in flight at once - these steps are pure latency), then reduced there.
+// ---------------------------------------------------------------------------
+constexpr int TRSV_THREADS = 512;
+constexpr size_t TRSV_SMEM = size_t(NB) * NB * sizeof(double);
+
+__device__ __forceinline__ void tile_to_smem(double* tile, const double* __restrict__ M, int64_t pitch) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < (NB * NB / 2) / TRSV_THREADS; ++i) {
+    const int ch = tid + i * TRSV_THREADS;   // 16-byte chunk id: 64 per column
+    const int c = ch >> 6, r = (ch & 63) * 2;
+    unsigned sa = (unsigned)__cvta_generic_to_shared(tile + r + c * NB);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(M + r + (int64_t)c * pitch) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+}
+
+// out[r] = sum_c tile[r + c*NB] * v[c]     (4 column groups of 32, then a shared-memory reduction)
+__device__ __forceinline__ void smem_gemv_n(const double* tile, const double* v, double* out, double* red) {
+  const int tid = threadIdx.x;
+  const int r = tid & (NB - 1), cg = tid >> 7;
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+  for (int c = cg * 32; c < cg * 32 + 32; c += 2) {
+    a0 = fma(tile[r + c * NB], v[c], a0);
+    a1 = fma(tile[r + (c + 1) * NB], v[c + 1], a1);
+  }
+  red[cg * NB + r] = a0 + a1;
+  __syncthreads();
+  if (tid < NB) out[tid] = (red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]);
+  __syncthreads();
+}
+
+// out[c] = sum_r tile[r + c*NB] * v[r]     (one warp per column, lanes along r, shuffle reduction)
+__device__ __forceinline__ void smem_gemv_t(const double* tile, const double* v, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
+#pragma unroll
+  for (int c = warp; c < NB; c += TRSV_THREADS / 32) {
+    const double* col = tile + c * NB;
+    double s = fma(col[lane], v0, fma(col[lane + 32], v1, fma(col[lane + 64], v2, col[lane + 96] * v3)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) out[c] = s;
+  }
+  __syncthreads();
+}
+
+// forward step k (grid T-k CTAs): every CTA forms z_k = Dinv_k * b_k in shared memory; CTA 0 stores it;
+// CTA i>0 updates b_{k+i} -= L[k+i, k] * z_k.
+__global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_fwd_kernel(const double* __restrict__ A, int64_t lda,
+                                                                   const double* __restrict__ Dinv,
+                                                                   double* __restrict__ b, double* __restrict__ z,
+                                                                   int k) {
+  extern __shared__ __align__(16) double tile[];
+  __shared__ double sb[NB], sz[NB], so[NB], red[4 * NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) sb[tid] = b[(int64_t)k * NB + tid];
+  tile_to_smem(tile, Dinv + (int64_t)k * NB * NB, NB);
+  smem_gemv_n(tile, sb, sz, red);
+  const int i = blockIdx.x;
+  if (i == 0) {
+    if (tid < NB) z[(int64_t)k * NB + tid] = sz[tid];
+  } else {
+    tile_to_smem(tile, A + (int64_t)(k + i) * NB + (int64_t)k * NB * lda, lda);
+    smem_gemv_n(tile, sz, so, red);
+    if (tid < NB) b[(int64_t)(k + i) * NB + tid] -= so[tid];
+  }
+}
+
+// backward step k (grid k+1 CTAs): every CTA forms x_k = Dinv_k^T * z_k; CTA k stores it;
+// CTA j<k updates z_j -= L[k, j]^T * x_k.
+__global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_bwd_kernel(const double* __restrict__ A, int64_t lda,
+                                                                   const double* __restrict__ Dinv,
+                                                                   double* __restrict__ z, double* __restrict__ x,
+                                                                   int k) {
+  extern __shared__ __align__(16) double tile[];
+  __shared__ double sz[NB], sx[NB], so[NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) sz[tid] = z[(int64_t)k * NB + tid];
+  tile_to_smem(tile, Dinv + (int64_t)k * NB * NB, NB);
+  smem_gemv_t(tile, sz, sx);
+  const int j = blockIdx.x;
+  if (j == k) {
+    if (tid < NB) x[(int64_t)k * NB + tid] = sx[tid];
+  } else {
+    tile_to_smem(tile, A + (int64_t)k * NB + (int64_t)j * NB * lda, lda);
+    smem_gemv_t(tile, sx, so);
+    if (tid < NB) z[(int64_t)j * NB + tid] -= so[tid];
+  }
 }
 
 int diag_init(Handle* h) {
   GPK_CK(h, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+  GPK_CK(h, cudaFuncSetAttribute(trsv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM));
+  GPK_CK(h, cudaFuncSetAttribute(trsv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM));
   return 0;
 }
 
 int launch_diag(Handle* h, cudaStream_t st, double* Ablk, int64_t lda, double* Dinv, double* logdet_slot, int* info,
-                int gidx0) {
-  potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0);
+                int gidx0, long long* dbg_clk) {
+  potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
   h->stats.launches++;
   GPK_CK(h, cudaGetLastError());
   return 0;
 }
 
-// ---------------------------------------------------------------------------
-// single right-hand-side substitution steps
-// ---------------------------------------------------------------------------
-// forward step k (grid T-k CTAs of 128 threads):
-//   every CTA forms z_k = Dinv_k * b_k in shared memory; CTA 0 stores it;
-//   CTA i>0 updates b_{k+i} -= L[k+i, k] * z_k.
-__global__ void __launch_bounds__(NB) trsv_fwd_kernel(const double* __restrict__ A, int64_t lda,
-                                                      const double* __restrict__ Dinv, double* __restrict__ b,
-                                                      double* __restrict__ z, int k) {
-  __shared__ double sb[NB], sz[NB];
-  const int tid = threadIdx.x;
-  const double* Dk = Dinv + (int64_t)k * NB * NB;
-  sb[tid] = b[(int64_t)k * NB + tid];
-  __syncthreads();
-  double acc = 0.0;
-#pragma unroll 8
-  for (int c = 0; c < NB; ++c) acc = fma(Dk[tid + c * NB], sb[c], acc);  // lower-triangular: zeros above the diagonal
-  sz[tid] = acc;
-  __syncthreads();
-  const int i = blockIdx.x;
-  if (i == 0) {
-    z[(int64_t)k * NB + tid] = acc;
-  } else {
-    const double* Lik = A + (int64_t)(k + i) * NB + (int64_t)k * NB * lda;
-    double s = 0.0;
-#pragma unroll 8
-    for (int c = 0; c < NB; ++c) s = fma(Lik[tid + (int64_t)c * lda], sz[c], s);
-    b[(int64_t)(k + i) * NB + tid] -= s;
-  }
-}
-
-// backward step k (grid k+1 CTAs of 128 threads):
-//   every CTA forms x_k = Dinv_k^T * z_k; CTA k stores it; CTA j<k updates z_j -= L[k, j]^T * x_k.
-__global__ void __launch_bounds__(NB) trsv_bwd_kernel(const double* __restrict__ A, int64_t lda,
-                                                      const double* __restrict__ Dinv, double* __restrict__ z,
-                                                      double* __restrict__ x, int k) {
-  __shared__ double sz[NB], sx[NB];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double* Dk = Dinv + (int64_t)k * NB * NB;
-  sz[tid] = z[(int64_t)k * NB + tid];
-  __syncthreads();
-  // x[c] = sum_r Dk[r,c] * z[r]; warp per column group so that loads run along r (contiguous)
-  for (int c = warp; c < NB; c += NB / 32) {
-    double s = 0.0;
-#pragma unroll
-    for (int r = lane; r < NB; r += 32) s = fma(Dk[r + c * NB], sz[r], s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    if (lane == 0) sx[c] = s;
-  }
-  __syncthreads();
-  const int j = blockIdx.x;
-  if (j == k) {
-    x[(int64_t)k * NB + tid] = sx[tid];
-  } else {
-    const double* Lkj = A + (int64_t)k * NB + (int64_t)j * NB * lda;
-    for (int c = warp; c < NB; c += NB / 32) {
-      double s = 0.0;
-#pragma unroll
-      for (int r = lane; r < NB; r += 32) s = fma(Lkj[r + (int64_t)c * lda], sx[r], s);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-      if (lane == 0) z[(int64_t)j * NB + c] -= s;
-    }
-  }
-}
-
 int launch_trsv_fwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* b, double* z,
                     int k, int T) {
-  trsv_fwd_kernel<<<T - k, NB, 0, st>>>(A, lda, Dinv, b, z, k);
+  trsv_fwd_kernel<<<T - k, TRSV_THREADS, TRSV_SMEM, st>>>(A, lda, Dinv, b, z, k);
   h->stats.launches++;
   GPK_CK(h, cudaGetLastError());
   return 0;
@@ -352,7 +397,7 @@ int launch_trsv_fwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, co
 int launch_trsv_bwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* z, double* x,
                     int k, int T) {
   (void)T;
-  trsv_bwd_kernel<<<k + 1, NB, 0, st>>>(A, lda, Dinv, z, x, k);
+  trsv_bwd_kernel<<<k + 1, TRSV_THREADS, TRSV_SMEM, st>>>(A, lda, Dinv, z, x, k);
   h->stats.launches++;
   GPK_CK(h, cudaGetLastError());
   return 0;

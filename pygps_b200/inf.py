@@ -17,6 +17,21 @@ from .tools import jitchol, solve_chol
 np.seterr(all='ignore')          # the reference does this at import (Core/inf.py:56)
 
 
+_SCRATCH = []
+
+
+def _scratch_engine():
+    """A second GPU handle used only to rebuild a factor that was overwritten on the model's handle."""
+    if not _SCRATCH:
+        _SCRATCH.append(_lib.Engine())
+    return _SCRATCH[0]
+
+
+def _x_signature(x):
+    """Cheap fingerprint of the training inputs (shape + a few entries + sum): detects in-place edits."""
+    return (x.shape, float(x.flat[0]), float(x.flat[-1]), float(x.sum()))
+
+
 class postStruct(object):
     """Posterior parameters alpha, sW, L (Core/inf.py:59-89).
 
@@ -30,17 +45,30 @@ class postStruct(object):
         self._engine = None      # engine that holds the factor this posterior describes
         self._epoch = -1
         self._n = 0
-        self._spec = None        # what the resident factor was built from (for predict)
+        self._spec = None        # what the resident factor was built from (for predict / rebuild)
+        self._x = None           # training inputs the factor was built from
+        self._xsig = None
 
     # -- lazy factor ----------------------------------------------------------
     def _resident(self):
         return self._engine is not None and self._engine.epoch == self._epoch
 
     def _materialize(self):
+        """post.L on first touch: copied out of the GPU if the factor is still resident, otherwise
+        rebuilt there from (x, hyper-parameters) - the factorisation is deterministic, so the result is
+        the same array the reference would have kept (at the price of one more evaluation)."""
         if self._L is None:
-            if not self._resident():
-                raise RuntimeError("posterior factor is no longer resident on the GPU")
-            self._L = self._engine.get_factor(self._n)
+            if self._resident():
+                self._L = self._engine.get_factor(self._n)
+            else:
+                if self._x is None or self._spec is None or _x_signature(self._x) != self._xsig:
+                    raise RuntimeError("posterior factor is no longer resident on the GPU and the training "
+                                       "inputs it was built from have changed")
+                _, kind, md, hyp, log_sn = self._spec
+                eng = _scratch_engine()
+                eng.set_data(self._x)
+                eng.exact_eval(kind, md, list(hyp), log_sn, np.zeros(self._x.shape[0]), False)
+                self._L = eng.get_factor(self._n)
         return self._L
 
     def _getL(self):
@@ -59,8 +87,7 @@ class postStruct(object):
         other.sW = np.array(self.sW, copy=True)
         other._L = None if self._L is None else np.array(self._L, copy=True)
         other._engine, other._epoch, other._n, other._spec = self._engine, self._epoch, self._n, self._spec
-        if other._L is None and other._engine is not None:
-            other._engine._live_posts.add(other)
+        other._x, other._xsig = self._x, self._xsig
         return other
 
     def __repr__(self):
@@ -151,7 +178,7 @@ class Exact(Inference):
         post._L = None
         post._engine, post._epoch, post._n = eng, eng.epoch, n
         post._spec = ('exact', kind, md, tuple(hyp), float(likfunc.hyp[0]))
-        eng._live_posts.add(post)
+        post._x, post._xsig = x, _x_signature(x)
         if nargout > 1:
             if nargout > 2:
                 dnlZ = dnlZStruct(meanfunc, covfunc, likfunc)

@@ -101,34 +101,45 @@ def trsv_bwd(A, Dinv, z, x, k, T):
         z[j * NB:(j + 1) * NB] -= A[k * NB:(k + 1) * NB, j * NB:(j + 1) * NB].T @ xk
 
 
-def potrf_device(A, b=None):
-    """api.cu potrf_device (stream order flattened).  A: padded (np,np) F-order, lower
-    triangle valid; factor overwrites it.  Returns Dinv list, logdet parts, info, z."""
+def potrf_device(A, b=None, W=2):
+    """api.cu potrf_device (stream order flattened): two-level blocking, outer blocks of W panels.
+    A: padded (np,np) F-order, lower triangle valid; the factor overwrites it.
+    Returns Dinv list, logdet parts, info, z."""
     np_ = A.shape[0]
     T = np_ // NB
     Dinv = [None] * T
     parts = np.zeros(T)
     info = 0
     z = np.zeros(np_) if b is not None else None
-    for k in range(T):
-        s = slice(k * NB, (k + 1) * NB)
-        L, Li, ld, inf_k = diag_block(A[s, s])
-        A[s, s] = L
-        Dinv[k], parts[k] = Li, ld
-        if inf_k and not info:
-            info = k * NB + inf_k
-        rem = T - k - 1
+    nblk = (T + W - 1) // W
+    for j in range(nblk):
+        pb, pe = j * W, min(j * W + W, T)
+        for p in range(pb, pe):
+            s = slice(p * NB, (p + 1) * NB)
+            L, Li, ld, inf_p = diag_block(A[s, s])
+            A[s, s] = L
+            Dinv[p], parts[p] = Li, ld
+            if inf_p and not info:
+                info = p * NB + inf_p
+            rem = T - p - 1
+            if rem > 0:
+                pan = A[(p + 1) * NB:, s]
+                gemm_nt(0, pan, pan.copy(), Li, NB, rem, 1)
+            if b is not None:
+                trsv_fwd(A, Dinv, b, z, p, T)
+            inner = pe - p - 1
+            if inner > 0:
+                pan = A[(p + 1) * NB:, s]
+                gemm_nt(1, A[(p + 1) * NB:, (p + 1) * NB:], pan, pan, NB, rem, inner, tri=1)
+        rem = T - pe
         if rem > 0:
-            pan = A[(k + 1) * NB:, s]
-            gemm_nt(0, pan, pan.copy(), Li, NB, rem, 1)
-        if b is not None:
-            trsv_fwd(A, Dinv, b, z, k, T)
-        if rem > 0:
-            pan = A[(k + 1) * NB:, s]
-            Ct = A[(k + 1) * NB:, (k + 1) * NB:]
-            gemm_nt(1, Ct, pan, pan, NB, rem, 1, tri=1)
-            if rem > 1:
-                gemm_nt(1, Ct[:, NB:], pan, pan[NB:], NB, rem, rem - 1, tri=1, tj_off=1)
+            kw = (pe - pb) * NB
+            pan = A[pe * NB:, pb * NB:pe * NB]
+            Ct = A[pe * NB:, pe * NB:]
+            first = min(W, rem)
+            gemm_nt(1, Ct, pan, pan, kw, rem, first, tri=1)
+            if rem > first:
+                gemm_nt(1, Ct[:, first * NB:], pan, pan[first * NB:], kw, rem, rem - first, tri=1, tj_off=first)
     return Dinv, parts, info, z
 
 

@@ -30,14 +30,17 @@ def test_diag_block_reports_first_bad_pivot():
     assert info == 41
 
 
-def test_blocked_potrf_with_lookahead_split_and_fused_forward_solve():
-    n = 300
+import pytest
+
+
+@pytest.mark.parametrize("n,W", [(300, 1), (300, 2), (700, 2), (700, 3), (520, 4)])
+def test_blocked_potrf_with_lookahead_split_and_fused_forward_solve(n, W):
     A = _spd(n, 3)
     rng = np.random.default_rng(0)
     y = rng.standard_normal(n)
     P = br.pad_spd(A)
     b = np.zeros(P.shape[0]); b[:n] = y
-    Dinv, parts, info, z = br.potrf_device(P, b)
+    Dinv, parts, info, z = br.potrf_device(P, b, W=W)
     Lref = np.linalg.cholesky(A)
     assert info == 0
     np.testing.assert_allclose(np.tril(P)[:n, :n], Lref, rtol=1e-10, atol=1e-10)

@@ -21,7 +21,7 @@ def _report(name, got, ref):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("shape", [(128, 128, 16), (256, 384, 128), (512, 128, 256)])
+@pytest.mark.parametrize("shape", [(128, 128, 32), (256, 384, 128), (512, 128, 256)])
 def test_gemm_nt_full(eng, mode, shape):
     M, N, K = shape
     rng = np.random.default_rng(M + N + K + mode)
@@ -51,6 +51,17 @@ def test_gemm_nt_trapezoid(eng):
     ref = U @ U.T
     lo = np.tril(np.ones((n, n), bool))
     assert np.allclose(got[lo], ref[lo], rtol=1e-12, atol=1e-11), _report("U U^T", np.where(lo, got, 0), np.where(lo, ref, 0))
+
+
+def test_gemm_nt_in_place_is_race_free(eng):
+    """Regression: the panel TRSM overwrites its own A operand.  With column-split tiles two CTAs shared a
+    row tile and one could overwrite columns the other was still reading (seen as a wrong nlZ at N=16384)."""
+    rng = np.random.default_rng(11)
+    M = 128 * 96
+    A = rng.standard_normal((M, 128)); B = np.tril(rng.standard_normal((128, 128)))
+    for _ in range(3):
+        got = eng.dbg_gemm_nt(4, A, B, np.zeros((M, 128)))
+        assert np.allclose(got, A @ B.T, rtol=1e-12, atol=1e-11), _report("in-place A*B^T", got, A @ B.T)
 
 
 def _spd128(seed):
