@@ -46,14 +46,14 @@ static int ensure_prof_events(Handle* h, size_t count) {
 //   s_aux                  : single-right-hand-side forward substitution step p, off the critical path
 // Outer block j+1 therefore overlaps the bulk of trailing update j (look-ahead 1).
 // ---------------------------------------------------------------------------
-static int g_potrf_w = 2;
+static int g_potrf_w = 0;   // 0: choose from the problem size (measured on B200: 3 panels at T>64, else 2)
 
 int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info, double* b_fwd,
                  double* z_out) {
   const int T = (int)(np / NB);
   const int64_t lda = np;
   if (const char* e = getenv("GPK_POTRF_W")) { g_potrf_w = atoi(e); }
-  const int W = (g_potrf_w < 1) ? 1 : (g_potrf_w > 8 ? 8 : g_potrf_w);
+  const int W = (g_potrf_w < 1) ? ((T > 64) ? 3 : (T > 8 ? 2 : 1)) : (g_potrf_w > 8 ? 8 : g_potrf_w);
   const int nblk = (T + W - 1) / W;
   GPK_TRY(ensure_events(h, 2 * (size_t)T + 4));
   if (h->profile) GPK_TRY(ensure_prof_events(h, 2 * (size_t)T + 2));
