@@ -139,7 +139,7 @@ static int collect_profile(Handle* h, int T) {
 }
 
 // per-kind input scaling; returns sf2
-static int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::vector<double>& scale,
+int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::vector<double>& scale,
                       int* divide, double* premul, double* sf2) {
   scale.assign(D, 1.0);
   *premul = 1.0;
@@ -168,7 +168,8 @@ static int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D
 
 static int free_all(Handle* h) {
   double** ptrs[] = {&h->dX, &h->dXs, &h->dScale, &h->dA, &h->dDinv, &h->dB, &h->dZ, &h->dAlpha, &h->dR, &h->dScal,
-                     &h->dU, &h->dW, &h->dP, &h->dTmp, &h->dUin, &h->dUs, &h->dLpost, &h->dAlphaU};
+                     &h->dU, &h->dW, &h->dP, &h->dTmp, &h->dUin, &h->dUs, &h->dLpost, &h->dAlphaU,
+                     &h->fKuu, &h->fDinvU, &h->fA2, &h->fDinv2, &h->fVt, &h->fVs, &h->fVec, &h->fWt, &h->dXtmp};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -176,6 +177,7 @@ static int free_all(Handle* h) {
   if (h->dInfo) cudaFree(h->dInfo);
   h->dInfo = nullptr;
   h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = 0;
+  h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->capUs = h->capLpost = h->capAlphaU = 0;
   return 0;
 }
 
@@ -204,11 +206,11 @@ static int alloc_problem(Handle* h, int64_t n, int D) {
   return 0;
 }
 
-static void stats_begin(Handle* h) {
+void stats_begin(Handle* h) {
   std::memset(&h->stats, 0, sizeof(h->stats));
 }
 
-static int check_handle(gpk_handle hh, Handle** out) {
+int check_handle(gpk_handle hh, Handle** out) {
   if (!hh) return GPK_ERR_ARG;
   Handle* h = reinterpret_cast<Handle*>(hh);
   cudaError_t e = cudaSetDevice(h->device);
@@ -219,7 +221,7 @@ static int check_handle(gpk_handle hh, Handle** out) {
 
 // Solve with many right-hand sides held TRANSPOSED: P is (rows x np) column-major with pitch ldp
 // (one right-hand side per ROW).  Forward: P <- P * L^-T, block column by block column.
-static int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A,
+int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A,
                          int64_t lda, const double* Dinv, int T) {
   for (int k = 0; k < T; ++k) {
     GemmArgs t{};
@@ -239,7 +241,7 @@ static int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int
 
 // U <- L^-T (upper triangular, np x np column-major pitch np) by the same sweep applied to the identity,
 // touching only the tiles on or above the diagonal.
-static int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv) {
+int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv) {
   const int T = (int)(np / NB);
   GPK_TRY(launch_set_identity(h, st, U, np, np, np));
   for (int k = 0; k < T; ++k) {
@@ -690,13 +692,6 @@ int gpk_potrs(gpk_handle hh, const double* B, int64_t nrhs, double* X_out) {
   GPK_CK(h, cudaStreamSynchronize(st));
   return 0;
 }
-
-// ---------------------------------------------------------------------------
-int gpk_fitc_eval(gpk_handle, int, int, const double*, int, double, const double*, int64_t, const double*, int,
-                  double*, double*, double*, double*, double*, double*) {
-  return GPK_ERR_STATE;
-}
-int gpk_fitc_predict(gpk_handle, const double*, int64_t, double*, double*) { return GPK_ERR_STATE; }
 
 // ---------------------------------------------------------------------------
 int gpk_bench_dmma(gpk_handle hh, int shape, int warps_per_cta, int iters, double* tflops, double* ms) {

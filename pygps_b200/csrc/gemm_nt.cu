@@ -43,6 +43,7 @@ __device__ __forceinline__ void dmma_16x8x8(double (&c)[4], const double (&a)[4]
 
 // MODE 0: C = A*B^T          (C is not read)
 // MODE 1: C = C - A*B^T      (accumulators start at -C, result is negated on store)
+// MODE 2: C = C + A*B^T
 // Variants (template parameters; picked at run time by GPK_GEMM_VARIANT for A/B measurements):
 //   BN   column width of the CTA tile (rows are always 128)
 //   WN   warps along N (4 along M): CTA = 128*WN threads, warp tile 32 x BN/WN
@@ -106,17 +107,18 @@ __global__ void __launch_bounds__(128 * WN, MINB) dgemm_nt_kernel(const GemmArgs
   double acc[2][NT][4];
   const int row_base = wm * 32 + g;
   const int col_base = wn * WTN + 2 * t;
-  if (MODE == 1) {
+  if (MODE != 0) {
+    const double isg = (MODE == 1) ? -1.0 : 1.0;
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
       for (int ni = 0; ni < NT; ++ni) {
         const int r = row_base + mi * 16, c = col_base + ni * 8;
         const double* cp = Cg + r + (int64_t)c * p.ldc;
-        acc[mi][ni][0] = -cp[0];
-        acc[mi][ni][1] = -cp[p.ldc];
-        acc[mi][ni][2] = -cp[8];
-        acc[mi][ni][3] = -cp[8 + p.ldc];
+        acc[mi][ni][0] = isg * cp[0];
+        acc[mi][ni][1] = isg * cp[p.ldc];
+        acc[mi][ni][2] = isg * cp[8];
+        acc[mi][ni][3] = isg * cp[8 + p.ldc];
       }
   } else {
 #pragma unroll
@@ -204,6 +206,8 @@ static int variant_init(Handle* h) {
                                  (int)gemm_smem<BN, BK, ST>()));
   GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<1, BN, WN, BK, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)gemm_smem<BN, BK, ST>()));
+  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<2, BN, WN, BK, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)gemm_smem<BN, BK, ST>()));
   return 0;
 }
 
@@ -212,8 +216,10 @@ static void variant_launch(cudaStream_t st, int mode, const GemmArgs& a, int til
   dim3 grid((unsigned)tiles_m, (unsigned)(tiles_n * (NB / BN)));
   if (mode == 0)
     dgemm_nt_kernel<0, BN, WN, BK, ST, MINB><<<grid, 128 * WN, gemm_smem<BN, BK, ST>(), st>>>(a);
-  else
+  else if (mode == 1)
     dgemm_nt_kernel<1, BN, WN, BK, ST, MINB><<<grid, 128 * WN, gemm_smem<BN, BK, ST>(), st>>>(a);
+  else
+    dgemm_nt_kernel<2, BN, WN, BK, ST, MINB><<<grid, 128 * WN, gemm_smem<BN, BK, ST>(), st>>>(a);
 }
 
 int gemm_init(Handle* h) {

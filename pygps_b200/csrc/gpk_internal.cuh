@@ -95,12 +95,16 @@ struct Handle {
   double* dW = nullptr; int64_t capW = 0;
   double* dP = nullptr; int64_t capP = 0;
   double* dTmp = nullptr; int64_t capTmp = 0;
+  double* dXtmp = nullptr; int64_t capXtmp = 0;
   // standalone potrf state
   int64_t pn = 0;
   // fitc state
   bool has_fitc = false; int64_t M = 0, Mp = 0;
   double* dUin = nullptr; double* dUs = nullptr; double* dLpost = nullptr; double* dAlphaU = nullptr;
-  int64_t capUin = 0;
+  int64_t capUin = 0, capUs = 0, capLpost = 0, capAlphaU = 0;
+  double *fKuu = nullptr, *fDinvU = nullptr, *fA2 = nullptr, *fDinv2 = nullptr, *fVt = nullptr, *fVs = nullptr,
+         *fVec = nullptr, *fWt = nullptr;
+  int64_t cKuu = 0, cDinvU = 0, cA2 = 0, cDinv2 = 0, cVt = 0, cVs = 0, cVec = 0, cWt = 0;
 };
 
 #define GPK_CK(h, call)                                                        \
@@ -149,6 +153,13 @@ int gemm_init(Handle* h);
 int diag_init(Handle* h);
 
 int ensure(Handle* h, double** p, int64_t* cap, int64_t need_elems);
+int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::vector<double>& scale, int* divide,
+               double* premul, double* sf2);
+void stats_begin(Handle* h);
+int check_handle(gpk_handle hh, Handle** out);
+int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A, int64_t lda,
+                  const double* Dinv, int T);
+int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv);
 int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info,
                  double* b_fwd /*nullable: fused forward solve in/out*/, double* z_out);
 

@@ -1,0 +1,87 @@
+"""inf.FITC_Exact / GPR_FITC on the GPU against the reference's frozen outputs (tests/golden)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import pygps_b200 as pg            # noqa: E402
+from oracle import gp_oracle as go  # noqa: E402
+
+TOL = 1e-6
+
+
+def rel(a, b):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def _check(m, g, tag, x, y, xs, L_tol=1e-5):
+    nlZ, dn, post = m.getPosterior(x, y)
+    ref = float(g[tag + "_nlZ"])
+    assert type(nlZ) is np.float64 and abs(nlZ - ref) < 1e-8 * abs(ref), (tag, nlZ, ref)
+    M = m.u.shape[0]
+    assert post.alpha.shape == (M, 1) and post.L.shape == (M, M) and post.sW.shape == (x.shape[0], 1)
+    assert rel(post.alpha, g[tag + "_alpha"]) < 1e-5, (tag, "alpha", rel(post.alpha, g[tag + "_alpha"]))
+    if tag + "_L" in g.files:
+        assert rel(post.L, g[tag + "_L"]) < L_tol, (tag, "L", rel(post.L, g[tag + "_L"]))
+    for got, key in ((dn.cov, "_dcov"), (dn.lik, "_dlik"), (dn.mean, "_dmean")):
+        r = g[tag + key]
+        assert len(got) == len(r)
+        if len(r):
+            assert rel(got, r) < 1e-5, (tag, key, got, r)
+    out = m.predict(xs)
+    for name, v in zip(("ym", "ys2", "fm", "fs2"), out[:4]):
+        assert rel(v, g[tag + "_" + name]) < 1e-5, (tag, name, rel(v, g[tag + "_" + name]))
+
+
+def test_kat4_reference_fixture(golden):
+    g = golden("kat_regression")
+    m = pg.GPR_FITC()
+    m.setPrior(kernel=pg.cov.RBF(), inducing_points=g["u"])
+    _check(m, g, "kat4", g["x"], g["y"], g["xs"])
+    assert abs(m.nlZ - 179.399011418159) < 1e-7
+    m = pg.GPR_FITC()
+    m.setData(g["x"], g["y"])                      # default 5-point grid + Const mean
+    assert np.allclose(m.u, g["kat4b_u"])
+    _check(m, g, "kat4b", g["x"], g["y"], g["xs"])
+
+
+@pytest.mark.parametrize("N,M", [(2000, 100), (4096, 256)])
+def test_c4_family_synthetic(golden, N, M):
+    g = golden("synthetic")
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((N, 8))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    U = rng.standard_normal((M, 8))
+    Xs = np.random.default_rng(1).standard_normal((300, 8))
+    m = pg.GPR_FITC()
+    m.setPrior(kernel=pg.cov.RBF(np.log(2.0), 0.0), inducing_points=U)
+    _check(m, g, "c4_%d_%d" % (N, M), X, y, Xs, L_tol=1e-4)
+
+
+def test_fitc_other_kernels_against_oracle():
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((600, 3)); y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((600, 1))
+    U = rng.standard_normal((40, 3)); Xs = rng.standard_normal((50, 3))
+    for kern, spec in ((pg.cov.RBFard(log_ell_list=[0.2, -0.1, 0.4], log_sigma=0.3), ("rbfard", [0.2, -0.1, 0.4, 0.3])),
+                       (pg.cov.Matern(0.3, 5, 0.1), ("matern", [0.3, 0.1], 5))):
+        m = pg.GPR_FITC()
+        m.setPrior(kernel=kern, inducing_points=U)
+        nlZ, dn, post = m.getPosterior(X, y)
+        rpost, rnlZ, rdn = go.fitc_evaluate(("zero",), spec, U, np.log(0.1), X, y, 3)
+        assert abs(nlZ - rnlZ) < 1e-8 * abs(rnlZ)
+        assert rel(dn.cov, rdn["cov"]) < 1e-5 and rel(dn.lik, rdn["lik"]) < 1e-5
+        out = m.predict(Xs)
+        ro = go.predict(("zero",), spec, np.log(0.1), X, rpost, Xs, xu=U)
+        assert rel(out[0], ro[0]) < 1e-5 and rel(out[1], ro[1]) < 1e-5
+
+
+def test_fitc_shape_contract_of_the_reference():
+    """Testing/unit_test_inf.py:43-56 (FITC: post.L is (nu,nu))."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((20, 2)); y = rng.standard_normal((20, 1)); u = rng.standard_normal((5, 2))
+    post, nlZ, dnlZ = pg.inf.FITC_Exact().evaluate(pg.mean.Zero(), pg.cov.RBF().fitc(u), pg.lik.Gauss(), x, y, nargout=3)
+    assert post.alpha.shape[0] == 5 and post.L.shape == (5, 5) and post.sW.shape == (20, 1)
+    assert type(nlZ) is np.float64 and all(type(v) is np.float64 for v in dnlZ.cov + dnlZ.lik)
+    with pytest.raises(Exception):
+        pg.inf.FITC_Exact().evaluate(pg.mean.Zero(), pg.cov.RBF(), pg.lik.Gauss(), x, y, nargout=2)
