@@ -102,6 +102,15 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------- CPU legs
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline must get every host core it can use."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def _blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -121,6 +130,7 @@ def cpu_port_measure(n_full, d, per_step_budget_s, steps=1, warmup=0):
     Returns (evals/s at n_full, seconds per step at the sample size, sample description, cores)."""
     from oracle import gp_oracle as go
     from pygps_b200._dist import replica_hyp
+    _use_all_host_threads()
 
     def one(X, y, k):
         h, sn = replica_hyp(k, 0)
@@ -339,8 +349,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_FULL)
-    ap.add_argument("--d", type=int, default=D_FULL)
+    ap.add_argument("--problem-n", dest="n", type=int, default=N_FULL)
+    ap.add_argument("--problem-d", dest="d", type=int, default=D_FULL)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-der", action="store_true", help="skip the derivative-rate side measurement")
     args = ap.parse_args()

@@ -136,6 +136,20 @@ int gpk_fitc_eval(gpk_handle h, int kind, int matern_d,
 /* FITC branch of GP.predict (Core/gp.py:418): fs2 = kss + colsum(Ks*(L Ks)). */
 int gpk_fitc_predict(gpk_handle h, const double* Xs, int64_t ns, double* ks_alpha, double* fs2);
 
+/* ---- one evaluation sharded over the GPUs of a box (BASELINE config 3) ---- *
+ * One process per GPU.  The matrix K/sn2+I is distributed by block columns (block-cyclic, block 128); each step
+ * broadcasts the solved panel over NVLink with NCCL (loaded at run time from `nccl_path`, e.g. the libnccl.so.2
+ * PyTorch ships); trailing updates, the K build and the substitutions run where the columns live.
+ *   gpk_dist_unique_id: rank 0 obtains the 128-byte NCCL id; the caller distributes it (torch.distributed).
+ *   gpk_dist_init:      collective; binds the handle to (rank, world).  world == 1 needs no NCCL.
+ *   gpk_exact_eval_dist: collective counterpart of gpk_exact_eval without derivatives; same X (gpk_set_data),
+ *                       hyper-parameters and y-m on every rank; every rank receives nlZ and the full alpha.    */
+int gpk_dist_unique_id(const char* nccl_path, char* out128);
+int gpk_dist_init(gpk_handle h, const char* nccl_path, int rank, int world, const char* id128);
+int gpk_dist_finalize(gpk_handle h);
+int gpk_exact_eval_dist(gpk_handle h, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
+                        const double* ymm, double* nlZ, double* alpha);
+
 /* ---- measurement helpers (bench.py / tests only) ------------------------ */
 /* fp64 tensor-pipe micro-benchmark: shape 0=m8n8k4 1=m16n8k4 2=m16n8k8
  * 3=m16n8k16 4=DFMA (no tensor pipe); returns TFLOP/s over `iters` inner loops. */

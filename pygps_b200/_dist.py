@@ -24,9 +24,11 @@ class DistCtx(object):
             os.environ.setdefault("MASTER_PORT", "29511")
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
+            kw = {}
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
-            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+                kw["device_id"] = torch.device("cuda", self.local_rank)
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world, **kw)
             self._dist, self._torch, self.backend = dist, torch, backend
 
     def _tensor(self, v):
@@ -50,6 +52,26 @@ class DistCtx(object):
         t = self._tensor(v)
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM)
         return float(t.item())
+
+    def broadcast_bytes(self, payload, nbytes, src=0):
+        """Broadcast a short byte string (the NCCL unique id) from `src` to all ranks."""
+        if self._dist is None:
+            return payload
+        t = self._torch.zeros(nbytes, dtype=self._torch.uint8)
+        if self.rank == src:
+            t = self._torch.frombuffer(bytearray(payload), dtype=self._torch.uint8).clone()
+        if self.backend == "nccl":
+            t = t.cuda(self.local_rank)
+        self._dist.broadcast(t, src=src)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def shard_engine(self, engine):
+        """Bind a libgpk engine to this process group: block-cyclic column sharding over NCCL/NVLink."""
+        uid = None
+        if self.world > 1:
+            uid = self.broadcast_bytes(engine.dist_unique_id() if self.rank == 0 else None, 128)
+        engine.dist_init(self.rank, self.world, uid)
+        return engine
 
     def close(self):
         if self._dist is not None:

@@ -63,6 +63,10 @@ PROTOTYPES = [
     ("gpk_fitc_eval", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, _L, c_double_p, _I,
                            c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     ("gpk_fitc_predict", _I, [_H, c_double_p, _L, c_double_p, c_double_p]),
+    ("gpk_dist_unique_id", _I, [ctypes.c_char_p, ctypes.c_char_p]),
+    ("gpk_dist_init", _I, [_H, ctypes.c_char_p, _I, _I, ctypes.c_char_p]),
+    ("gpk_dist_finalize", _I, [_H]),
+    ("gpk_exact_eval_dist", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, c_double_p, c_double_p]),
     ("gpk_bench_dmma", _I, [_H, _I, _I, _I, c_double_p, c_double_p]),
     ("gpk_bench_syrk", _I, [_H, _L, _I, _I, c_double_p, c_double_p]),
     ("gpk_bench_copy", _I, [_H, _L, _I, c_double_p]),
@@ -236,6 +240,43 @@ class Engine(object):
         rc = self._lib.gpk_predict(self._h, _dp(xs), ns, _dp(ka), _dp(fs2))
         self._check(rc, "gpk_predict")
         return ka, fs2
+
+    # -- one evaluation sharded over several GPUs (one process per GPU) ------------------
+    @staticmethod
+    def nccl_path():
+        """libnccl.so.2 as shipped with PyTorch (resolved without importing torch's CUDA runtime)."""
+        try:
+            import nvidia.nccl
+            base = os.path.dirname(nvidia.nccl.__file__) if getattr(nvidia.nccl, "__file__", None) else \
+                list(nvidia.nccl.__path__)[0]
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+        except Exception:
+            pass
+        return "libnccl.so.2"
+
+    def dist_unique_id(self):
+        buf = ctypes.create_string_buffer(128)
+        rc = self._lib.gpk_dist_unique_id(self.nccl_path().encode(), buf)
+        self._check(rc, "gpk_dist_unique_id")
+        return buf.raw
+
+    def dist_init(self, rank, world, uid=None):
+        rc = self._lib.gpk_dist_init(self._h, self.nccl_path().encode(), rank, world, uid)
+        self._check(rc, "gpk_dist_init")
+        self.rank, self.world = rank, world
+
+    def exact_eval_dist(self, kind, matern_d, hyp, log_sn, ymm):
+        hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+        ymm = np.ascontiguousarray(ymm, dtype=np.float64).reshape(-1)
+        self._retire_factor()
+        alpha = np.empty((ymm.size, 1))
+        nlZ = ctypes.c_double(0.0)
+        rc = self._lib.gpk_exact_eval_dist(self._h, kind, matern_d, _dp(hyp), hyp.size, float(log_sn), _dp(ymm),
+                                           ctypes.byref(nlZ), _dp(alpha))
+        self._check(rc, "gpk_exact_eval_dist")
+        return np.float64(nlZ.value), alpha
 
     # -- FITC -----------------------------------------------------------------
     def fitc_eval(self, kind, matern_d, hyp, log_sn, u, ymm, want_der):

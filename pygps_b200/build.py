@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpk.so")
-SOURCES = ["api.cu", "gemm_nt.cu", "potrf_diag.cu", "kbuild.cu", "misc.cu", "fitc.cu"]
+SOURCES = ["api.cu", "gemm_nt.cu", "potrf_diag.cu", "kbuild.cu", "misc.cu", "fitc.cu", "dist.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libgpk.so")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -169,7 +169,7 @@ int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::
 static int free_all(Handle* h) {
   double** ptrs[] = {&h->dX, &h->dXs, &h->dScale, &h->dA, &h->dDinv, &h->dB, &h->dZ, &h->dAlpha, &h->dR, &h->dScal,
                      &h->dU, &h->dW, &h->dP, &h->dTmp, &h->dUin, &h->dUs, &h->dLpost, &h->dAlphaU,
-                     &h->fKuu, &h->fDinvU, &h->fA2, &h->fDinv2, &h->fVt, &h->fVs, &h->fVec, &h->fWt, &h->dXtmp};
+                     &h->fKuu, &h->fDinvU, &h->fA2, &h->fDinv2, &h->fVt, &h->fVs, &h->fVec, &h->fWt, &h->dXtmp, &h->gA, &h->gDinv, &h->gPack, &h->gVec};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -177,7 +177,7 @@ static int free_all(Handle* h) {
   if (h->dInfo) cudaFree(h->dInfo);
   h->dInfo = nullptr;
   h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = 0;
-  h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->capUs = h->capLpost = h->capAlphaU = 0;
+  h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->cgA = h->cgDinv = h->cgPack = h->cgVec = h->capUs = h->capLpost = h->capAlphaU = 0;
   return 0;
 }
 
@@ -321,6 +321,7 @@ int gpk_destroy(gpk_handle hh) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  gpk_dist_finalize(hh);
   free_all(h);
   for (auto e : h->ev) cudaEventDestroy(e);
   for (auto e : h->prof_ev) cudaEventDestroy(e);

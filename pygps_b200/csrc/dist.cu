@@ -1,0 +1,316 @@
+// dist.cu - one exact-GP evaluation sharded over the GPUs of one box (BASELINE config 3).
+//
+// One process per GPU.  The (np x np) matrix K/sn2+I is distributed by BLOCK COLUMNS, block-cyclic with block
+// 128: rank r owns global column blocks r, r+G, r+2G, ... stored packed, full height.  Each panel (one block
+// column) is therefore local to its owner: diag + TRSM need no communication.  The ONE exchange per step is the
+// broadcast of the solved panel over NVLink (ncclBroadcast); every rank then updates the columns it owns with the
+// same DMMA kernel (GemmArgs::cstride = G maps its packed columns to global ones).  K tiles are built where they
+// live (CovArgs::s_bstride), X is replicated (<= 16 MiB).
+//
+// The forward substitution needs no kernel and no message of its own: y-m rides along as one extra ROW of the matrix
+// (the Cholesky factor of [A b; b' c] carries z' = b'L^-T in its last row), so the panel TRSM and the trailing updates
+// produce z.  The backward substitution is the dot-product form over the owner's local column with the solution
+// block broadcast (1 KiB) per step.
+//
+// NCCL is resolved at run time (dlopen of the libnccl.so.2 PyTorch ships) so libgpk.so has no link-time dependency.
+#include <dlfcn.h>
+#include <cmath>
+#include "gpk_internal.cuh"
+
+namespace gpk {
+
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_get_uid)(nccl_uid*);
+typedef int (*fn_init_rank)(void**, int, nccl_uid, int);
+typedef int (*fn_destroy)(void*);
+typedef int (*fn_bcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*fn_errstr)(int);
+
+static struct {
+  void* lib = nullptr;
+  fn_get_uid get_uid = nullptr;
+  fn_init_rank init_rank = nullptr;
+  fn_destroy destroy = nullptr;
+  fn_bcast bcast = nullptr;
+  fn_allreduce allreduce = nullptr;
+  fn_errstr errstr = nullptr;
+} g_nccl;
+
+constexpr int NCCL_F64 = 8, NCCL_I32 = 2, NCCL_SUM = 0, NCCL_MAX = 2;
+
+static int nccl_load(const char* path) {
+  if (g_nccl.lib) return 0;
+  const char* cands[] = {path, "libnccl.so.2", "libnccl.so"};
+  for (const char* c : cands) {
+    if (!c || !*c) continue;
+    g_nccl.lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return GPK_ERR_STATE;
+  g_nccl.get_uid = (fn_get_uid)dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.init_rank = (fn_init_rank)dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.bcast = (fn_bcast)dlsym(g_nccl.lib, "ncclBroadcast");
+  g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.bcast || !g_nccl.allreduce) return GPK_ERR_STATE;
+  return 0;
+}
+
+#define NCCL_CK(h, call)                                                                       \
+  do {                                                                                         \
+    int r__ = (call);                                                                          \
+    if (r__ != 0) {                                                                            \
+      (h)->last_msg = std::string(#call) + ": " + (g_nccl.errstr ? g_nccl.errstr(r__) : "nccl error"); \
+      return GPK_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+// row np of the local columns <- (y-m) of the matching global columns; the other 127 rows of the extra tile row <- 0
+__global__ void fill_aug_kernel(double* __restrict__ A, int64_t ld, int64_t np, int64_t ncols_loc, int G, int r,
+                                const double* __restrict__ ymm, int64_t n) {
+  const int64_t total = ncols_loc * NB;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = k / NB, i = k % NB;           // local column, row within the extra tile row
+    const int64_t gc = (c / NB) * G * NB + (int64_t)r * NB + c % NB;
+    A[np + i + c * ld] = (i == 0 && gc < n) ? ymm[gc] : 0.0;
+  }
+}
+
+constexpr int DT_THREADS = 512;
+constexpr size_t DT_SMEM = size_t(NB) * NB * sizeof(double);
+
+// partial[i][c] = sum_r L[(k+1+i)*128 + r, c] * x[(k+1+i)*128 + r]   for tile i of the owner's local column k
+__global__ void __launch_bounds__(DT_THREADS, 1) bwd_partial_kernel(const double* __restrict__ Acol, int64_t ld,
+                                                                    const double* __restrict__ x, int k,
+                                                                    double* __restrict__ partial) {
+  extern __shared__ __align__(16) double tile[];
+  __shared__ double sx[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)(k + 1 + blockIdx.x) * NB;
+  if (tid < NB) sx[tid] = x[row0 + tid];
+#pragma unroll
+  for (int i = 0; i < (NB * NB / 2) / DT_THREADS; ++i) {
+    const int ch = tid + i * DT_THREADS;
+    const int c = ch >> 6, r = (ch & 63) * 2;
+    unsigned sa = (unsigned)__cvta_generic_to_shared(tile + r + c * NB);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(Acol + row0 + r + (int64_t)c * ld) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  const double v0 = sx[lane], v1 = sx[lane + 32], v2 = sx[lane + 64], v3 = sx[lane + 96];
+  for (int c = warp; c < NB; c += DT_THREADS / 32) {
+    const double* col = tile + c * NB;
+    double s = fma(col[lane], v0, fma(col[lane + 32], v1, fma(col[lane + 64], v2, col[lane + 96] * v3)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) partial[(int64_t)blockIdx.x * NB + c] = s;
+  }
+}
+
+// x_k = Dinv_k^T (z_k - sum_i partial[i]) ; z_k is row `zrow` of the local column block (pitch ld)
+__global__ void __launch_bounds__(NB) bwd_finish_kernel(const double* __restrict__ Acol, int64_t ld, int64_t zrow,
+                                                        const double* __restrict__ Dk, const double* __restrict__ partial,
+                                                        int ntiles, double* __restrict__ xk) {
+  __shared__ double s[NB];
+  const int c = threadIdx.x;
+  double acc = Acol[zrow + (int64_t)c * ld];
+  for (int i = 0; i < ntiles; ++i) acc -= partial[(int64_t)i * NB + c];
+  s[c] = acc;
+  __syncthreads();
+  double o = 0.0;
+  for (int r = c; r < NB; ++r) o = fma(Dk[r + c * NB], s[r], o);   // (Dinv^T s)_c = sum_{r>=c} Dinv[r,c] s_r
+  xk[c] = o;
+}
+
+// alpha = x/sn2 ; res[0] = r'alpha
+__global__ void __launch_bounds__(1024) dist_finish_kernel(const double* __restrict__ x, const double* __restrict__ r,
+                                                           double inv_sn2, int64_t n, double* __restrict__ alpha,
+                                                           double* __restrict__ res) {
+  __shared__ double sh[32];
+  double dot = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double a = x[i] * inv_sn2;
+    alpha[i] = a;
+    dot = fma(r[i], a, dot);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if (lane == 0) sh[warp] = dot;
+  __syncthreads();
+  if (warp == 0) {
+    double t = sh[lane];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) res[0] = t;
+  }
+}
+
+}  // namespace gpk
+
+using namespace gpk;
+
+extern "C" {
+
+int gpk_dist_unique_id(const char* nccl_path, char* out128) {
+  if (!out128) return GPK_ERR_ARG;
+  if (nccl_load(nccl_path) != 0) return GPK_ERR_STATE;
+  nccl_uid id;
+  if (g_nccl.get_uid(&id) != 0) return GPK_ERR_CUDA;
+  std::memcpy(out128, id.internal, 128);
+  return 0;
+}
+
+int gpk_dist_init(gpk_handle hh, const char* nccl_path, int rank, int world, const char* id128) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (world < 1 || rank < 0 || rank >= world) return GPK_ERR_ARG;
+  h->rank = rank; h->world = world;
+  if (world == 1) return 0;
+  if (!id128) return GPK_ERR_ARG;
+  if (nccl_load(nccl_path) != 0) { h->last_msg = "cannot load libnccl.so.2"; return GPK_ERR_STATE; }
+  nccl_uid id;
+  std::memcpy(id.internal, id128, 128);
+  NCCL_CK(h, g_nccl.init_rank(&h->nccl_comm, world, id, rank));
+  GPK_CK(h, cudaFuncSetAttribute(bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_SMEM));
+  return 0;
+}
+
+int gpk_dist_finalize(gpk_handle hh) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (h->nccl_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
+  h->nccl_comm = nullptr;
+  h->world = 1; h->rank = 0;
+  return 0;
+}
+
+// Sharded counterpart of gpk_exact_eval (no derivatives): every rank calls it with the same arguments after
+// gpk_set_data with the same X; every rank gets the same nlZ and the full alpha.
+int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
+                        const double* ymm, double* nlZ, double* alpha) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!h->dX || h->n <= 0) return GPK_ERR_STATE;
+  if (!hyp || !ymm || !nlZ || !alpha) return GPK_ERR_ARG;
+  const int G = h->world, r = h->rank;
+  if (G > 1 && !h->nccl_comm) return GPK_ERR_STATE;
+  const int64_t n = h->n, np = h->np;
+  const int D = h->D, T = (int)(np / NB);
+  const int64_t ld = np + NB;                       // one extra tile row carries y-m
+  const int nloc = (T > r) ? (T - 1 - r) / G + 1 : 0;   // owned block columns
+  std::vector<double> scale;
+  int divide = 0;
+  double premul = 1.0, sf2 = 1.0;
+  GPK_TRY(kind_scale(kind, matern_d, hyp, nhyp, D, scale, &divide, &premul, &sf2));
+  if (D > 1900) return GPK_ERR_ARG;
+  const double sn2 = std::exp(2.0 * log_sn);
+  stats_begin(h);
+  h->has_post = false; h->has_fitc = false; h->pn = 0;
+  cudaStream_t st = h->s_main;
+  GPK_CK(h, cudaFuncSetAttribute(bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_SMEM));
+
+  const int64_t ncl = (int64_t)(nloc > 0 ? nloc : 1) * NB;
+  GPK_TRY(ensure(h, &h->gA, &h->cgA, ld * ncl));
+  GPK_TRY(ensure(h, &h->gDinv, &h->cgDinv, ncl * NB));
+  GPK_TRY(ensure(h, &h->gPack, &h->cgPack, ld * NB));
+  // vectors: x (np) | parts (T) | res (16) | partial (T*NB) | xk staging (NB)
+  GPK_TRY(ensure(h, &h->gVec, &h->cgVec, np + T + 16 + (int64_t)T * NB + NB));
+  double* x = h->gVec;
+  double* parts = x + np;
+  double* res = parts + T;
+  double* partial = res + 16;
+
+  GPK_CK(h, cudaEventRecord(h->t0, st));
+  std::memcpy(h->hPinned, scale.data(), D * sizeof(double));
+  GPK_CK(h, cudaMemcpyAsync(h->dScale, h->hPinned, D * sizeof(double), cudaMemcpyHostToDevice, st));
+  GPK_CK(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), st));
+  GPK_CK(h, cudaMemsetAsync(parts, 0, (size_t)(T + 16) * sizeof(double), st));
+  GPK_CK(h, cudaMemsetAsync(x, 0, (size_t)np * sizeof(double), st));
+  GPK_CK(h, cudaMemsetAsync(h->dR, 0, (size_t)np * sizeof(double), st));
+  GPK_CK(h, cudaMemcpyAsync(h->dR, ymm, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  GPK_TRY(launch_prescale(h, st, h->dX, n, np, D, h->dScale, divide, premul, h->dXs));
+  if (nloc > 0) {
+    CovArgs c{};
+    c.F = h->dXs; c.S = h->dXs; c.out = h->gA; c.ld = ld;
+    c.nF = n; c.nS = n; c.pF = np; c.pS = (int64_t)nloc * NB; c.D = D;
+    c.kind = kind; c.matern_d = matern_d; c.epi = EPI_COV;
+    c.sf2 = sf2; c.scale = 1.0 / sn2; c.diag_add = 1.0;
+    c.same_set = 1; c.lower_only = 1; c.pad_identity = 1;
+    c.s_bstride = G; c.s_boff = r;
+    GPK_TRY(launch_cov(h, st, c));
+    fill_aug_kernel<<<148, 256, 0, st>>>(h->gA, ld, np, (int64_t)nloc * NB, G, r, h->dR, n);
+    h->stats.launches++;
+  }
+  GPK_CK(h, cudaEventRecord(h->t1, st));
+
+  // ---- right-looking factorisation, one panel broadcast per step ---------------------------------------------
+  for (int k = 0; k < T; ++k) {
+    const int o = k % G, lk = k / G;
+    const int rem = T - k;                          // tile rows below the diagonal block, incl. the extra row
+    const int64_t prow = (int64_t)rem * NB;         // packed panel height
+    if (r == o) {
+      double* Akk = h->gA + (int64_t)k * NB + (int64_t)lk * NB * ld;
+      double* Dk = h->gDinv + (int64_t)lk * NB * NB;
+      GPK_TRY(launch_diag(h, st, Akk, ld, Dk, parts + k, h->dInfo, k * NB));
+      GemmArgs t{};
+      t.A = Akk + NB; t.B = Dk; t.C = Akk + NB; t.lda = ld; t.ldb = NB; t.ldc = ld; t.K = NB; t.tri = 0;
+      GPK_TRY(launch_gemm_nt(h, st, 0, t, rem, 1));
+      GPK_CK(h, cudaMemcpy2DAsync(h->gPack, (size_t)prow * sizeof(double), Akk + NB, (size_t)ld * sizeof(double),
+                                  (size_t)prow * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+    }
+    if (G > 1) NCCL_CK(h, g_nccl.bcast(h->gPack, h->gPack, (size_t)prow * NB, NCCL_F64, o, h->nccl_comm, st));
+    // update the owned columns j > k:  C[:, j] -= P[rows >= j] * P[j]^T
+    const int j0 = k + 1 + (((r - (k + 1)) % G) + G) % G;
+    if (j0 < T) {
+      const int ncols = (T - 1 - j0) / G + 1;
+      GemmArgs u{};
+      u.A = h->gPack; u.B = h->gPack + (int64_t)(j0 - (k + 1)) * NB;
+      u.C = h->gA + (int64_t)(k + 1) * NB + (int64_t)(j0 / G) * NB * ld;
+      u.lda = prow; u.ldb = prow; u.ldc = ld; u.K = NB; u.tri = 1; u.ti_off = k + 1; u.tj_off = j0; u.cstride = G;
+      GPK_TRY(launch_gemm_nt(h, st, 1, u, rem, ncols));
+    }
+  }
+  GPK_CK(h, cudaEventRecord(h->t2, st));
+
+  // ---- backward substitution: x_k = Dinv_k^T (z_k - sum_{i>k} L[i,k]^T x_i), x_k broadcast ------------------------
+  for (int k = T - 1; k >= 0; --k) {
+    const int o = k % G, lk = k / G;
+    double* xk = x + (int64_t)k * NB;
+    if (r == o) {
+      const double* Acol = h->gA + (int64_t)lk * NB * ld;
+      const int nt = T - 1 - k;
+      if (nt > 0) bwd_partial_kernel<<<nt, DT_THREADS, DT_SMEM, st>>>(Acol, ld, x, k, partial);
+      bwd_finish_kernel<<<1, NB, 0, st>>>(Acol, ld, np, h->gDinv + (int64_t)lk * NB * NB, partial, nt, xk);
+      h->stats.launches += 2;
+    }
+    if (G > 1) NCCL_CK(h, g_nccl.bcast(xk, xk, NB, NCCL_F64, o, h->nccl_comm, st));
+  }
+  // log-det parts and info: every entry has exactly one non-zero contributor
+  if (G > 1) {
+    NCCL_CK(h, g_nccl.allreduce(parts, parts, (size_t)T, NCCL_F64, NCCL_SUM, h->nccl_comm, st));
+    NCCL_CK(h, g_nccl.allreduce(h->dInfo, h->dInfo, 1, NCCL_I32, NCCL_MAX, h->nccl_comm, st));
+  }
+  dist_finish_kernel<<<1, 1024, 0, st>>>(x, h->dR, 1.0 / sn2, np, h->dAlpha, res);
+  GPK_TRY(launch_sum_parts(h, st, parts, T, res + 1));
+  GPK_CK(h, cudaGetLastError());
+  GPK_CK(h, cudaEventRecord(h->t3, st));
+  GPK_CK(h, cudaMemcpyAsync(h->hPinned, res, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaMemcpyAsync(h->hPinned + 2048, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaMemcpyAsync(alpha, h->dAlpha, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->t0, h->t3); h->stats.total_ms = ms;
+  cudaEventElapsedTime(&ms, h->t0, h->t1); h->stats.kbuild_ms = ms;
+  cudaEventElapsedTime(&ms, h->t1, h->t2); h->stats.potrf_ms = ms;
+  cudaEventElapsedTime(&ms, h->t2, h->t3); h->stats.solve_ms = ms;
+  h->stats.h2d_bytes = (n + D) * (int64_t)sizeof(double);
+  h->stats.d2h_bytes = (n + 2) * (int64_t)sizeof(double) + 4;
+  const int info = *reinterpret_cast<int*>(h->hPinned + 2048);
+  *nlZ = h->hPinned[0] / 2.0 + h->hPinned[1] + (double)n * std::log(2.0 * M_PI * sn2) / 2.0;
+  if (info != 0) return info;
+  return 0;
+}
+
+}  // extern "C"

@@ -62,7 +62,10 @@ __global__ void __launch_bounds__(128 * WN, MINB) dgemm_nt_kernel(const GemmArgs
 
   const int ti = blockIdx.x, tjs = blockIdx.y;          // tjs counts BN-wide column tiles
   const int gi = ti + p.ti_off;
-  const int gcol0 = tjs * BN + p.tj_off * NB;           // first global column (relative to the tile grid origin)
+  constexpr int SUBS = NB / BN;                         // BN-wide sub-tiles per 128-wide column tile
+  const int tc = tjs / SUBS, sub = tjs % SUBS;
+  const int cs = (p.cstride > 1) ? p.cstride : 1;
+  const int gcol0 = (p.tj_off + tc * cs) * NB + sub * BN;   // first global column of this tile
   const int grow0 = gi * NB;
   if (p.tri && grow0 + NB - 1 < gcol0) return;          // tile entirely above the diagonal
   const bool diag_tile = (p.tri != 0) && (gcol0 + BN - 1 > grow0);   // crosses the diagonal
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(128 * WN, MINB) dgemm_nt_kernel(const GemmArgs
   const int g = lane >> 2, t = lane & 3;
 
   const double* __restrict__ Ag = p.A + (int64_t)ti * NB;
-  const double* __restrict__ Bg = p.B + (int64_t)tjs * BN;
+  const double* __restrict__ Bg = p.B + (int64_t)(tc * cs) * NB + sub * BN;
   double* __restrict__ Cg = p.C + (int64_t)ti * NB + (int64_t)tjs * BN * p.ldc;
 
   const int kbeg = (p.tri == 2) ? gi * NB : 0;

@@ -35,6 +35,8 @@ struct GemmArgs {
   int tj_off;       // global tile index of grid column 0
   int tri;          // 0: all tiles; 1: only gi>=gj, diagonal tiles store row>=col;
                     // 2: as 1, and the contraction starts at k = gi*NB (U*U^T of an upper-triangular U)
+  int cstride;      // block-cyclic columns (multi-GPU): grid column tile tc is GLOBAL column tile tj_off + tc*cstride;
+                    // B rows advance by cstride*NB per tc while C columns stay packed.  0/1 = contiguous.
 };
 
 enum CovEpi { EPI_COV = 0, EPI_DER_ELL = 1, EPI_DER_SF = 2, EPI_DER_ARD = 3 };
@@ -57,6 +59,8 @@ struct CovArgs {
   int same_set;     // F and S are the same point set (train mode): f==s is the diagonal
   int lower_only;   // skip tiles entirely above the diagonal (f-tile < s-tile); zero strict upper inside diagonal tiles
   int pad_identity; // padded diagonal entries (f==s>=nF) get 1.0 instead of 0.0
+  int s_bstride;    // block-cyclic slow index (multi-GPU): local s maps to the GLOBAL point
+  int s_boff;       //   (s/128)*s_bstride*128 + s_boff*128 + s%128 ; 0 = identity.  nS bounds the global index.
 };
 
 // ---- handle ---------------------------------------------------------------
@@ -98,6 +102,12 @@ struct Handle {
   double* dXtmp = nullptr; int64_t capXtmp = 0;
   // standalone potrf state
   int64_t pn = 0;
+  // multi-GPU (block-cyclic columns over NCCL); see dist.cu
+  void* nccl_comm = nullptr; int rank = 0, world = 1;
+  double* gA = nullptr; int64_t cgA = 0;        // local columns of the (np+128) x np augmented matrix
+  double* gDinv = nullptr; int64_t cgDinv = 0;  // inverses of the owned diagonal blocks
+  double* gPack = nullptr; int64_t cgPack = 0;  // packed panel being broadcast
+  double* gVec = nullptr; int64_t cgVec = 0;
   // fitc state
   bool has_fitc = false; int64_t M = 0, Mp = 0;
   double* dUin = nullptr; double* dUs = nullptr; double* dLpost = nullptr; double* dAlphaU = nullptr;

@@ -65,10 +65,12 @@ __global__ void __launch_bounds__(256) cov_kernel(const CovArgs a) {
   __shared__ double Fs[CDK][CT + 1];
   __shared__ double Ss[CDK][CT + 1];
   const int bf = blockIdx.x, bs = blockIdx.y;
-  if (a.lower_only && bf < bs) return;
   const int tid = threadIdx.x;
   const int tf = tid & 15, ts = tid >> 4;
   const int64_t f0 = (int64_t)bf * CT, s0 = (int64_t)bs * CT;
+  // global index of the tile's first slow point (block-cyclic column ownership on multi-GPU runs)
+  const int64_t gs0 = (a.s_bstride > 0) ? (s0 / NB) * a.s_bstride * NB + (int64_t)a.s_boff * NB + s0 % NB : s0;
+  if (a.lower_only && f0 + CT - 1 < gs0) return;
 
   double acc[4][4];
   double accd[4][4];
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(256) cov_kernel(const CovArgs a) {
       double vf = 0.0, vs = 0.0;
       if (d < dc) {
         if (f0 + p < a.nF) vf = a.F[(f0 + p) * a.D + d0 + d];
-        if (s0 + p < a.nS) vs = a.S[(s0 + p) * a.D + d0 + d];
+        if (gs0 + p < a.nS) vs = a.S[(gs0 + p) * a.D + d0 + d];
       }
       Fs[d][p] = vf;
       Ss[d][p] = vs;
@@ -112,18 +114,19 @@ __global__ void __launch_bounds__(256) cov_kernel(const CovArgs a) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int64_t s = s0 + ts * 4 + j;
+    const int64_t gs = gs0 + ts * 4 + j;
     if (s >= a.pS) continue;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int64_t f = f0 + tf + 16 * i;
       if (f >= a.pF) continue;
       double v;
-      if (f < a.nF && s < a.nS) {
+      if (f < a.nF && gs < a.nS) {
         v = cov_value(a, acc[i][j], accd[i][j]) * a.scale;
-        if (a.same_set && f == s) v += a.diag_add;
-        if (a.lower_only && f < s) v = 0.0;
+        if (a.same_set && f == gs) v += a.diag_add;
+        if (a.lower_only && f < gs) v = 0.0;
       } else {
-        v = (a.pad_identity && f == s) ? 1.0 : 0.0;
+        v = (a.pad_identity && f == gs) ? 1.0 : 0.0;
       }
       a.out[f + s * a.ld] = v;
     }

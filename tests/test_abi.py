@@ -35,8 +35,10 @@ def test_binding_covers_the_header():
 
 def test_no_torch_or_python_types_in_signatures():
     text = open(os.path.join(ROOT, "include", "gpk.h")).read()
-    assert "torch" not in text.lower().replace("pytorch", "") and "PyObject" not in text
     assert 'extern "C"' in text
+    decls = re.sub(r"/\*.*?\*/", "", text, flags=re.S)      # declarations only, comments stripped
+    for banned in ("torch", "at::", "PyObject", "Tensor", "std::"):
+        assert banned not in decls, banned
 
 
 def test_version_and_errors_need_no_gpu(lib):
