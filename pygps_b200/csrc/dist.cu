@@ -214,7 +214,6 @@ int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp
   const int64_t ncl = (int64_t)(nloc > 0 ? nloc : 1) * NB;
   GPK_TRY(ensure(h, &h->gA, &h->cgA, ld * ncl));
   GPK_TRY(ensure(h, &h->gDinv, &h->cgDinv, ncl * NB));
-  GPK_TRY(ensure(h, &h->gPack, &h->cgPack, ld * NB));
   // vectors: x (np) | parts (T) | res (16) | partial (T*NB) | xk staging (NB)
   GPK_TRY(ensure(h, &h->gVec, &h->cgVec, np + T + 16 + (int64_t)T * NB + NB));
   double* x = h->gVec;
@@ -245,33 +244,84 @@ int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp
   }
   GPK_CK(h, cudaEventRecord(h->t1, st));
 
-  // ---- right-looking factorisation, one panel broadcast per step ---------------------------------------------
+  // ---- right-looking factorisation, one panel broadcast per step, look-ahead 1 --------------------------------
+  //   s_panel : owner(k): diag(k) -> trsm(k) -> pack into Pack[k%2]
+  //   s_aux   : every rank: ncclBroadcast(k) in step order (the communicator's stream)
+  //   s_main  : every rank: update(k) - the column that becomes panel k+1 first (its owner can then factor it and
+  //             get the next broadcast on the wire while everybody is still updating), then the other owned columns
+  // Pack is double-buffered: broadcast k+1 lands while update k still reads Pack[k%2].
+  GPK_TRY(ensure(h, &h->gPack, &h->cgPack, 2 * ld * NB));
+  {
+    // event pool layout: [0,T) packed  [T,2T) bcast done  [2T,3T) update done  [3T,4T) column ready  [4T] fork
+    while (h->ev.size() < 4 * (size_t)T + 4) {
+      cudaEvent_t e;
+      GPK_CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->ev.push_back(e);
+    }
+  }
+  cudaEvent_t* ev_packed = h->ev.data();
+  cudaEvent_t* ev_bcast = h->ev.data() + T;
+  cudaEvent_t* ev_upd = h->ev.data() + 2 * T;
+  cudaEvent_t* ev_col = h->ev.data() + 3 * T;
+  cudaEvent_t ev_fork = h->ev[4 * T];
+  cudaStream_t sp = h->s_panel, sc = h->s_aux;
+  GPK_CK(h, cudaEventRecord(ev_fork, st));
+  GPK_CK(h, cudaStreamWaitEvent(sp, ev_fork, 0));
+  GPK_CK(h, cudaStreamWaitEvent(sc, ev_fork, 0));
   for (int k = 0; k < T; ++k) {
     const int o = k % G, lk = k / G;
     const int rem = T - k;                          // tile rows below the diagonal block, incl. the extra row
     const int64_t prow = (int64_t)rem * NB;         // packed panel height
+    double* pack = h->gPack + (int64_t)(k & 1) * ld * NB;
     if (r == o) {
       double* Akk = h->gA + (int64_t)k * NB + (int64_t)lk * NB * ld;
       double* Dk = h->gDinv + (int64_t)lk * NB * NB;
-      GPK_TRY(launch_diag(h, st, Akk, ld, Dk, parts + k, h->dInfo, k * NB));
+      if (k > 0) GPK_CK(h, cudaStreamWaitEvent(sp, ev_col[k], 0));          // column k has all its updates
+      if (k > 1) GPK_CK(h, cudaStreamWaitEvent(sp, ev_upd[k - 2], 0));      // Pack[k%2] no longer read
+      GPK_TRY(launch_diag(h, sp, Akk, ld, Dk, parts + k, h->dInfo, k * NB));
       GemmArgs t{};
       t.A = Akk + NB; t.B = Dk; t.C = Akk + NB; t.lda = ld; t.ldb = NB; t.ldc = ld; t.K = NB; t.tri = 0;
-      GPK_TRY(launch_gemm_nt(h, st, 0, t, rem, 1));
-      GPK_CK(h, cudaMemcpy2DAsync(h->gPack, (size_t)prow * sizeof(double), Akk + NB, (size_t)ld * sizeof(double),
-                                  (size_t)prow * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+      GPK_TRY(launch_gemm_nt(h, sp, 0, t, rem, 1));
+      GPK_CK(h, cudaMemcpy2DAsync(pack, (size_t)prow * sizeof(double), Akk + NB, (size_t)ld * sizeof(double),
+                                  (size_t)prow * sizeof(double), NB, cudaMemcpyDeviceToDevice, sp));
+      GPK_CK(h, cudaEventRecord(ev_packed[k], sp));
     }
-    if (G > 1) NCCL_CK(h, g_nccl.bcast(h->gPack, h->gPack, (size_t)prow * NB, NCCL_F64, o, h->nccl_comm, st));
+    if (G > 1) {
+      if (r == o) GPK_CK(h, cudaStreamWaitEvent(sc, ev_packed[k], 0));
+      else if (k > 1) GPK_CK(h, cudaStreamWaitEvent(sc, ev_upd[k - 2], 0));  // receive buffer free
+      NCCL_CK(h, g_nccl.bcast(pack, pack, (size_t)prow * NB, NCCL_F64, o, h->nccl_comm, sc));
+      GPK_CK(h, cudaEventRecord(ev_bcast[k], sc));
+      GPK_CK(h, cudaStreamWaitEvent(st, ev_bcast[k], 0));
+    } else {
+      GPK_CK(h, cudaStreamWaitEvent(st, ev_packed[k], 0));
+    }
     // update the owned columns j > k:  C[:, j] -= P[rows >= j] * P[j]^T
     const int j0 = k + 1 + (((r - (k + 1)) % G) + G) % G;
-    if (j0 < T) {
-      const int ncols = (T - 1 - j0) / G + 1;
+    int jstart = j0;
+    if (j0 == k + 1 && j0 < T) {
+      // this rank owns the next panel: bring that one column up to date first
       GemmArgs u{};
-      u.A = h->gPack; u.B = h->gPack + (int64_t)(j0 - (k + 1)) * NB;
-      u.C = h->gA + (int64_t)(k + 1) * NB + (int64_t)(j0 / G) * NB * ld;
+      u.A = pack; u.B = pack; u.C = h->gA + (int64_t)(k + 1) * NB + (int64_t)(j0 / G) * NB * ld;
       u.lda = prow; u.ldb = prow; u.ldc = ld; u.K = NB; u.tri = 1; u.ti_off = k + 1; u.tj_off = j0; u.cstride = G;
+      GPK_TRY(launch_gemm_nt(h, st, 1, u, rem, 1));
+      GPK_CK(h, cudaEventRecord(ev_col[k + 1], st));
+      jstart = j0 + G;
+    }
+    if (jstart < T) {
+      const int ncols = (T - 1 - jstart) / G + 1;
+      GemmArgs u{};
+      u.A = pack; u.B = pack + (int64_t)(jstart - (k + 1)) * NB;
+      u.C = h->gA + (int64_t)(k + 1) * NB + (int64_t)(jstart / G) * NB * ld;
+      u.lda = prow; u.ldb = prow; u.ldc = ld; u.K = NB; u.tri = 1; u.ti_off = k + 1; u.tj_off = jstart; u.cstride = G;
       GPK_TRY(launch_gemm_nt(h, st, 1, u, rem, ncols));
     }
+    GPK_CK(h, cudaEventRecord(ev_upd[k], st));
   }
+  // join the helper streams
+  GPK_CK(h, cudaEventRecord(ev_fork, sp));
+  GPK_CK(h, cudaStreamWaitEvent(st, ev_fork, 0));
+  GPK_CK(h, cudaEventRecord(ev_fork, sc));
+  GPK_CK(h, cudaStreamWaitEvent(st, ev_fork, 0));
   GPK_CK(h, cudaEventRecord(h->t2, st));
 
   // ---- backward substitution: x_k = Dinv_k^T (z_k - sum_{i>k} L[i,k]^T x_i), x_k broadcast ------------------------
