@@ -147,6 +147,13 @@ __global__ void __launch_bounds__(1024) dist_finish_kernel(const double* __restr
   }
 }
 
+// sum-all-reduce of a device buffer over the handle's communicator (no-op on one rank); used by fitc.cu
+int dist_allreduce_sum(Handle* h, double* buf, size_t count, cudaStream_t st) {
+  if (h->world <= 1 || !h->nccl_comm) return 0;
+  NCCL_CK(h, g_nccl.allreduce(buf, buf, count, NCCL_F64, NCCL_SUM, h->nccl_comm, st));
+  return 0;
+}
+
 }  // namespace gpk
 
 using namespace gpk;

@@ -6,6 +6,10 @@
 //   A2 = I + V diag(1/g) V'  -> SYRK over n after a transpose-and-scale        (Vs = diag(g^-1/2) V, M x n)
 //   dnlZ: B = iKuu Ku, W = Lu^-1 (V/g), R = 2 dKu - dKuu B, R W', B W'         -> GEMMs on the same layouts
 // Ku is never kept: its storage becomes V.  The two M x M factorisations reuse potrf_device.
+//
+// Multi-GPU (BASELINE config 4): after gpk_dist_init the data points are SHARDED over the ranks (each rank passes its
+// own rows of X and y-m); U, Kuu, Luu are replicated.  The exchanges are sum-all-reduces of the M x M SYRK partial, a
+// few M-vectors and scalars; the M x M tail (Lu, alpha, post.L) is computed redundantly on every rank.
 #include <cmath>
 #include "gpk_internal.cuh"
 
@@ -196,6 +200,14 @@ __global__ void __launch_bounds__(1024) fitc_hyp_scalars_kernel(const double* wv
   }
 }
 
+__global__ void res_n_kernel(double* res, double n) { if (threadIdx.x == 0) { res[6] = n; res[7] = 0.0; } }
+
+// X[i] *= s for i in [0,count)  (used to keep rank-replicated scalars from being summed G times)
+__global__ void scale_small_kernel(double* __restrict__ X, int count, double s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) X[i] *= s;
+}
+
 static inline int grid1(int64_t total, int bs = 256) {
   int64_t b = (total + bs - 1) / bs;
   if (b > 148 * 32) b = 148 * 32;
@@ -323,20 +335,30 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
   // 5. Vs = diag(g^-1/2) V  (Mp x np)
   GPK_TRY(transpose_scale(h, st, h->fVt, np, np, Mp, rs, h->fVs, Mp));
   // 6. A2 = I + Vs Vs'  (lower)                                                   :417
-  GPK_TRY(launch_set_identity(h, st, h->fA2, Mp, Mp, Mp));
+  const bool sharded = (h->world > 1 && h->nccl_comm);
+  if (!sharded || h->rank == 0) GPK_TRY(launch_set_identity(h, st, h->fA2, Mp, Mp, Mp));
+  else GPK_CK(h, cudaMemsetAsync(h->fA2, 0, (size_t)Mp * Mp * sizeof(double), st));
   {
     GemmArgs a{};
     a.A = h->fVs; a.B = h->fVs; a.C = h->fA2; a.lda = Mp; a.ldb = Mp; a.ldc = Mp; a.K = (int)np; a.tri = 1;
     GPK_TRY(launch_gemm_nt(h, st, 2, a, Tm, Tm));
   }
+  GPK_TRY(dist_allreduce_sum(h, h->fA2, (size_t)Mp * Mp, st));          // the one big exchange: M x M partial
   // 7. Lu
   GPK_TRY(potrf_device(h, h->fA2, Mp, h->fDinv2, parts2, h->dInfo + 1, nullptr, nullptr));
   // 8. be = Lu^-1 (V r/sqrt(g)) = Lu^-1 (Vs r)                                    :419
   GPK_TRY(launch_rowdot(h, st, h->fVs, Mp, Mp, np, r, 0, 1.0, 0.0, part, nsplit, tv, Mp));
+  GPK_TRY(dist_allreduce_sum(h, tv, (size_t)Mp, st));
   GPK_CK(h, cudaMemcpyAsync(wk, tv, (size_t)Mp * sizeof(double), cudaMemcpyDeviceToDevice, st));
   GPK_TRY(vec_fwd(h, st, h->fA2, Mp, h->fDinv2, wk, be, Tm));
   // 9. scalars of nlZ                                                             :428
   fitc_reduce_kernel<<<1, 1024, 0, st>>>(g, n, r, n, be, Mp, parts2, Tm, nullptr, nullptr, 0, res);
+  if (sharded) {
+    // res[0]=sum log g and res[1]=r'r are sums over the LOCAL data; res[2]=be'be and res[3]=logdet Lu are replicated
+    res_n_kernel<<<1, 32, 0, st>>>(res, (double)n);                      // res[6] = local n
+    if (h->rank != 0) scale_small_kernel<<<1, 32, 0, st>>>(res + 2, 2, 0.0);
+    GPK_TRY(dist_allreduce_sum(h, res, 8, st));
+  }
   // 10. post.alpha = Luu^-T Lu^-T be                                              :422
   GPK_CK(h, cudaMemcpyAsync(wk, be, (size_t)Mp * sizeof(double), cudaMemcpyDeviceToDevice, st));
   GPK_TRY(vec_bwd(h, st, h->fA2, Mp, h->fDinv2, wk, x1, Tm));
@@ -384,6 +406,7 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
     }
     // w = B al                                                                           :433
     coldot_kernel<<<(unsigned)Mp, 256, 0, st>>>(Bt, np, np, al, nullptr, wv);
+    GPK_TRY(dist_allreduce_sum(h, wv, (size_t)Mp, st));
     // W = Lu^-1 (V/g)   ->   Wt = diag(1/g) Vt * Lu^-T                                    :434
     rowscale_kernel<<<grid1(np * Mp), 256, 0, st>>>(h->fVt, np, np, Mp, rs, Wt);
     rowscale_kernel<<<grid1(np * Mp), 256, 0, st>>>(Wt, np, np, Mp, rs, Wt);
@@ -398,6 +421,7 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
       GemmArgs a{};
       a.A = Bm; a.B = Wm; a.C = h->dTmp; a.lda = Mp; a.ldb = Mp; a.ldc = Mp; a.K = (int)np; a.tri = 0;
       GPK_TRY(launch_gemm_nt(h, st, 0, a, Tm, Tm));
+      GPK_TRY(dist_allreduce_sum(h, h->dTmp, (size_t)Mp * Mp, st));        // Q = B W' summed over all data shards
       GemmArgs q{};
       q.A = Wt; q.B = h->dTmp; q.C = Gt; q.lda = np; q.ldb = Mp; q.ldc = np; q.K = (int)Mp; q.tri = 0;
       GPK_TRY(launch_gemm_nt(h, st, 0, q, Tn, Tm));
@@ -444,6 +468,14 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
       GPK_CK(h, cudaGetLastError());
     }
     nres = 24 + 8 * nhyp;
+    if (sharded) {
+      // every scalar from res[8] on is a sum over local data EXCEPT the w'(dKuu w) entries (slot 0 of each 8-block)
+      if (h->rank != 0) {
+        scale_small_kernel<<<1, 32, 0, st>>>(res + 16, 1, 0.0);
+        for (int ii = 0; ii < nhyp; ++ii) scale_small_kernel<<<1, 32, 0, st>>>(res + 24 + 8 * ii, 1, 0.0);
+      }
+      GPK_TRY(dist_allreduce_sum(h, res + 8, (size_t)(nres - 8), st));
+    }
     GPK_CK(h, cudaMemcpyAsync(al_out, al, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
   GPK_CK(h, cudaEventRecord(h->t4, st));
@@ -465,7 +497,8 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
   const int* infos = reinterpret_cast<const int*>(h->hPinned + 2048);
   const double* R = h->hPinned;
   // nlZ = sum(log diag Lu) + (sum(log g) + n log 2pi + r'r - be'be)/2                    Core/inf.py:428
-  *nlZ = R[3] + (R[0] + (double)n * std::log(2.0 * M_PI) + R[1] - R[2]) / 2.0;
+  const double n_total = (h->world > 1 && h->nccl_comm) ? R[6] : (double)n;
+  *nlZ = R[3] + (R[0] + n_total * std::log(2.0 * M_PI) + R[1] - R[2]) / 2.0;
   if (want_der) {
     const double alal = R[9], sumww = R[11], suminvg = R[12];
     for (int ii = 0; ii < nhyp; ++ii) {

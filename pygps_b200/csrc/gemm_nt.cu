@@ -318,7 +318,78 @@ __global__ void __launch_bounds__(512) dmma_peak_kernel(double* out, int iters) 
   if (s == 123.456) out[0] = s;
 }
 
+// shape 5: even warps run DMMA chains, odd warps run DFMA chains: do the two fp64 paths overlap?
+__global__ void __launch_bounds__(512) mixed_peak_kernel(double* out, int iters) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double seed = 1.0 + 1e-9 * lane;
+  if (warp & 1) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = seed * i;
+    const double a = 1.0000001, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) out[0] = s;
+  } else {
+    double c[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[i][q] = 0.0;
+    double a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = seed * 1e-3 * (i + 1);
+    b[0] = seed * 2e-3; b[1] = seed * 3e-3;
+    // same flop count per iteration as the DFMA warps: 16 FMA/lane = 512 flop... DMMA m16n8k8 = 2048 flop/instr
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                     : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3])
+                     : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s += c[i][q];
+    if (s == 123.456) out[0] = s;
+  }
+}
+
 int bench_dmma(Handle* h, int shape, int warps, int iters, double* tflops, double* ms_out) {
+  if (shape == 5) {
+    if (warps < 2 || warps > 16 || iters < 1) return GPK_ERR_ARG;
+    int sms = 0;
+    GPK_CK(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    double* d = nullptr;
+    GPK_CK(h, cudaMalloc(&d, 64));
+    dim3 grid(sms * 2), block(warps * 32);
+    mixed_peak_kernel<<<grid, block, 0, h->s_main>>>(d, iters / 10 + 1);
+    GPK_CK(h, cudaStreamSynchronize(h->s_main));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      GPK_CK(h, cudaEventRecord(h->t0, h->s_main));
+      mixed_peak_kernel<<<grid, block, 0, h->s_main>>>(d, iters);
+      GPK_CK(h, cudaEventRecord(h->t1, h->s_main));
+      GPK_CK(h, cudaEventSynchronize(h->t1));
+      float ms = 0;
+      GPK_CK(h, cudaEventElapsedTime(&ms, h->t0, h->t1));
+      if (ms < best) best = ms;
+    }
+    GPK_CK(h, cudaGetLastError());
+    cudaFree(d);
+    // per iteration: DMMA warp 8 x 2048 flop, DFMA warp 16 x 64 flop ; the kernel ends when the slower half ends
+    const double total = ((warps / 2) * 8.0 * 2048.0 + (warps / 2) * 16.0 * 64.0) * iters * (double)grid.x;
+    *ms_out = best;
+    *tflops = total / (best * 1e-3) / 1e12;
+    return 0;
+  }
   if (shape < 0 || shape > 4 || warps < 1 || warps > 16 || iters < 1) return GPK_ERR_ARG;
   int sms = 0;
   GPK_CK(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));

@@ -163,6 +163,7 @@ int gemm_init(Handle* h);
 int diag_init(Handle* h);
 
 int ensure(Handle* h, double** p, int64_t* cap, int64_t need_elems);
+int dist_allreduce_sum(Handle* h, double* buf, size_t count, cudaStream_t st);
 int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::vector<double>& scale, int* divide,
                double* premul, double* sf2);
 void stats_begin(Handle* h);
