@@ -254,8 +254,47 @@ def housing():
     np.savez_compressed(os.path.join(OUT, "housing.npz"), **s)
 
 
+
+
+def classification():
+    """Config 5 family: GPC + inf.EP + lik.Erf.  KAT5 on the reference's Demo/Classification fixture
+    (nlZ=50.454379530956) and synthetic sign labels at N=200/512, D=16, RBF(log 4, 0)."""
+    d = np.load(os.path.join(REF, "pyGPs/Demo/Classification/classification_data.npz"))
+    x, y, xs = d["x"], d["y"], d["xstar"][::40]
+    s = {"kat5_x": x, "kat5_y": y, "kat5_xs": xs}
+    m = pyGPs.GPC()
+    nlZ, dn, post = m.getPosterior(x, y)
+    s["kat5_nlZ"] = np.float64(nlZ); s["kat5_dcov"] = np.array(dn.cov); s["kat5_alpha"] = post.alpha
+    s["kat5_sW"] = post.sW; s["kat5_L"] = post.L
+    s["kat5_ttau"] = m.inffunc.last_ttau; s["kat5_tnu"] = m.inffunc.last_tnu
+    out = m.predict(xs, np.ones((xs.shape[0], 1)))
+    for name, v in zip(("ym", "ys2", "fm", "fs2", "lp"), out):
+        s["kat5_" + name] = v
+    print("kat5 nlZ", nlZ, dn.cov)
+    for N in (200, 512):
+        rng = np.random.default_rng(0)
+        X = rng.standard_normal((N, 16))
+        lab = np.sign(X[:, :1] + 0.5 * X[:, 1:2] + 0.3 * rng.standard_normal((N, 1)))
+        lab[lab == 0] = 1
+        m = pyGPs.GPC()
+        m.setPrior(kernel=pyGPs.cov.RBF(np.log(4.0), 0.0))
+        nlZ, dn, post = m.getPosterior(X, lab)
+        Xs = np.random.default_rng(1).standard_normal((64, 16))
+        out = m.predict(Xs)
+        tag = "c5_%d" % N
+        s[tag + "_nlZ"] = np.float64(nlZ); s[tag + "_dcov"] = np.array(dn.cov); s[tag + "_alpha"] = post.alpha
+        s[tag + "_sW"] = post.sW; s[tag + "_ym"] = out[0]; s[tag + "_ys2"] = out[1]; s[tag + "_fm"] = out[2]
+        s[tag + "_fs2"] = out[3]; s[tag + "_lp"] = out[4] if out[4] is not None else np.zeros(0)
+        print(tag, nlZ)
+    np.savez_compressed(os.path.join(OUT, "classification.npz"), **s)
+
+
 if __name__ == "__main__":
-    kat_regression()
-    cov_vectors()
-    synthetic(big="--big" in sys.argv)
-    housing()
+    if "--only-classification" in sys.argv:
+        classification()
+    else:
+        kat_regression()
+        cov_vectors()
+        synthetic(big="--big" in sys.argv)
+        housing()
+        classification()

@@ -387,3 +387,162 @@ def synth_regression(N, D, seed=0):
     X = rng.standard_normal((N, D))
     y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
     return X, y
+
+
+# --------------------------------------------------------------------------
+# lik.Erf + inf.EP  (BASELINE config 5; Core/lik.py:236-366, Core/inf.py:174-189, 723-806)
+# --------------------------------------------------------------------------
+from scipy.special import erf as _erf  # noqa: E402
+
+
+def erf_logphi(z, p):
+    """Safe log of the normal cdf.  Core/lik.py:354-366 (thresholds -6.2 / -5.5)."""
+    z = np.asarray(z, dtype=float)
+    lp = np.zeros_like(z)
+    zmin, zmax = -6.2, -5.5
+    ok = z > zmax
+    bd = z < zmin
+    nok = ~ok
+    ip = nok & ~bd
+    lam = 1.0 / (1.0 + np.exp(25.0 * (0.5 - (z[ip] - zmin) / (zmax - zmin))))
+    lp[ok] = np.log(p[ok])
+    lp[nok] = -np.log(np.pi) / 2.0 - z[nok] ** 2 / 2.0 - np.log(np.sqrt(z[nok] ** 2 / 2.0 + 2.0) - z[nok] / np.sqrt(2.0))
+    lp[ip] = (1 - lam) * lp[ip] + lam * np.log(p[ip])
+    return lp
+
+
+def erf_cum_gauss(y, f):
+    """(p, log p) of the probit likelihood.  Core/lik.py:328-339."""
+    yf = y * f
+    p = (1.0 + _erf(yf / np.sqrt(2.0))) / 2.0
+    return p, erf_logphi(yf, p)
+
+
+def erf_gau_over_cum_gauss(f, p):
+    """N(f)/Phi(f) with the asymptotic branch below -6 and interpolation on [-6,-5].  Core/lik.py:341-352."""
+    f = np.asarray(f, dtype=float)
+    n_p = np.zeros_like(f)
+    ok = f > -5
+    n_p[ok] = (np.exp(-f[ok] ** 2 / 2) / np.sqrt(2 * np.pi)) / p[ok]
+    bd = f < -6
+    n_p[bd] = np.sqrt(f[bd] ** 2 / 4 + 1) - f[bd] / 2
+    it = ~ok & ~bd
+    tmp = f[it]
+    lam = -5.0 - f[it]
+    n_p[it] = (1 - lam) * (np.exp(-tmp ** 2 / 2) / np.sqrt(2 * np.pi)) / p[it] + lam * (np.sqrt(tmp ** 2 / 4 + 1) - tmp / 2)
+    return n_p
+
+
+def erf_ep_moments(y, mu, s2, nargout=1):
+    """lZ [, dlZ, d2lZ] of int Phi(y f) N(f|mu,s2) df.  Core/lik.py:295-311."""
+    y = np.sign(np.asarray(y, dtype=float))
+    y = np.where(y == 0, 1.0, y)
+    z = mu / np.sqrt(1 + s2)
+    _, lZ = erf_cum_gauss(y, z)
+    if nargout == 1:
+        return lZ
+    z = z * y
+    n_p = erf_gau_over_cum_gauss(z, np.exp(lZ))
+    dlZ = y * n_p / np.sqrt(1.0 + s2)
+    if nargout == 2:
+        return lZ, dlZ
+    return lZ, dlZ, -n_p * (z + n_p) / (1.0 + s2)
+
+
+def erf_predict(ys, fmu, fs2):
+    """Prediction mode of lik.Erf (Core/lik.py:253-271): returns (lp, ymu, ys2)."""
+    y = np.ones_like(fmu) if ys is None else np.where(np.sign(ys) == 0, 1.0, np.sign(ys)) * np.ones_like(fmu)
+    if fs2 is not None and np.linalg.norm(fs2) > 0:
+        lp = erf_ep_moments(y, fmu, fs2, 1)
+        p = np.exp(lp)
+    else:
+        p, lp = erf_cum_gauss(y, fmu)
+    return lp, 2 * p - 1, 4 * p * (1 - p)
+
+
+def _ep_compute_params(K, y, ttau, tnu, m):
+    """Core/inf.py:174-189."""
+    n = len(y)
+    ssi = np.sqrt(ttau)
+    R = jitchol(np.eye(n) + np.dot(ssi, ssi.T) * K).T
+    V = np.linalg.solve(R.T, np.tile(ssi, (1, n)) * K)
+    Sigma = K - np.dot(V.T, V)
+    mu = np.dot(Sigma, tnu)
+    Ds = np.diag(Sigma).reshape(-1, 1)
+    tau_n = 1 / Ds - ttau
+    nu_n = mu / Ds - tnu + m * tau_n
+    lZ = erf_ep_moments(y, nu_n / tau_n, 1 / tau_n, 1)
+    nlZ = (np.log(np.diag(R)).sum() - lZ.sum() - np.dot(tnu.T, np.dot(Sigma, tnu)) / 2
+           - np.dot((nu_n - m * tau_n).T, ((ttau / tau_n * (nu_n - m * tau_n) - 2 * tnu) / (ttau + tau_n))) / 2
+           + (tnu ** 2 / (tau_n + ttau)).sum() / 2.0 - np.log(1.0 + ttau / tau_n).sum() / 2.0)
+    return Sigma, mu, nlZ[0], R
+
+
+def ep_evaluate(mean, cov, x, y, nargout=2, last=None):
+    """inf.EP.evaluate with lik.Erf.  Core/inf.py:731-806.  `last` = (ttau, tnu) warm start or None.
+    Returns post {alpha, sW, L}, nlZ [, dnlZ], and the site parameters (ttau, tnu) and sweep count."""
+    tol, max_sweep, min_sweep = 1e-4, 10, 2
+    n = x.shape[0]
+    K = cov_matrix(cov, x=x, mode="train")
+    m = mean_vec(mean, x)
+    nlZ0 = -erf_ep_moments(y, m, np.diag(K).reshape(-1, 1), 1).sum()
+    if last is None:
+        ttau, tnu = np.zeros((n, 1)), np.zeros((n, 1))
+        Sigma, mu, nlZ = K.copy(), np.zeros((n, 1)), nlZ0
+    else:
+        ttau, tnu = last[0].copy(), last[1].copy()
+        Sigma, mu, nlZ, R = _ep_compute_params(K, y, ttau, tnu, m)
+        if nlZ > nlZ0:
+            ttau, tnu = np.zeros((n, 1)), np.zeros((n, 1))
+            Sigma, mu, nlZ = K.copy(), np.zeros((n, 1)), nlZ0
+    nlZ_old, sweep = np.inf, 0
+    while (np.abs(nlZ - nlZ_old) > tol and sweep < max_sweep) or sweep < min_sweep:
+        nlZ_old = nlZ
+        sweep += 1
+        for i in range(n):
+            tau_ni = 1 / Sigma[i, i] - ttau[i]
+            nu_ni = mu[i] / Sigma[i, i] + m[i] * tau_ni - tnu[i]
+            lZ, dlZ, d2lZ = erf_ep_moments(y[i], nu_ni / tau_ni, 1 / tau_ni, 3)
+            ttau_old = ttau[i].copy()
+            ttau[i] = max(-d2lZ / (1.0 + d2lZ / tau_ni), 0)
+            tnu[i] = (dlZ + (m[i] - nu_ni / tau_ni) * d2lZ) / (1.0 + d2lZ / tau_ni)
+            ds2 = ttau[i] - ttau_old
+            si = Sigma[:, i].reshape(-1, 1)
+            Sigma = Sigma - ds2 / (1.0 + ds2 * si[i]) * np.dot(si, si.T)
+            mu = np.dot(Sigma, tnu)
+        Sigma, mu, nlZ, R = _ep_compute_params(K, y, ttau, tnu, m)
+    sW = np.sqrt(ttau)
+    alpha = tnu - sW * solve_chol(R, sW * np.dot(K, tnu))
+    post = {"alpha": alpha, "sW": sW, "L": R}
+    extra = {"ttau": ttau, "tnu": tnu, "sweeps": sweep}
+    if nargout <= 2:
+        return post, nlZ, extra
+    V = np.linalg.solve(R.T, np.tile(sW, (1, n)) * K)
+    Sigma = K - np.dot(V.T, V)
+    mu = np.dot(Sigma, tnu)
+    Ds = np.diag(Sigma).reshape(-1, 1)
+    tau_n = 1 / Ds - ttau
+    nu_n = mu / Ds - tnu
+    F = np.dot(alpha, alpha.T) - np.tile(sW, (1, n)) * solve_chol(R, np.diag(sW.reshape(-1)))
+    dn = {"cov": [-(F * cov_der_matrix(cov, x=x, mode="train", der=j)).sum() / 2.0 for j in range(len(cov[1]))],
+          "lik": [], "mean": []}
+    _, dlZ = erf_ep_moments(y, nu_n / tau_n, 1 / tau_n, 2)
+    for i in range(len(mean_hyp(mean))):
+        dn["mean"].append(-np.dot(dlZ.T, mean_der(mean, x, i))[0, 0])
+    return post, nlZ, dn, extra
+
+
+def predict_class(mean, cov, x, post, xs, ys=None, nperbatch=1000):
+    """GP.predict for GPC (EP posterior, lik.Erf).  Core/gp.py:388-437."""
+    alpha, R, sW = post["alpha"], post["L"], post["sW"]
+    ns = xs.shape[0]
+    fmu = np.zeros((ns, 1)); fs2 = np.zeros((ns, 1))
+    for lo in range(0, ns, nperbatch):
+        sl = slice(lo, min(lo + nperbatch, ns))
+        kss = cov_matrix(cov, z=xs[sl], mode="self_test")
+        Ks = cov_matrix(cov, x=x, z=xs[sl], mode="cross")
+        fmu[sl] = mean_vec(mean, xs[sl]) + np.dot(Ks.T, alpha)
+        V = np.linalg.solve(R.T, sW * Ks)
+        fs2[sl] = np.maximum(kss - (V * V).sum(axis=0).reshape(-1, 1), 0)
+    lp, ymu, ys2 = erf_predict(ys, fmu, fs2)
+    return ymu, ys2, fmu, fs2, (lp if ys is not None else None), lp

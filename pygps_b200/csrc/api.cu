@@ -130,10 +130,16 @@ static int collect_profile(Handle* h, int T) {
   h->stats.syrk_ms = 0.0;
   (void)T;
   if (!h->profile) return 0;
+  const bool dump = getenv("GPK_PROFILE_DUMP") != nullptr;
   for (int k = 0; k < h->prof_pairs; ++k) {
     float ms = 0.f;
     GPK_CK(h, cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]));
     h->stats.syrk_ms += ms;
+    if (dump) {
+      float gap = 0.f;
+      if (k + 1 < h->prof_pairs) cudaEventElapsedTime(&gap, h->prof_ev[2 * k + 1], h->prof_ev[2 * k + 2]);
+      fprintf(stderr, "step %d update %.3f ms, wait-for-next-panel %.3f ms\n", k, ms, gap);
+    }
   }
   return 0;
 }
@@ -185,13 +191,14 @@ static int free_all(Handle* h) {
 static int alloc_problem(Handle* h, int64_t n, int D) {
   const int64_t np = round_up(n, NB);
   const int T = (int)(np / NB);
-  if (np != h->np || D != h->D || !h->dA) {
+  if (np != h->np || D != h->D || !h->dXs) {
     double** ptrs[] = {&h->dXs, &h->dScale, &h->dDinv, &h->dB, &h->dZ, &h->dAlpha, &h->dR, &h->dScal};
     for (auto p : ptrs) {
       if (*p) cudaFree(*p);
       *p = nullptr;
     }
-    GPK_TRY(ensure(h, &h->dA, &h->capA, np * np));
+    // the (np x np) factor storage is allocated by the entry points that need it (exact_eval, potrf): FITC and the
+    // sharded evaluation never hold an N x N matrix on one GPU
     GPK_CK(h, cudaMalloc((void**)&h->dXs, (size_t)np * D * sizeof(double)));
     GPK_CK(h, cudaMalloc((void**)&h->dScale, (size_t)(D + 8) * sizeof(double)));
     GPK_CK(h, cudaMalloc((void**)&h->dDinv, (size_t)np * NB * sizeof(double)));
@@ -390,6 +397,7 @@ int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int
   stats_begin(h);
   h->has_post = false;
   cudaStream_t st = h->s_main;
+  GPK_TRY(ensure(h, &h->dA, &h->capA, np * np));
 
   GPK_CK(h, cudaEventRecord(h->t0, st));
   std::memcpy(h->hPinned, scale.data(), D * sizeof(double));
@@ -630,11 +638,12 @@ int gpk_potrf(gpk_handle hh, const double* A, int64_t n, double* R_out, double* 
   stats_begin(h);
   h->has_post = false; h->has_fitc = false;
   // the standalone factor reuses the posterior's storage; sizes follow this call
-  if (pn != h->np || !h->dA) {
+  if (pn != h->np || !h->dXs) {
     h->n = 0;
     GPK_TRY(alloc_problem(h, n, h->D > 0 ? h->D : 1));
     h->n = 0;
   }
+  GPK_TRY(ensure(h, &h->dA, &h->capA, pn * pn));
   GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, n * n));
   GPK_CK(h, cudaMemcpyAsync(h->dTmp, A, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
   GPK_CK(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), st));

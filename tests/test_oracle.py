@@ -155,3 +155,40 @@ def test_housing_published_value(golden):
     h = g["opt_hyp"]
     _, nlZo = go.exact_evaluate(("zero",), ("rbf", [h[0], h[1]]), h[2], g["x"], g["y"], 2)
     close(nlZo, g["opt_nlZ"], rtol=1e-9)
+
+
+def test_ep_classification_against_reference(golden):
+    """inf.EP + lik.Erf (config 5 family): KAT5 on Demo/Classification and synthetic sign labels."""
+    g = golden("classification")
+    x, y, xs = g["kat5_x"], g["kat5_y"], g["kat5_xs"]
+    post, nlZ, dn, extra = go.ep_evaluate(("zero",), ("rbf", [0., 0.]), x, y, nargout=3)
+    close(nlZ, g["kat5_nlZ"], rtol=1e-9)
+    assert abs(float(g["kat5_nlZ"]) - 50.454379530956) < 1e-8            # SURVEY 8(c) KAT5
+    close(dn["cov"], g["kat5_dcov"], rtol=1e-6)
+    close(post["alpha"], g["kat5_alpha"], rtol=1e-7, atol=1e-10)
+    close(post["sW"], g["kat5_sW"], rtol=1e-7)
+    close(post["L"], g["kat5_L"], rtol=1e-7, atol=1e-10)
+    close(extra["ttau"], g["kat5_ttau"], rtol=1e-7)
+    out = go.predict_class(("zero",), ("rbf", [0., 0.]), x, post, xs, np.ones((xs.shape[0], 1)))
+    for name, v in zip(("ym", "ys2", "fm", "fs2", "lp"), out[:5]):
+        close(v, g["kat5_" + name], rtol=1e-6, atol=1e-9)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((200, 16))
+    lab = np.sign(X[:, :1] + 0.5 * X[:, 1:2] + 0.3 * rng.standard_normal((200, 1)))
+    lab[lab == 0] = 1
+    post, nlZ, dn, extra = go.ep_evaluate(("zero",), ("rbf", [np.log(4.0), 0.0]), X, lab, nargout=3)
+    close(nlZ, g["c5_200_nlZ"], rtol=1e-9)
+    close(dn["cov"], g["c5_200_dcov"], rtol=1e-6)
+    close(post["alpha"], g["c5_200_alpha"], rtol=1e-6, atol=1e-10)
+
+
+def test_erf_special_functions_cover_all_branches():
+    z = np.array([-8.0, -6.2, -6.0, -5.8, -5.5, -5.2, -5.0, -3.0, 0.0, 2.0, 7.0])
+    p = (1 + __import__("scipy.special", fromlist=["erf"]).erf(z / np.sqrt(2))) / 2
+    lp = go.erf_logphi(z, p)
+    assert np.all(np.isfinite(lp)) and np.all(np.diff(lp) > 0)
+    from scipy.stats import norm
+    np.testing.assert_allclose(lp, norm.logcdf(z), rtol=2e-3, atol=1e-3)
+    n_p = go.erf_gau_over_cum_gauss(z, p)
+    np.testing.assert_allclose(n_p[z > -5], norm.pdf(z[z > -5]) / norm.cdf(z[z > -5]), rtol=1e-10)
+    assert np.all(np.diff(n_p) < 0)
