@@ -136,6 +136,18 @@ int gpk_fitc_eval(gpk_handle h, int kind, int matern_d,
 /* FITC branch of GP.predict (Core/gp.py:418): fs2 = kss + colsum(Ks*(L Ks)). */
 int gpk_fitc_predict(gpk_handle h, const double* Xs, int64_t ns, double* ks_alpha, double* fs2);
 
+/* ---- inf.EP.evaluate with lik.Erf (Core/inf.py:731-806; BASELINE config 5) -- *
+ * Binary GP classification by Expectation Propagation, sites visited in the reference's fixed order.
+ *   mvec (n) prior mean m(x) ; y (n) labels (sign is used, 0 -> +1)
+ *   ttau_io, tnu_io (n): site parameters; read as the warm start when use_last != 0 (EP.last_ttau / last_tnu,
+ *                        Core/inf.py:738-753), always written back (:776)
+ *   alpha (n), sW (n) out: post.alpha, post.sW ; post.L through gpk_get_factor ; gpk_predict works afterwards
+ *   dcov (nhyp) and dlz_out (n) if want_der: dnlZ.cov (:789-791) and d lZ / d mu of the cavity (:796) from which
+ *   the caller forms dnlZ.mean = -dlZ'dm (:797-800).  lik.Erf has no hyper-parameters.                          */
+int gpk_ep_eval(gpk_handle h, int kind, int matern_d, const double* hyp, int nhyp, const double* mvec,
+                const double* y, double* ttau_io, double* tnu_io, int use_last, int want_der, double* nlZ,
+                double* alpha, double* sW, double* dcov, double* dlz_out, int* sweeps_out);
+
 /* ---- one evaluation sharded over the GPUs of a box (BASELINE config 3) ---- *
  * One process per GPU.  The matrix K/sn2+I is distributed by block columns (block-cyclic, block 128); each step
  * broadcasts the solved panel over NVLink with NCCL (loaded at run time from `nccl_path`, e.g. the libnccl.so.2

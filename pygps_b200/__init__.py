@@ -12,7 +12,7 @@ Drop-in for `pyGPs.GPR / GPR_FITC`, `pyGPs.cov.RBF / RBFard / Matern`,
 libgpk.so (hand-written sm_100a CUDA, include/gpk.h); there is no CPU fallback.
 """
 from . import cov, inf, lik, mean, opt, tools   # noqa: F401
-from .gp import GP, GPR, GP_FITC, GPR_FITC      # noqa: F401
+from .gp import GP, GPR, GPC, GP_FITC, GPR_FITC  # noqa: F401
 from . import gp                                # noqa: F401
 
 __version__ = "0.1.0"

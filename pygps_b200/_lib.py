@@ -63,6 +63,8 @@ PROTOTYPES = [
     ("gpk_fitc_eval", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, _L, c_double_p, _I,
                            c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     ("gpk_fitc_predict", _I, [_H, c_double_p, _L, c_double_p, c_double_p]),
+    ("gpk_ep_eval", _I, [_H, _I, _I, c_double_p, _I, c_double_p, c_double_p, c_double_p, c_double_p, _I, _I,
+                         c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
     ("gpk_dist_unique_id", _I, [ctypes.c_char_p, ctypes.c_char_p]),
     ("gpk_dist_init", _I, [_H, ctypes.c_char_p, _I, _I, ctypes.c_char_p]),
     ("gpk_dist_finalize", _I, [_H]),
@@ -240,6 +242,26 @@ class Engine(object):
         rc = self._lib.gpk_predict(self._h, _dp(xs), ns, _dp(ka), _dp(fs2))
         self._check(rc, "gpk_predict")
         return ka, fs2
+
+    # -- EP classification --------------------------------------------------------------
+    def ep_eval(self, kind, matern_d, hyp, mvec, y, ttau, tnu, use_last, want_der):
+        hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+        mvec = np.ascontiguousarray(mvec, dtype=np.float64).reshape(-1)
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        n = y.size
+        ttau = np.ascontiguousarray(ttau, dtype=np.float64).reshape(-1).copy() if use_last else np.zeros(n)
+        tnu = np.ascontiguousarray(tnu, dtype=np.float64).reshape(-1).copy() if use_last else np.zeros(n)
+        self._retire_factor()
+        alpha = np.empty((n, 1)); sW = np.empty((n, 1)); dlz = np.zeros((n, 1))
+        nlZ = ctypes.c_double(0.0)
+        dcov = np.zeros(max(hyp.size, 1))
+        sweeps = ctypes.c_int(0)
+        rc = self._lib.gpk_ep_eval(self._h, kind, matern_d, _dp(hyp), hyp.size, _dp(mvec), _dp(y), _dp(ttau), _dp(tnu),
+                                   1 if use_last else 0, 1 if want_der else 0, ctypes.byref(nlZ), _dp(alpha), _dp(sW),
+                                   _dp(dcov), _dp(dlz), ctypes.byref(sweeps))
+        self._check(rc, "gpk_ep_eval")
+        return (np.float64(nlZ.value), alpha, sW, dcov[:hyp.size], dlz, ttau.reshape(-1, 1), tnu.reshape(-1, 1),
+                sweeps.value)
 
     # -- one evaluation sharded over several GPUs (one process per GPU) ------------------
     @staticmethod

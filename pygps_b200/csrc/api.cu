@@ -175,7 +175,7 @@ int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::
 static int free_all(Handle* h) {
   double** ptrs[] = {&h->dX, &h->dXs, &h->dScale, &h->dA, &h->dDinv, &h->dB, &h->dZ, &h->dAlpha, &h->dR, &h->dScal,
                      &h->dU, &h->dW, &h->dP, &h->dTmp, &h->dUin, &h->dUs, &h->dLpost, &h->dAlphaU,
-                     &h->fKuu, &h->fDinvU, &h->fA2, &h->fDinv2, &h->fVt, &h->fVs, &h->fVec, &h->fWt, &h->dXtmp, &h->gA, &h->gDinv, &h->gPack, &h->gVec};
+                     &h->fKuu, &h->fDinvU, &h->fA2, &h->fDinv2, &h->fVt, &h->fVs, &h->fVec, &h->fWt, &h->dXtmp, &h->gA, &h->gDinv, &h->gPack, &h->gVec, &h->eK, &h->eSig, &h->eVec, &h->eSW};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -183,7 +183,7 @@ static int free_all(Handle* h) {
   if (h->dInfo) cudaFree(h->dInfo);
   h->dInfo = nullptr;
   h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = 0;
-  h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->cgA = h->cgDinv = h->cgPack = h->cgVec = h->capUs = h->capLpost = h->capAlphaU = 0;
+  h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->cgA = h->cgDinv = h->cgPack = h->cgVec = h->ceK = h->ceSig = h->ceVec = h->ceSW = h->capUs = h->capLpost = h->capAlphaU = 0;
   return 0;
 }
 
@@ -395,7 +395,7 @@ int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int
   if (D > 1900) return GPK_ERR_ARG;  // pinned staging layout
   const double sn2 = std::exp(2.0 * log_sn);
   stats_begin(h);
-  h->has_post = false;
+  h->has_post = false; h->post_ep = false;
   cudaStream_t st = h->s_main;
   GPK_TRY(ensure(h, &h->dA, &h->capA, np * np));
 
@@ -524,10 +524,12 @@ int gpk_predict(gpk_handle hh, const double* Xs, int64_t ns, double* ks_alpha, d
     c.F = dXsc; c.S = h->dXs; c.out = h->dP; c.ld = mp;
     c.nF = m; c.nS = n; c.pF = mp; c.pS = np; c.D = D;
     c.kind = h->kind; c.matern_d = h->matern_d; c.epi = EPI_COV;
-    c.sf2 = sf2; c.scale = 1.0 / sn; c.diag_add = 0.0; c.same_set = 0; c.lower_only = 0; c.pad_identity = 0;
+    const bool ep = h->post_ep;                   // EP posterior: sW is a vector (sqrt of the site precisions)
+    c.sf2 = sf2; c.scale = ep ? 1.0 : 1.0 / sn; c.diag_add = 0.0; c.same_set = 0; c.lower_only = 0; c.pad_identity = 0;
     GPK_TRY(launch_cov(h, st, c));
     // Ks' alpha  (undo the 1/sn scaling)
-    GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, h->dAlpha, 0, sn, 0.0, dPart, nsplit, dOut, m));
+    GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, h->dAlpha, 0, ep ? 1.0 : sn, 0.0, dPart, nsplit, dOut, m));
+    if (ep) GPK_TRY(launch_colscale_inplace(h, st, h->dP, mp, mp, np, h->eSW));   // sW .* Ks  (Core/gp.py:415)
     GPK_TRY(sweep_forward(h, st, h->dP, mp, (int)(mp / NB), h->dA, np, h->dDinv, T));
     GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, nullptr, 1, 1.0, sf2, dPart, nsplit, dOut + mp, m));
     GPK_CK(h, cudaMemcpyAsync(ks_alpha + lo, dOut, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -102,6 +102,10 @@ struct Handle {
   double* dXtmp = nullptr; int64_t capXtmp = 0;
   // standalone potrf state
   int64_t pn = 0;
+  // EP (classification) state; see ep.cu
+  bool post_ep = false;
+  double *eK = nullptr, *eSig = nullptr, *eVec = nullptr, *eSW = nullptr;
+  int64_t ceK = 0, ceSig = 0, ceVec = 0, ceSW = 0;
   // multi-GPU (block-cyclic columns over NCCL); see dist.cu
   void* nccl_comm = nullptr; int rank = 0, world = 1;
   double* gA = nullptr; int64_t cgA = 0;        // local columns of the (np+128) x np augmented matrix
@@ -156,6 +160,11 @@ int launch_rowdot(Handle* h, cudaStream_t st, const double* P, int64_t ld, int64
 int launch_dnlz(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
                 const double* alpha, double inv_sn2, double sf2, int kind, int matern_d, double* part,
                 int64_t part_cap, double* res);
+int launch_dnlz_sw(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
+                   const double* alpha, const double* sw, double sf2, int kind, int matern_d, double* part,
+                   int64_t part_cap, double* res);
+int launch_colscale_inplace(Handle* h, cudaStream_t st, double* P, int64_t ld, int64_t rows, int64_t cols,
+                            const double* s);
 int launch_copy(Handle* h, cudaStream_t st, const double* src, double* dst, int64_t n);
 int launch_fill_random(Handle* h, cudaStream_t st, double* p, int64_t n, unsigned seed);
 int bench_dmma(Handle* h, int shape, int warps, int iters, double* tflops, double* ms_out);

@@ -137,6 +137,7 @@ struct DnlzArgs {
   const double* Xs; int64_t n; int D;
   const double* Ainv; int64_t ld;
   const double* alpha;
+  const double* sw;  // EP: Q_ij = Ainv_ij*sw_i*sw_j - alpha_i alpha_j (Core/inf.py:788); null: Ainv_ij*inv_sn2
   double inv_sn2, sf2;
   int kind, matern_d;
   int d_begin;      // ARD: first length-scale index handled by this pass
@@ -166,10 +167,11 @@ __global__ void __launch_bounds__(256) dnlz_kernel(const DnlzArgs a) {
     const int ti = tid & 63, tj0 = tid >> 6;  // i fastest across lanes -> coalesced Ainv reads
     const int64_t i = i0 + ti;
     const double ai = (i < a.n) ? a.alpha[i] : 0.0;
+    const double swi = (a.sw && i < a.n) ? a.sw[i] : 0.0;
     for (int jj = tj0; jj < DT_; jj += 4) {
       const int64_t j = j0 + jj;
       if (i >= a.n || j >= a.n || i < j) continue;
-      const double q = a.Ainv[i + j * a.ld] * a.inv_sn2 - ai * a.alpha[j];
+      const double q = a.Ainv[i + j * a.ld] * (a.sw ? swi * a.sw[j] : a.inv_sn2) - ai * a.alpha[j];
       const double w = (i == j) ? 1.0 : 2.0;
       double d2 = 0.0;
       for (int d = 0; d < a.D; ++d) { const double df = Xi[ti * a.D + d] - Xj[jj * a.D + d]; d2 = fma(df, df, d2); }
@@ -289,9 +291,24 @@ int launch_rowdot(Handle* h, cudaStream_t st, const double* P, int64_t ld, int64
 }
 
 // Runs the fused reduction; res gets [dcov_0 .. dcov_{nhyp-1}, trace(Q)] (before the 1/2 and sn2 factors).
+static int launch_dnlz_impl(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv,
+                            int64_t ld, const double* alpha, const double* sw, double inv_sn2, double sf2, int kind,
+                            int matern_d, double* part, int64_t part_cap, double* res);
+
 int launch_dnlz(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
                 const double* alpha, double inv_sn2, double sf2, int kind, int matern_d, double* part,
                 int64_t part_cap, double* res) {
+  return launch_dnlz_impl(h, st, Xs, n, D, Ainv, ld, alpha, nullptr, inv_sn2, sf2, kind, matern_d, part, part_cap, res);
+}
+int launch_dnlz_sw(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
+                   const double* alpha, const double* sw, double sf2, int kind, int matern_d, double* part,
+                   int64_t part_cap, double* res) {
+  return launch_dnlz_impl(h, st, Xs, n, D, Ainv, ld, alpha, sw, 1.0, sf2, kind, matern_d, part, part_cap, res);
+}
+
+static int launch_dnlz_impl(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv,
+                            int64_t ld, const double* alpha, const double* sw, double inv_sn2, double sf2, int kind,
+                            int matern_d, double* part, int64_t part_cap, double* res) {
   const int64_t g = (n + DT_ - 1) / DT_;
   if (g > 65535) return GPK_ERR_ARG;
   const int64_t nctas = g * g;
@@ -299,7 +316,7 @@ int launch_dnlz(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, 
   if (smem > 200 * 1024) return GPK_ERR_ARG;
   GPK_CK(h, cudaFuncSetAttribute(dnlz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DnlzArgs a;
-  a.Xs = Xs; a.n = n; a.D = D; a.Ainv = Ainv; a.ld = ld; a.alpha = alpha; a.inv_sn2 = inv_sn2; a.sf2 = sf2;
+  a.Xs = Xs; a.n = n; a.D = D; a.Ainv = Ainv; a.ld = ld; a.alpha = alpha; a.sw = sw; a.inv_sn2 = inv_sn2; a.sf2 = sf2;
   a.kind = kind; a.matern_d = matern_d; a.part = part;
   dim3 grid((unsigned)g, (unsigned)g);
   if (kind != GPK_COV_RBFARD) {

@@ -162,15 +162,16 @@ class GP(object):
         if dev is None:
             return False
         kind, md, hyp = dev
-        return (spec[1] == kind and spec[2] == md and tuple(hyp) == spec[3]
-                and float(self.likfunc.hyp[0]) == spec[4])
+        lik0 = float(self.likfunc.hyp[0]) if self.likfunc.hyp else 0.0
+        return (spec[1] == kind and spec[2] == md and tuple(hyp) == spec[3] and lik0 == spec[4])
 
     def _predict_core(self, post, xs, ys):
         meanfunc, covfunc, likfunc = self.meanfunc, self.covfunc, self.likfunc
         x = self.x
         ns = xs.shape[0]
         fitc = isinstance(covfunc, FITCOfKernel)
-        if self._posterior_matches(post, 'fitc' if fitc else 'exact'):
+        kindname = 'fitc' if fitc else ('ep' if isinstance(self.inffunc, inf.EP) else 'exact')
+        if self._posterior_matches(post, kindname):
             # fast path: cross-covariances, the triangular solves and the column reductions
             # all happen next to the resident factor (gpk_predict / gpk_fitc_predict)
             eng = post._engine
@@ -253,6 +254,50 @@ class GPR(GP):
 
     def useLikelihood(self, newLik):
         raise Exception('Only the Gaussian likelihood is on the accelerated path.')
+
+
+class GPC(GP):
+    """Gaussian-process binary classification: lik.Erf + inf.EP (Core/gp.py:641-732)."""
+
+    def __init__(self):
+        super(GPC, self).__init__()
+        self.meanfunc = mean.Zero()
+        self.covfunc = cov.RBF()
+        self.likfunc = lik.Erf()
+        self.inffunc = inf.EP()
+        self.optimizer = opt.Minimize(self)
+
+    def getPosterior(self, x=None, y=None, der=True):
+        self._take_xy(x, y)
+        uy = np.unique(self.y)                       # labels must be +1 / -1 (Core/gp.py:329-333)
+        if np.any((uy != 1) & (uy != -1)):
+            raise Exception('You attempt classification using labels different from {+1,-1}')
+        return super(GPC, self).getPosterior(der=der)
+
+    def setOptimizer(self, method, num_restarts=None, min_threshold=None, meanRange=None, covRange=None,
+                     likRange=None):
+        conf = None
+        if (num_restarts is not None) or (min_threshold is not None):
+            conf = opt.random_init_conf(self.meanfunc, self.covfunc, self.likfunc)
+            conf.num_restarts = num_restarts
+            conf.min_threshold = min_threshold
+            if meanRange is not None:
+                conf.meanRange = meanRange
+            if covRange is not None:
+                conf.covRange = covRange
+            if likRange is not None:
+                conf.likRange = likRange
+        table = {"Minimize": opt.Minimize, "SCG": opt.SCG, "CG": opt.CG, "BFGS": opt.BFGS}
+        if method in table:
+            self.optimizer = table[method](self, conf)
+
+    def useInference(self, newInf):
+        raise Exception('Only EP inference is on the accelerated classification path ("Laplace" is out of scope).')
+
+    def useLikelihood(self, newLik):
+        if newLik == "Logistic":
+            raise Exception("Logistic likelihood is currently not implemented.")
+        raise Exception('Possible lik values are "Logistic".')
 
 
 class GP_FITC(GP):

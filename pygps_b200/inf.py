@@ -214,6 +214,56 @@ class Exact(Inference):
         return post
 
 
+class EP(Inference):
+    """Expectation Propagation for binary classification with lik.Erf (Core/inf.py:723-806).
+
+    The whole evaluation (kernel matrix, sequential site updates with rank-1 posterior updates, the
+    per-sweep refactorisation, posterior parameters and derivatives) is one call, gpk_ep_eval.  Like the
+    reference, the site parameters of the previous call are tried as the starting point (last_ttau/last_tnu)."""
+
+    def __init__(self):
+        self.name = 'Expectation Propagation'
+        self.last_ttau = None
+        self.last_tnu = None
+        self.last_sweeps = 0
+        self._engine = None
+
+    def evaluate(self, meanfunc, covfunc, likfunc, x, y, nargout=1):
+        if not isinstance(likfunc, lik.Erf):
+            raise Exception('EP on the GPU path supports the Erf likelihood (binary classification) only')
+        spec = covfunc._device_spec() if not isinstance(covfunc, cov.FITCOfKernel) else None
+        if spec is None:
+            raise Exception('EP on the GPU path needs cov.RBF, cov.RBFard or cov.Matern')
+        kind, md, hyp = spec
+        n = x.shape[0]
+        m = meanfunc.getMean(x)
+        eng = self._get_engine()
+        eng.set_data(x)
+        warm = self.last_ttau is not None and len(self.last_ttau) == n
+        nlZ, alpha, sW, dcov, dlz, ttau, tnu, sweeps = eng.ep_eval(
+            kind, md, hyp, m, y, self.last_ttau if warm else None, self.last_tnu if warm else None, warm, nargout > 2)
+        if sweeps == 10:
+            logging.getLogger(__name__).warning("maximum number of sweeps reached in function infEP")
+        self.last_ttau, self.last_tnu, self.last_sweeps = ttau, tnu, sweeps
+        post = postStruct()
+        post.alpha = alpha
+        post.sW = sW
+        post._L = None
+        post._engine, post._epoch, post._n = eng, eng.epoch, n
+        post._spec = ('ep', kind, md, tuple(hyp), 0.0)
+        post.L                                    # EP evaluations take seconds: fetch the factor now (no rebuild path)
+        if nargout > 1:
+            if nargout > 2:
+                dnlZ = dnlZStruct(meanfunc, covfunc, likfunc)
+                dnlZ.cov = [np.float64(v) for v in dcov]
+                dnlZ.lik = []
+                for i in range(len(meanfunc.hyp)):
+                    dnlZ.mean[i] = np.float64(-np.dot(dlz.T, meanfunc.getDerMatrix(x, i))[0, 0])
+                return post, nlZ, dnlZ
+            return post, nlZ
+        return post
+
+
 class FITC_Exact(Inference):
     """FITC approximation with Gaussian likelihood (Core/inf.py:387-455)."""
 

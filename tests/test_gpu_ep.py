@@ -1,0 +1,82 @@
+"""GPC + inf.EP + lik.Erf on the GPU (BASELINE config 5 family) against the reference's frozen outputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import pygps_b200 as pg            # noqa: E402
+from oracle import gp_oracle as go  # noqa: E402
+
+
+def rel(a, b):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def test_kat5_classification_fixture(golden):
+    g = golden("classification")
+    x, y, xs = g["kat5_x"], g["kat5_y"], g["kat5_xs"]
+    m = pg.GPC()
+    nlZ, dn, post = m.getPosterior(x, y)
+    assert type(nlZ) is np.float64
+    assert abs(nlZ - float(g["kat5_nlZ"])) < 1e-6 * abs(float(g["kat5_nlZ"])), (nlZ, g["kat5_nlZ"])
+    assert abs(nlZ - 50.454379530956) < 1e-4
+    assert rel(dn.cov, g["kat5_dcov"]) < 1e-5, (dn.cov, g["kat5_dcov"])
+    assert dn.lik == [] and dn.mean == []
+    assert post.alpha.shape == (120, 1) and post.sW.shape == (120, 1) and post.L.shape == (120, 120)
+    assert rel(post.alpha, g["kat5_alpha"]) < 1e-5 and rel(post.sW, g["kat5_sW"]) < 1e-5
+    assert np.all(np.tril(post.L, -1) == 0) and rel(post.L, g["kat5_L"]) < 1e-5
+    assert rel(m.inffunc.last_ttau, g["kat5_ttau"]) < 1e-5 and rel(m.inffunc.last_tnu, g["kat5_tnu"]) < 1e-5
+    out = m.predict(xs, np.ones((xs.shape[0], 1)))
+    for name, v in zip(("ym", "ys2", "fm", "fs2", "lp"), out):
+        assert rel(v, g["kat5_" + name]) < 1e-5, (name, rel(v, g["kat5_" + name]))
+
+
+@pytest.mark.parametrize("N", [200, 512])
+def test_c5_family_synthetic(golden, N):
+    g = golden("classification")
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((N, 16))
+    lab = np.sign(X[:, :1] + 0.5 * X[:, 1:2] + 0.3 * rng.standard_normal((N, 1)))
+    lab[lab == 0] = 1
+    m = pg.GPC()
+    m.setPrior(kernel=pg.cov.RBF(np.log(4.0), 0.0))
+    nlZ, dn, post = m.getPosterior(X, lab)
+    tag = "c5_%d" % N
+    assert abs(nlZ - float(g[tag + "_nlZ"])) < 1e-6 * abs(float(g[tag + "_nlZ"])), (nlZ, g[tag + "_nlZ"])
+    assert rel(dn.cov, g[tag + "_dcov"]) < 1e-4
+    assert rel(post.alpha, g[tag + "_alpha"]) < 1e-4 and rel(post.sW, g[tag + "_sW"]) < 1e-4
+    Xs = np.random.default_rng(1).standard_normal((64, 16))
+    out = m.predict(Xs)
+    assert rel(out[0], g[tag + "_ym"]) < 1e-4 and rel(out[2], g[tag + "_fm"]) < 1e-4 and rel(out[3], g[tag + "_fs2"]) < 1e-4
+    assert out[4] is None
+    if N == 512:
+        assert abs(float(g[tag + "_nlZ"]) - 199.32798736) < 1e-6          # BASELINE.md C5 scaled
+
+
+def test_warm_start_and_const_mean_match_the_oracle():
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((150, 4))
+    lab = np.sign(X[:, :1] - 0.3 + 0.2 * rng.standard_normal((150, 1))); lab[lab == 0] = 1
+    m = pg.GPC()
+    m.setPrior(mean=pg.mean.Const(0.2), kernel=pg.cov.RBFard(log_ell_list=[0.3, 0.1, 0.5, 0.2], log_sigma=0.4))
+    nlZ1, dn1, post1 = m.getPosterior(X, lab)
+    spec = ("rbfard", [0.3, 0.1, 0.5, 0.2, 0.4])
+    rpost, rnlZ, rdn, extra = go.ep_evaluate(("const", 0.2), spec, X, lab, nargout=3)
+    assert abs(nlZ1 - rnlZ) < 1e-6 * abs(rnlZ)
+    assert rel(dn1.cov, rdn["cov"]) < 1e-4 and rel(dn1.mean, rdn["mean"]) < 1e-4
+    m.covfunc.hyp = [0.35, 0.1, 0.5, 0.2, 0.4]                     # second call warm-starts from the first
+    nlZ2, dn2, _ = m.getPosterior(X, lab)
+    spec2 = ("rbfard", [0.35, 0.1, 0.5, 0.2, 0.4])
+    _, rnlZ2, _, _ = go.ep_evaluate(("const", 0.2), spec2, X, lab, nargout=3, last=(extra["ttau"], extra["tnu"]))
+    assert abs(nlZ2 - rnlZ2) < 1e-5 * abs(rnlZ2)
+
+
+def test_labels_are_checked_and_shapes_follow_the_reference():
+    x = np.random.default_rng(0).standard_normal((20, 2))
+    with pytest.raises(Exception):
+        pg.GPC().getPosterior(x, np.arange(20.0).reshape(-1, 1))
+    y = np.sign(x[:, :1]); y[y == 0] = 1
+    post, nlZ, dnlZ = pg.inf.EP().evaluate(pg.mean.Zero(), pg.cov.RBF(), pg.lik.Erf(), x, y, nargout=3)
+    assert post.alpha.shape[0] == 20 and post.L.shape == (20, 20) and post.sW.shape == (20, 1)
+    assert type(nlZ) is np.float64 and all(type(v) is np.float64 for v in dnlZ.cov)
