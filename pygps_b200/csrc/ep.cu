@@ -11,6 +11,7 @@
 // After every sweep Sigma, mu and nlZ are rebuilt from scratch exactly like _epComputeParams, with the blocked
 // Cholesky, the transposed multi-right-hand-side sweep and the DMMA SYRK of gemm_nt.cu.
 #include <cmath>
+#include <cstdlib>
 #include "gpk_internal.cuh"
 
 namespace gpk {
@@ -108,6 +109,80 @@ __global__ void __launch_bounds__(512) ep_site_kernel(const double* __restrict__
     const double s = (r >= i) ? Sig[r + (int64_t)i * ld] : Sig[i + r * ld];
     sbuf[r] = s;
     mu[r] += s * coef;
+  }
+}
+
+// Blocked ("delayed update") form of the same site update.  Within a block of EPB consecutive sites the rank-1
+// corrections are NOT applied to Sigma; site t of the block reconstructs its column of the current Sigma as
+//     s = Sigma0[:, i] - S[:, 0:t] * w ,  w_j = c_j * S[i, j]
+// (S holds the earlier columns of the block, c their coefficients), which is O(n*t) instead of O(n^2).  After the
+// block, Sigma0 -= (S diag c) S' is ONE rank-EPB update on the tensor pipe.  Same arithmetic as :759-770 up to
+// rounding; the per-sweep rebuild (_epComputeParams) bounds any drift exactly as in the reference.
+// grid = ceil(n/256) CTAs; every CTA recomputes the (deterministic) site scalars, each thread owns one row.
+constexpr int EPB = 128;
+__global__ void __launch_bounds__(256) ep_site_blk_kernel(const double* __restrict__ Sig, int64_t ld, int64_t n, int i,
+                                                          int t, const double* __restrict__ y,
+                                                          const double* __restrict__ m, double* __restrict__ ttau,
+                                                          double* __restrict__ tnu, double* __restrict__ mu,
+                                                          double* __restrict__ S, double* __restrict__ Sc,
+                                                          double* __restrict__ cvec, const double* __restrict__ mu_in,
+                                                          double* __restrict__ mu_out) {
+  __shared__ double w[EPB];
+  __shared__ double sh[8];
+  __shared__ double s_c, s_coef, s_tt, s_tn;
+  const int tid = threadIdx.x;
+  // w_j = c_j * S[i, j]  and  Sii = Sigma0[i,i] - sum_j w_j S[i,j]
+  double part = 0.0;
+  if (tid < t) {
+    const double sij = S[i + (int64_t)tid * ld];
+    const double wj = cvec[tid] * sij;
+    w[tid] = wj;
+    part = wj * sij;
+  }
+  // deterministic block sum of `part` over the first EPB threads
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((tid & 31) == 0) sh[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    const double corr = (sh[0] + sh[1]) + (sh[2] + sh[3]);
+    const double Sii = Sig[i + (int64_t)i * ld] - corr;
+    const double mui = mu_in[0];
+    const double tau_ni = 1.0 / Sii - ttau[i];
+    const double nu_ni = mui / Sii + m[i] * tau_ni - tnu[i];
+    double lZ, dlZ, d2lZ;
+    d_erf_moments(d_sign1(y[i]), nu_ni / tau_ni, 1.0 / tau_ni, lZ, dlZ, d2lZ);
+    const double ttau_old = ttau[i], tnu_old = tnu[i];
+    double tt = -d2lZ / (1.0 + d2lZ / tau_ni);
+    tt = fmax(tt, 0.0);
+    const double tn = (dlZ + (m[i] - nu_ni / tau_ni) * d2lZ) / (1.0 + d2lZ / tau_ni);
+    const double ds2 = tt - ttau_old;
+    const double c = ds2 / (1.0 + ds2 * Sii);
+    s_c = c; s_tt = tt; s_tn = tn;
+    s_coef = (tn - tnu_old) * (1.0 - c * Sii) - c * mui;
+  }
+  __syncthreads();
+  const double c = s_c, coef = s_coef;
+  const int64_t r = (int64_t)blockIdx.x * 256 + tid;
+  if (r < n) {
+    double s = (r >= i) ? Sig[r + (int64_t)i * ld] : Sig[i + r * ld];
+    double a0 = 0.0, a1 = 0.0;
+    int j = 0;
+    for (; j + 1 < t; j += 2) {
+      a0 = fma(S[r + (int64_t)j * ld], w[j], a0);
+      a1 = fma(S[r + (int64_t)(j + 1) * ld], w[j + 1], a1);
+    }
+    if (j < t) a0 = fma(S[r + (int64_t)j * ld], w[j], a0);
+    s -= (a0 + a1);
+    S[r + (int64_t)t * ld] = s;
+    Sc[r + (int64_t)t * ld] = c * s;
+    const double munew = mu[r] + s * coef;
+    mu[r] = munew;
+    if (r == i + 1) mu_out[0] = munew;           // mu of the NEXT site, read by its launch (two alternating slots)
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    ttau[i] = s_tt;
+    tnu[i] = s_tn;
+    cvec[t] = c;
   }
 }
 
@@ -300,7 +375,8 @@ int gpk_ep_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nh
   GPK_TRY(ensure(h, &h->eSig, &h->ceSig, np * np));
   GPK_TRY(ensure(h, &h->dP, &h->capP, np * np));
   const int nsplit = 8;
-  GPK_TRY(ensure(h, &h->eVec, &h->ceVec, 14 * np + T + 128 + 4 * (int64_t)D + (int64_t)nsplit * np));
+  GPK_TRY(ensure(h, &h->eVec, &h->ceVec, 14 * np + T + 128 + 4 * (int64_t)D + (int64_t)nsplit * np + 256));
+  GPK_TRY(ensure(h, &h->dU, &h->capU, 2 * np * EPB));
   EpBuf b;
   b.K = h->eK; b.Sig = h->eSig; b.P = h->dP;
   double* v0 = h->eVec;
@@ -310,6 +386,9 @@ int gpk_ep_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nh
   double* ttau0 = v0 + 12 * np;   // zero vectors kept for resets
   // res: [0,1] nlZ pieces, [8] nlZ0, [12] scratch, [14] cbuf, [16..) dnlZ results (+ ARD scratch)
   b.parts = v0 + 14 * np; b.res = b.parts + T; b.cbuf = b.res + 14; b.part = b.res + 128 + 4 * D;
+  double* cvec = b.part + (int64_t)nsplit * np;   // EPB coefficients of the current block
+  double* mun = cvec + EPB;                       // two alternating slots: mu of the next site
+  const bool naive = getenv("GPK_EP_NAIVE") != nullptr;   // the unblocked rank-1 form, kept for A/B checks
 
   GPK_CK(h, cudaEventRecord(h->t0, st));
   std::memcpy(h->hPinned, scale.data(), D * sizeof(double));
@@ -354,11 +433,31 @@ int gpk_ep_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nh
   while ((std::fabs(nlz - nlz_old) > tol && sweep < max_sweep) || sweep < min_sweep) {
     nlz_old = nlz;
     ++sweep;
-    for (int i = 0; i < (int)n; ++i) {
-      ep_site_kernel<<<1, 512, 0, st>>>(b.Sig, np, n, i, b.y, b.m, b.ttau, b.tnu, b.mu, b.sbuf, b.cbuf);
-      ep_rank1_kernel<<<dim3(g64, g64), 256, 0, st>>>(b.Sig, np, n, b.sbuf, b.cbuf);
+    if (naive) {
+      for (int i = 0; i < (int)n; ++i) {
+        ep_site_kernel<<<1, 512, 0, st>>>(b.Sig, np, n, i, b.y, b.m, b.ttau, b.tnu, b.mu, b.sbuf, b.cbuf);
+        ep_rank1_kernel<<<dim3(g64, g64), 256, 0, st>>>(b.Sig, np, n, b.sbuf, b.cbuf);
+      }
+      h->stats.launches += 2 * n;
+    } else {
+      double* S = h->dU;
+      double* Sc = h->dU + np * EPB;
+      GPK_CK(h, cudaMemcpyAsync(mun, b.mu, sizeof(double), cudaMemcpyDeviceToDevice, st));   // slot 0 = mu[0]
+      const unsigned gsite = (unsigned)((n + 255) / 256);
+      for (int i0 = 0; i0 < (int)n; i0 += EPB) {
+        const int bl = ((int)n - i0 < EPB) ? (int)n - i0 : EPB;
+        GPK_CK(h, cudaMemsetAsync(S, 0, (size_t)(2 * np * EPB) * sizeof(double), st));
+        for (int t = 0; t < bl; ++t) {
+          const int i = i0 + t;
+          ep_site_blk_kernel<<<gsite, 256, 0, st>>>(b.Sig, np, n, i, t, b.y, b.m, b.ttau, b.tnu, b.mu, S, Sc, cvec,
+                                                    mun + (i & 1), mun + ((i + 1) & 1));
+        }
+        GemmArgs a{};                                 // Sigma0 -= (S diag c) S'  on the lower triangle
+        a.A = Sc; a.B = S; a.C = b.Sig; a.lda = np; a.ldb = np; a.ldc = np; a.K = EPB; a.tri = 1;
+        GPK_TRY(launch_gemm_nt(h, st, 1, a, T, T));
+        h->stats.launches += bl;
+      }
     }
-    h->stats.launches += 2 * n;
     GPK_CK(h, cudaGetLastError());
     GPK_TRY(ep_compute_params(h, st, b, n, np, &nlz, &info));
     if (info != 0) return info;
