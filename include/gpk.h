@@ -182,6 +182,11 @@ int gpk_dbg_gemm_nt(gpk_handle h, int mode, int64_t M, int64_t N, int64_t K,
 int gpk_dbg_diag(gpk_handle h, const double* A128, double* L128, double* Linv128,
                  double* logdet_half, int* info);
 
+/* debug: C(128,N) int32 = A(128,K) int8 * B(N,K)' int8 (row-major host arrays) through one tcgen05.mma.kind::i8 tile
+ * (TMEM accumulator, shared-memory descriptors) - the building block of the planned int8 emulation of the fp64
+ * trailing update.  N in {64,128,256}, K a multiple of 32, K <= 256.                                             */
+int gpk_dbg_i8_tile(gpk_handle h, int N, int K, const int8_t* A, const int8_t* B, int32_t* C);
+
 #ifdef __cplusplus
 }
 #endif

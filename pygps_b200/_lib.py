@@ -74,6 +74,7 @@ PROTOTYPES = [
     ("gpk_bench_copy", _I, [_H, _L, _I, c_double_p]),
     ("gpk_dbg_gemm_nt", _I, [_H, _I, _L, _L, _L, c_double_p, c_double_p, c_double_p]),
     ("gpk_dbg_diag", _I, [_H, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
+    ("gpk_dbg_i8_tile", _I, [_H, _I, _I, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 ]
 
 
@@ -356,6 +357,15 @@ class Engine(object):
         rc = self._lib.gpk_dbg_gemm_nt(self._h, mode, M, N, K, A.ctypes.data_as(c_double_p),
                                        B.ctypes.data_as(c_double_p), C.ctypes.data_as(c_double_p))
         self._check(rc, "gpk_dbg_gemm_nt")
+        return C
+
+    def dbg_i8_tile(self, A, B):
+        """int32 C = A (128,K) int8 @ B (N,K) int8 ^T through one tcgen05.mma.kind::i8 tile."""
+        A = np.ascontiguousarray(A, dtype=np.int8)
+        B = np.ascontiguousarray(B, dtype=np.int8)
+        C = np.zeros((128, B.shape[0]), dtype=np.int32)
+        rc = self._lib.gpk_dbg_i8_tile(self._h, B.shape[0], A.shape[1], A.ctypes.data, B.ctypes.data, C.ctypes.data)
+        self._check(rc, "gpk_dbg_i8_tile")
         return C
 
     def dbg_diag(self, A):

@@ -167,3 +167,14 @@ def test_tools_jitchol_solve_chol_drop_in(eng, golden):
     assert np.allclose(X2, g["chol_X"], rtol=1e-8, atol=1e-10)
     with pytest.raises(Exception):
         pg.tools.solve_chol(L.T, np.zeros((3, 1)))
+
+
+@pytest.mark.parametrize("N,K", [(64, 32), (64, 128), (128, 64), (256, 256)])
+def test_tcgen05_int8_tile_is_exact(eng, N, K):
+    """tcgen05.mma.kind::i8 through hand-built shared-memory/instruction descriptors and a TMEM accumulator:
+    exact int32 result (the primitive of the int8 emulation of the fp64 trailing update)."""
+    rng = np.random.default_rng(N + K)
+    A = rng.integers(-64, 65, size=(128, K), dtype=np.int8)
+    B = rng.integers(-64, 65, size=(N, K), dtype=np.int8)
+    C = eng.dbg_i8_tile(A, B)
+    assert np.array_equal(C, A.astype(np.int32) @ B.astype(np.int32).T)
