@@ -187,6 +187,17 @@ int gpk_dbg_diag(gpk_handle h, const double* A128, double* L128, double* Linv128
  * trailing update.  N in {64,128,256}, K a multiple of 32, K <= 256.                                             */
 int gpk_dbg_i8_tile(gpk_handle h, int N, int K, const int8_t* A, const int8_t* B, int32_t* C);
 
+/* debug/bench: C (n,n column-major, lower triangle) -= P (n,kw column-major) * P' - the trailing update of the
+ * blocked Cholesky (reference: the BLAS-3 inside np.linalg.cholesky, tools.py:86).  mode 0: int8 tensor-core
+ * (Ozaki split, tcgen05 + TMEM) path, mode 1: fp64 DMMA path.  n, kw multiples of 128.  *ms = mean device time
+ * of the update over `reps` repetitions (each starts from the given C).                                          */
+/* bench: issue rate of tcgen05.mma.kind::i8 (128 x N x 32) for a given shared-memory descriptor geometry
+ * (leading/stride byte offsets, per-MMA operand step), max clocks per MMA over `ctas` concurrent CTAs.        */
+int gpk_bench_i8_rate(gpk_handle h, int N, int iters, int lbo, int sbo, int astep, int same_acc, int ctas,
+                      double* clk_per_mma);
+
+int gpk_dbg_oz_syrk(gpk_handle h, int64_t n, int kw, const double* P, double* C, int mode, int reps, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

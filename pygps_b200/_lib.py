@@ -75,6 +75,8 @@ PROTOTYPES = [
     ("gpk_dbg_gemm_nt", _I, [_H, _I, _L, _L, _L, c_double_p, c_double_p, c_double_p]),
     ("gpk_dbg_diag", _I, [_H, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
     ("gpk_dbg_i8_tile", _I, [_H, _I, _I, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    ("gpk_bench_i8_rate", _I, [_H, _I, _I, _I, _I, _I, _I, _I, c_double_p]),
+    ("gpk_dbg_oz_syrk", _I, [_H, _L, _I, c_double_p, c_double_p, _I, _I, c_double_p]),
 ]
 
 
@@ -367,6 +369,22 @@ class Engine(object):
         rc = self._lib.gpk_dbg_i8_tile(self._h, B.shape[0], A.shape[1], A.ctypes.data, B.ctypes.data, C.ctypes.data)
         self._check(rc, "gpk_dbg_i8_tile")
         return C
+
+    def bench_i8_rate(self, N, iters, lbo, sbo, astep=0, same_acc=0, ctas=148):
+        v = ctypes.c_double(0)
+        rc = self._lib.gpk_bench_i8_rate(self._h, N, iters, lbo, sbo, astep, same_acc, ctas, ctypes.byref(v))
+        self._check(rc, "gpk_bench_i8_rate")
+        return v.value
+
+    def dbg_oz_syrk(self, P, C, mode=0, reps=1):
+        """lower(C) - P P' through the int8 tensor-core path (mode 0) or the DMMA path (mode 1); returns (C_new, ms)."""
+        P = np.asfortranarray(P, dtype=np.float64)
+        C = np.array(C, dtype=np.float64, order="F", copy=True)
+        ms = ctypes.c_double(0)
+        rc = self._lib.gpk_dbg_oz_syrk(self._h, P.shape[0], P.shape[1], P.ctypes.data_as(c_double_p),
+                                       C.ctypes.data_as(c_double_p), mode, reps, ctypes.byref(ms))
+        self._check(rc, "gpk_dbg_oz_syrk")
+        return C, ms.value
 
     def dbg_diag(self, A):
         A = np.asfortranarray(A, dtype=np.float64)

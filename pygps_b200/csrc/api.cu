@@ -182,6 +182,9 @@ static int free_all(Handle* h) {
   }
   if (h->dInfo) cudaFree(h->dInfo);
   h->dInfo = nullptr;
+  if (h->ozSl) cudaFree(h->ozSl);
+  if (h->ozEx) cudaFree(h->ozEx);
+  h->ozSl = nullptr; h->ozEx = nullptr; h->ozCap = h->ozExCap = 0;
   h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = 0;
   h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->cgA = h->cgDinv = h->cgPack = h->cgVec = h->ceK = h->ceSig = h->ceVec = h->ceSW = h->capUs = h->capLpost = h->capAlphaU = 0;
   return 0;

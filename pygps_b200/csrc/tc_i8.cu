@@ -7,50 +7,9 @@
 // tile product used by the tests.
 #include <cstdint>
 #include "gpk_internal.cuh"
+#include "tc_common.cuh"
 
 namespace gpk {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, SWIZZLE_NONE ("interleave") canonical layout, in 16-byte units: ((8,n),2):((1,SBO),LBO)
-//   address(row, kchunk) = start + (row%8)*16 + (row/8)*SBO + kchunk*LBO
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version 1 (Blackwell)
-  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
-}
-
-// kind::i8, signed x signed -> s32, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint64_t* mbar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(smem_u32(mbar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr) : "memory");
-}
 
 // C(128 x N, int32, row-major) = A(128 x K, int8, row-major) * B(N x K, int8, row-major)^T ; one CTA, 128 threads.
 template <int N>
@@ -109,9 +68,75 @@ __global__ void __launch_bounds__(128) i8_tile_kernel(const int8_t* __restrict__
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tbase), "n"(N < 32 ? 32 : N) : "memory");
 }
 
+// issue-rate probe: `iters` back-to-back MMAs (128 x N x 32, int8) from one thread per CTA, operands anywhere in a
+// 64 KB shared window, accumulators rotating over the 512 TMEM columns; clocks per MMA written per CTA.
+__global__ void __launch_bounds__(128) i8_rate_kernel(int N, int iters, uint32_t lbo, uint32_t sbo, uint32_t astep,
+                                                      int same_acc, float* out) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int c = tid; c < 65536 / 16; c += 128) reinterpret_cast<int4*>(sm)[c] = make_int4(0x01010101, 0x01010101, 0x01010101, 0x01010101);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 0) { mbar_init(&mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_i8(128, N);
+    const uint32_t amask = same_acc ? 0u : (uint32_t)(512 / N - 1);   // 512/N is a power of two for N in {64,128,256}
+    const uint32_t sa = smem_u32(sm);
+    uint64_t ad[8], bd[8];
+    uint32_t dcol[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      ad[q] = make_smem_desc(sa + q * astep, lbo, sbo);
+      bd[q] = make_smem_desc(sa + 32768 + q * astep, lbo, sbo);
+      dcol[q] = tbase + ((uint32_t)q & amask) * N;
+    }
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it += 8) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tc_mma_i8(dcol[q], ad[q], bd[q], idesc, 1u);
+    }
+    tc_commit(&mbar);
+    mbar_wait(&mbar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = (float)(t1 - t0) / iters;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tbase), "n"(512) : "memory");
+}
+
 }  // namespace gpk
 
 using namespace gpk;
+
+extern "C" int gpk_bench_i8_rate(gpk_handle hh, int N, int iters, int lbo, int sbo, int astep, int same_acc, int ctas,
+                                 double* clk_per_mma) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!clk_per_mma || N < 16 || N > 256 || N % 16 || iters < 1 || ctas < 1 || ctas > 1024) return GPK_ERR_ARG;
+  float* d = nullptr;
+  GPK_CK(h, cudaMalloc((void**)&d, ctas * sizeof(float)));
+  GPK_CK(h, cudaFuncSetAttribute(i8_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  i8_rate_kernel<<<ctas, 128, 65536, h->s_main>>>(N, iters, (uint32_t)lbo, (uint32_t)sbo, (uint32_t)astep, same_acc, d);
+  std::vector<float> v(ctas);
+  cudaError_t e = cudaMemcpyAsync(v.data(), d, ctas * sizeof(float), cudaMemcpyDeviceToHost, h->s_main);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_main);
+  cudaFree(d);
+  GPK_CK(h, e);
+  double m = 0;
+  for (float x : v) m = x > m ? x : m;
+  *clk_per_mma = m;
+  return 0;
+}
 
 extern "C" int gpk_dbg_i8_tile(gpk_handle hh, int N, int K, const int8_t* A, const int8_t* B, int32_t* C) {
   Handle* h;
