@@ -74,7 +74,7 @@ PROTOTYPES = [
     ("gpk_bench_copy", _I, [_H, _L, _I, c_double_p]),
     ("gpk_dbg_gemm_nt", _I, [_H, _I, _L, _L, _L, c_double_p, c_double_p, c_double_p]),
     ("gpk_dbg_diag", _I, [_H, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
-    ("gpk_dbg_i8_tile", _I, [_H, _I, _I, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    ("gpk_dbg_i8_tile", _I, [_H, _I, _I, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _I]),
     ("gpk_bench_i8_rate", _I, [_H, _I, _I, _I, _I, _I, _I, _I, c_double_p]),
     ("gpk_dbg_oz_syrk", _I, [_H, _L, _I, c_double_p, c_double_p, _I, _I, c_double_p]),
 ]
@@ -362,11 +362,14 @@ class Engine(object):
         return C
 
     def dbg_i8_tile(self, A, B):
-        """int32 C = A (128,K) int8 @ B (N,K) int8 ^T through one tcgen05.mma.kind::i8 tile."""
-        A = np.ascontiguousarray(A, dtype=np.int8)
-        B = np.ascontiguousarray(B, dtype=np.int8)
+        """int32 C = A (128,K) @ B (N,K)^T through one tcgen05.mma.kind::i8 tile; A, B int8 or uint8 arrays."""
+        fmt = (1 if A.dtype == np.uint8 else 0) | (2 if B.dtype == np.uint8 else 0)
+        A = np.ascontiguousarray(A)
+        B = np.ascontiguousarray(B)
+        if A.dtype.itemsize != 1 or B.dtype.itemsize != 1:
+            raise TypeError("int8 / uint8 operands expected")
         C = np.zeros((128, B.shape[0]), dtype=np.int32)
-        rc = self._lib.gpk_dbg_i8_tile(self._h, B.shape[0], A.shape[1], A.ctypes.data, B.ctypes.data, C.ctypes.data)
+        rc = self._lib.gpk_dbg_i8_tile(self._h, B.shape[0], A.shape[1], A.ctypes.data, B.ctypes.data, C.ctypes.data, fmt)
         self._check(rc, "gpk_dbg_i8_tile")
         return C
 

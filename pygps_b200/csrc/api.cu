@@ -55,6 +55,11 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   if (const char* e = getenv("GPK_POTRF_W")) { g_potrf_w = atoi(e); }
   const int W = (g_potrf_w < 1) ? ((T > 64) ? 3 : (T > 8 ? 2 : 1)) : (g_potrf_w > 8 ? 8 : g_potrf_w);
   const int nblk = (T + W - 1) / W;
+  // trailing updates with at least oz_min tile rows go to the int8 tensor cores (GPK_OZAKI=0 keeps everything on DMMA)
+  int oz = 0, oz_min = 24;
+  if (const char* e = getenv("GPK_OZAKI")) oz = atoi(e);
+  if (const char* e = getenv("GPK_OZAKI_MIN")) oz_min = atoi(e);
+  if (oz && T - W >= oz_min) GPK_TRY(oz_ensure(h, (int64_t)(T - W) * NB, W * NB));
   GPK_TRY(ensure_events(h, 2 * (size_t)T + 4));
   if (h->profile) GPK_TRY(ensure_prof_events(h, 2 * (size_t)T + 2));
   cudaEvent_t* ev_panel = h->ev.data();      // [T]   panel p factored and solved
@@ -101,16 +106,26 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
       if (h->profile) GPK_CK(h, cudaEventRecord(h->prof_ev[2 * h->prof_pairs], h->s_main));
       const int kw = (pe - pb) * NB;
       const int first = (W < rem) ? W : rem;           // the next block's columns go first
-      GemmArgs u{};
-      u.A = A + (int64_t)pe * NB + (int64_t)pb * NB * lda; u.B = u.A;
-      u.C = A + (int64_t)pe * NB * (1 + lda);
-      u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = kw; u.tri = 1; u.ti_off = 0; u.tj_off = 0;
-      GPK_TRY(launch_gemm_nt(h, h->s_main, 1, u, rem, first));
-      GPK_CK(h, cudaEventRecord(ev_col[j + 1], h->s_main));
-      if (rem > first) {
-        GemmArgs v = u;
-        v.B = u.B + (int64_t)first * NB; v.C = u.C + (int64_t)first * NB * lda; v.tj_off = first;
-        GPK_TRY(launch_gemm_nt(h, h->s_main, 1, v, rem, rem - first));
+      double* Pblk = A + (int64_t)pe * NB + (int64_t)pb * NB * lda;
+      double* Ctr = A + (int64_t)pe * NB * (1 + lda);
+      if (oz && rem >= oz_min) {
+        // int8 tensor-core path (ozaki.cu): slice the panel block once, then the same two launches
+        GPK_TRY(launch_oz_slice(h, h->s_main, Pblk, lda, rem * NB, kw));
+        GPK_TRY(launch_oz_syrk(h, h->s_main, Ctr, lda, rem * NB, kw, 0, first));
+        GPK_CK(h, cudaEventRecord(ev_col[j + 1], h->s_main));
+        if (rem > first) GPK_TRY(launch_oz_syrk(h, h->s_main, Ctr, lda, rem * NB, kw, first, rem));
+      } else {
+        GemmArgs u{};
+        u.A = Pblk; u.B = u.A;
+        u.C = Ctr;
+        u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = kw; u.tri = 1; u.ti_off = 0; u.tj_off = 0;
+        GPK_TRY(launch_gemm_nt(h, h->s_main, 1, u, rem, first));
+        GPK_CK(h, cudaEventRecord(ev_col[j + 1], h->s_main));
+        if (rem > first) {
+          GemmArgs v = u;
+          v.B = u.B + (int64_t)first * NB; v.C = u.C + (int64_t)first * NB * lda; v.tj_off = first;
+          GPK_TRY(launch_gemm_nt(h, h->s_main, 1, v, rem, rem - first));
+        }
       }
       if (h->profile) { GPK_CK(h, cudaEventRecord(h->prof_ev[2 * h->prof_pairs + 1], h->s_main)); h->prof_pairs++; }
       const double nt = (double)rem * NB;
@@ -183,8 +198,8 @@ static int free_all(Handle* h) {
   if (h->dInfo) cudaFree(h->dInfo);
   h->dInfo = nullptr;
   if (h->ozSl) cudaFree(h->ozSl);
-  if (h->ozEx) cudaFree(h->ozEx);
-  h->ozSl = nullptr; h->ozEx = nullptr; h->ozCap = h->ozExCap = 0;
+  if (h->ozSc) cudaFree(h->ozSc);
+  h->ozSl = nullptr; h->ozSc = nullptr; h->ozCap = h->ozScCap = 0;
   h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = 0;
   h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->cgA = h->cgDinv = h->cgPack = h->cgVec = h->ceK = h->ceSig = h->ceVec = h->ceSW = h->capUs = h->capLpost = h->capAlphaU = 0;
   return 0;

@@ -4,21 +4,23 @@
 // rank-(W*128) update is >90 % of gp.GPR.getPosterior() at N=16384.  `tcgen05.mma.kind::i8` runs at 4.5 POP/s with
 // EXACT int32 accumulation in TMEM.  The update is therefore computed by an error-free split (Ozaki scheme):
 //
-//   row i of the panel:  P[i,:] = 2^e_i * sum_{t=1..S} d_t[i,:] * 2^(-7t)  + O(2^(e_i-7S-1)),   d_t int8 in [-64,64]
-//   (P P')[i,j]          = 2^(e_i+e_j) * sum_{m=2..S+1} 2^(-7m) * G_m[i,j],   G_m = sum_{t+u=m} d_t[i,:]·d_u[j,:]
+//   row i of the panel:  P[i,:] = 2^e_i * sum_{t=1..S} d_t[i,:] * 2^(-8t)  + O(2^(e_i-8S-1)),   d_t int8 in [-128,127]
+//   (P P')[i,j]          = 2^(e_i+e_j) * sum_{m=2..S+1} 2^(-8m) * G_m[i,j],   G_m = sum_{t+u=m} d_t[i,:]·d_u[j,:]
 //
-// Each G_m is an exact integer (|G_m| <= 8 * 384 * 64^2 < 2^31), the S accumulators G_2..G_{S+1} live in TMEM
-// (S x 64 columns), and only the final weighted sum is rounded, in fp64.  Products with t+u > S+1 are below 2^(-7(S+2)) relative to
-// the row scales and are dropped.  With S=8 the split keeps 56 bits per entry relative to the row maximum, i.e.
+// Each G_m is an exact integer (|G_m| <= 7 * 1024 * 128^2 < 2^31), the S accumulators G_2..G_{S+1} live in TMEM
+// (S x 64 columns), and only the final weighted sum is rounded, in fp64.  Products with t+u > S+1 are below 2^(-8(S+2)) relative to
+// the row scales and are dropped.  With S=7 (radix 256) the split keeps 56 bits per entry relative to the row maximum, i.e.
 // the result is at least as accurate as an fp64 DMMA accumulation of the same contraction.
 //
 // Kernels:
-//   oz_rowexp_kernel : e_i = exponent of the largest |P[i,k]| over the panel row
-//   oz_slice_kernel  : writes the int8 slices directly in the tensor core's canonical K-major "core matrix" order
+//   oz_slice_kernel  : row exponents, then the int8 slices written directly in the tensor core's canonical K-major "core matrix" order
 //                      [k-step 32][row group 8][slice t][k chunk 2][row 8][16 B], so that a (rows x 32 k) stage of
 //                      ALL slices of a tile is ONE contiguous block: a single cp.async.bulk (TMA) per operand per stage
-//   oz_syrk_kernel   : one CTA per 128x64 tile of C; warp 5 = TMA producer, warp 4 = MMA issuer, warps 0-3 = epilogue
-//                      (TMEM -> fp64 -> C).  S(S+1)/2 MMAs of 128x64x32 per k-step.
+//   oz_syrk_kernel   : 128x64 tiles of C (a few per CTA, lower triangle only); warp 9 = TMA producer, warp 8 = MMA
+//                      issuer, warps 0-7 = epilogue (C prefetch -> TMEM -> fp64 -> C).  S(S+1)/2 MMAs of 128x64x32
+//                      per k-step; the producer runs ahead into the next tile while the epilogue drains TMEM.
+// Short CTAs (not one persistent CTA per SM) on purpose: the high-priority panel stream of the look-ahead
+// Cholesky needs SMs to free up every few microseconds.
 #include <cstdint>
 #include <cstdlib>
 #include "gpk_internal.cuh"
@@ -31,68 +33,114 @@ constexpr int OZ_ST = 4;         // pipeline stages
 constexpr int OZ_EPI_WARPS = 8;  // epilogue warps 0..7, then the MMA issuer warp and the TMA producer warp
 constexpr int OZ_THREADS = (OZ_EPI_WARPS + 2) * 32;
 
-__global__ void __launch_bounds__(256) oz_rowexp_kernel(const double* __restrict__ P, int64_t lda, int n, int kw,
-                                                         int* __restrict__ ex) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  double m = 0.0;
-#pragma unroll 8
-  for (int k = 0; k < kw; ++k) m = fmax(m, fabs(P[i + (int64_t)k * lda]));
-  // |x| < 2^(ilogb+1)  ->  |x| * 2^-(ilogb+2) < 0.5
-  int e = 0;
-  if (m > 0.0 && m < 1.0e300) e = ilogb(m) + 2;
-  ex[i] = e;
+// Balanced digits in radix 2^RB, all slices signed: x (|x| <= 0.48) is rounded ONCE to S*RB fractional bits
+// (integer q, exact in int64 since S*RB <= 56), then q is split from the least significant digit upwards with
+// carries, d_t in [-2^(RB-1), 2^(RB-1)-1].  x = sum_t d_t 2^(-RB(t+1)) + r, |r| <= 2^(-S*RB-1), unbiased.
+// Balanced digits keep the dropped cross terms (t+u > S-1) at random-walk size; unsigned digits would add them
+// coherently (measured: 10x larger error).  RB=8,S=7 and RB=7,S=8 both carry 56 bits; the former needs 28 instead
+// of 36 tensor-core products per k-step.
+template <int S, int RB>
+__device__ __forceinline__ void oz_digits(double x, int8_t (&d)[S]) {
+  long long q = __double2ll_rn(x * (double)(1ll << (S * RB)));
+#pragma unroll
+  for (int t = S - 1; t >= 0; --t) {
+    const int lo = (int)(q & ((1 << RB) - 1));
+    const int dd = (lo >= (1 << (RB - 1))) ? lo - (1 << RB) : lo;
+    d[t] = (int8_t)dd;
+    q = (q - dd) >> RB;
+  }
 }
 
-template <int S>
+// One CTA = 32 panel rows x the whole contraction length.  Pass 1: row exponent; pass 2: digits, written in the
+// tensor core's canonical order so that the CTA's output per k-step (4 row groups x S x 256 B) is contiguous.
+template <int S, int RB>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t lda, int n, int kw,
-                                                        const int* __restrict__ ex, int8_t* __restrict__ sl) {
-  // CTA: 32 rows x 32 k (one k-step).  Output block = 4 row groups x S x 256 B, contiguous in `sl`.
+                                                        double* __restrict__ sc, int8_t* __restrict__ sl) {
   __shared__ __align__(16) int8_t out[4][S][2][8][16];
-  const int r0 = blockIdx.x * 32, ks = blockIdx.y;
+  __shared__ double red[8][32];
+  __shared__ int sh_e[32];
+  const int r0 = blockIdx.x * 32;
   const int r = threadIdx.x & 31, kq = threadIdx.x >> 5;
-  const int e = ex[r0 + r];
-  for (int kk = kq; kk < 32; kk += 8) {
-    double x = scalbn(P[(r0 + r) + (int64_t)(ks * 32 + kk) * lda], -e);   // exact; |x| < 0.5
+  const double* prow = P + r0 + r;
+  double m = 0.0;
+#pragma unroll 4
+  for (int k = kq; k < kw; k += 8) m = fmax(m, fabs(prow[(int64_t)k * lda]));
+  red[kq][r] = m;
+  __syncthreads();
+  if (kq == 0) {
 #pragma unroll
-    for (int t = 0; t < S; ++t) {
-      const double y = x * 128.0;
-      const double d = rint(y);          // in [-64, 64]
-      x = y - d;                         // exact, |x| <= 0.5
-      out[r >> 3][t][kk >> 4][r & 7][kk & 15] = (int8_t)(int)d;
+    for (int q = 1; q < 8; ++q) m = fmax(m, red[q][r]);
+    // |x| < 2^(ilogb+1)  ->  |x| * 2^-(ilogb+2) < 0.5 ; exponents clamped so that 2^(e-RB) stays a normal double
+    int e = 0;
+    if (m > 0.0 && m < 1.0e150) {
+      e = ilogb(m) + 2;
+      if (scalbn(m, -e) > 0.48) ++e;         // head room for the carry into the leading digit
     }
+    if (e < -500) e = -500;
+    sh_e[r] = e;
+    sc[r0 + r] = scalbn(1.0, e - RB);
   }
   __syncthreads();
-  int8_t* dst = sl + (size_t)ks * ((size_t)n * S * 32) + (size_t)r0 * S * 32;
+  const int e = sh_e[r];
+  const size_t kstride = (size_t)n * S * 32;
+  int4* dst4 = reinterpret_cast<int4*>(sl + (size_t)r0 * S * 32);
   const int4* src4 = reinterpret_cast<const int4*>(&out[0][0][0][0][0]);
-  int4* dst4 = reinterpret_cast<int4*>(dst);
-  for (int c = threadIdx.x; c < 4 * S * 16; c += 256) dst4[c] = src4[c];
+  for (int ks = 0; ks < kw / 32; ++ks) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = kq + 8 * j;
+      int8_t d[S];
+      oz_digits<S, RB>(scalbn(prow[(int64_t)(ks * 32 + kk) * lda], -e), d);   // scaling exact; |x| <= 0.48
+#pragma unroll
+      for (int t = 0; t < S; ++t) out[r >> 3][t][kk >> 4][r & 7][kk & 15] = d[t];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 4 * S * 16; c += 256) dst4[ks * (kstride / 16) + c] = src4[c];
+    __syncthreads();
+  }
 }
 
 struct OzArgs {
   const int8_t* sl;   // slices of the panel rows [kw/32][n/8][S][2][8][16]
-  const int* ex;      // row exponents
+  const double* sc;   // 2^(e_i - RB) per row
   double* C;          // trailing matrix origin (row 0 / col 0 of the sliced rows), column-major
   int64_t ldc;
   int n, kw;          // sliced rows, contraction length
-  int cj0;            // first 64-column tile of this launch
+  int jb0;            // first 128-column block of this launch
+  int ntiles;         // lower-triangle 128x64 tiles of this launch
+  int tpc;            // tiles per CTA
 };
 
-template <int S>
+// tile index -> (128-row tile, 64-column tile): column blocks jb0.. in order, each 128-column block jb holds
+// 2*(nt-jb) tiles (two 64-column halves x the row tiles jb..nt-1)
+__device__ __forceinline__ void oz_decode(int idx, int nt, int jb0, int& ti, int& tj) {
+  // f(jb) = tiles before block jb = 2*nt*(jb-jb0) - (jb*(jb-1) - jb0*(jb0-1))
+  const double bb = 2.0 * nt + 1.0, cc = (double)idx + 2.0 * nt * jb0 - (double)jb0 * (jb0 - 1);
+  int jb = (int)((bb - sqrt(fmax(bb * bb - 4.0 * cc, 0.0))) * 0.5);
+  if (jb < jb0) jb = jb0;
+  if (jb > nt - 1) jb = nt - 1;
+  auto f = [&](int b) { return 2 * nt * (b - jb0) - (b * (b - 1) - jb0 * (jb0 - 1)); };
+  while (jb > jb0 && f(jb) > idx) --jb;
+  while (jb + 1 < nt && f(jb + 1) <= idx) ++jb;
+  const int rem = idx - f(jb), cnt = nt - jb;
+  tj = 2 * jb + rem / cnt;
+  ti = jb + rem % cnt;
+}
+
+template <int S, int RB>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   constexpr uint32_t A_BYTES = 128 * S * 32, B_BYTES = OZ_BN * S * 32, STAGE = A_BYTES + B_BYTES;
   constexpr uint32_t TCOLS = 512;
+  constexpr double HORNER = 1.0 / (double)(1 << RB);
   extern __shared__ __align__(128) uint8_t sm[];
-  __shared__ uint64_t full[OZ_ST], empty[OZ_ST], done;
+  __shared__ uint64_t full[OZ_ST], empty[OZ_ST], done, tfree;
   __shared__ uint32_t tmem_base;
-  __shared__ double scol[OZ_BN];     // 2^(e_j - 7) of the tile's columns
 
-  const int ti = blockIdx.x, tj = a.cj0 + blockIdx.y;
-  const int row0 = ti * 128, col0 = tj * OZ_BN;
-  if (row0 + 128 <= col0) return;                       // tile entirely above the diagonal
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nk = a.kw / 32;
+  const int nk = a.kw / 32, nt = a.n / 128;
   const size_t kstride = (size_t)a.n * S * 32;
+  const int tile0 = blockIdx.x * a.tpc;
+  const int tile1 = min(tile0 + a.tpc, a.ntiles);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(TCOLS) : "memory");
@@ -101,9 +149,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   if (tid == 32) {
     for (int s = 0; s < OZ_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&done, 1);
+    mbar_init(&tfree, OZ_EPI_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (tid >= 64 && tid < 64 + OZ_BN) scol[tid - 64] = scalbn(1.0, a.ex[col0 + tid - 64] - 7);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -111,70 +159,91 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
 
   if (warp == OZ_EPI_WARPS + 1) {
     if (elect_one()) {
-      const int8_t* gA = a.sl + (size_t)row0 * S * 32;
-      const int8_t* gB = a.sl + (size_t)col0 * S * 32;
-      for (int ks = 0; ks < nk; ++ks) {
-        const int slot = ks % OZ_ST;
-        if (ks >= OZ_ST) mbar_wait(&empty[slot], ((ks / OZ_ST) - 1) & 1);
-        mbar_expect_tx(&full[slot], STAGE);
-        uint8_t* s = sm + (size_t)slot * STAGE;
-        bulk_g2s(s, gA + ks * kstride, A_BYTES, &full[slot]);
-        bulk_g2s(s + A_BYTES, gB + ks * kstride, B_BYTES, &full[slot]);
+      int it = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        int ti, tj;
+        oz_decode(tile, nt, a.jb0, ti, tj);
+        const int8_t* gA = a.sl + (size_t)ti * 128 * S * 32;
+        const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
+        for (int ks = 0; ks < nk; ++ks, ++it) {
+          const int slot = it % OZ_ST;
+          if (it >= OZ_ST) mbar_wait(&empty[slot], ((it / OZ_ST) - 1) & 1);
+          mbar_expect_tx(&full[slot], STAGE);
+          uint8_t* s = sm + (size_t)slot * STAGE;
+          bulk_g2s(s, gA + ks * kstride, A_BYTES, &full[slot]);
+          bulk_g2s(s + A_BYTES, gB + ks * kstride, B_BYTES, &full[slot]);
+        }
       }
     }
   } else if (warp == OZ_EPI_WARPS) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_i8(128, OZ_BN);
-      // descriptors differ only in the 14-bit start-address field: slice t sits 256 B (= 16 units) further
+      // smem descriptors differ only in the 14-bit start-address field: slice t sits 256 B (= 16 units) further
       const uint64_t dbase = make_smem_desc(0, 128, S * 256);
-      for (int ks = 0; ks < nk; ++ks) {
-        const int slot = ks % OZ_ST;
-        mbar_wait(&full[slot], (ks / OZ_ST) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(sm + (size_t)slot * STAGE);
-        const uint64_t da = dbase | (uint64_t)(sa >> 4), db = dbase | (uint64_t)((sa + A_BYTES) >> 4);
+      int it = 0, tcount = 0;
+      for (int tile = tile0; tile < tile1; ++tile, ++tcount) {
+        if (tcount > 0) { mbar_wait(&tfree, (tcount - 1) & 1); tc_fence_after(); }
+        for (int ks = 0; ks < nk; ++ks, ++it) {
+          const int slot = it % OZ_ST;
+          mbar_wait(&full[slot], (it / OZ_ST) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sm + (size_t)slot * STAGE);
+          const uint64_t da = dbase | (uint64_t)(sa >> 4), db = dbase | (uint64_t)((sa + A_BYTES) >> 4);
 #pragma unroll
-        for (int t = 0; t < S; ++t) {
+          for (int t = 0; t < S; ++t) {
 #pragma unroll
-          for (int u = 0; u < S - t; ++u)
-            tc_mma_i8(tbase + (uint32_t)(t + u) * OZ_BN, da + 16 * t, db + 16 * u, idesc, (ks > 0 || t > 0) ? 1u : 0u);
+            for (int u = 0; u < S - t; ++u) {
+              tc_mma_i8(tbase + (uint32_t)(t + u) * OZ_BN, da + 16 * t, db + 16 * u, idesc, (ks > 0 || t > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty[slot]);
         }
-        tc_commit(&empty[slot]);
+        tc_commit(&done);
       }
-      tc_commit(&done);
     }
   } else {
     // epilogue warps: TMEM lanes 32*(warp%4).. = rows of the tile; warps 4..7 take the upper 32 columns.
     // The C tile is fetched BEFORE the accumulators are complete, so its latency hides under the MMA loop.
     const int q4 = warp & 3, chalf = (warp >> 2) * (OZ_BN / 2);
-    const int gi = row0 + q4 * 32 + lane;
-    const double si = scalbn(1.0, a.ex[gi] - 7);
-    double* crow = a.C + gi + (int64_t)(col0 + chalf) * a.ldc;
-    double cv[OZ_BN / 2];
-#pragma unroll
-    for (int q = 0; q < OZ_BN / 2; ++q) cv[q] = (gi >= col0 + chalf + q) ? crow[(int64_t)q * a.ldc] : 0.0;
-    mbar_wait(&done, 0);
-    tc_fence_after();
     const uint32_t tw = tbase + ((uint32_t)(q4 * 32) << 16) + chalf;
+    int tcount = 0;
+    for (int tile = tile0; tile < tile1; ++tile, ++tcount) {
+      int ti, tj;
+      oz_decode(tile, nt, a.jb0, ti, tj);
+      const int gi = ti * 128 + q4 * 32 + lane, gj0 = tj * OZ_BN + chalf;
+      const double si = a.sc[gi];
+      double* crow = a.C + gi + (int64_t)gj0 * a.ldc;
+      // pull this thread's 32 C entries towards L2 now; they are read after the accumulators are complete
 #pragma unroll
-    for (int c0 = 0; c0 < OZ_BN / 2; c0 += 16) {
-      double acc[16];
-      uint32_t v[16];
-      tc_ld16(tw + (uint32_t)(S - 1) * OZ_BN + c0, v);
-      tc_wait_ld();
+      for (int q = 0; q < OZ_BN / 2; ++q)
+        if (gi >= gj0 + q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + (int64_t)q * a.ldc));
+      mbar_wait(&done, tcount & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < OZ_BN / 2; c0 += 8) {
+        uint32_t v[S][8];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q] = (double)(int)v[q];
+        for (int m = 0; m < S; ++m) tc_ld8(tw + (uint32_t)m * OZ_BN + c0, v[m]);
+        double cv[8], sj[8];
 #pragma unroll
-      for (int m = S - 2; m >= 0; --m) {
-        tc_ld16(tw + (uint32_t)m * OZ_BN + c0, v);
+        for (int q = 0; q < 8; ++q) {
+          cv[q] = (gi >= gj0 + c0 + q) ? crow[(int64_t)(c0 + q) * a.ldc] : 0.0;
+          sj[q] = __ldg(a.sc + gj0 + c0 + q);
+        }
         tc_wait_ld();
+        if (c0 + 8 == OZ_BN / 2) {           // all accumulator reads of this tile are done: hand TMEM back
+          tc_fence_before();
+          mbar_arrive(&tfree);
+        }
 #pragma unroll
-        for (int q = 0; q < 16; ++q) acc[q] = fma(acc[q], 0.0078125, (double)(int)v[q]);
-      }
+        for (int q = 0; q < 8; ++q) {
+          // int32 -> fp64 without the (slow) conversion unit: 2^52 + 2^31 + v is exactly representable
+          double acc = __hiloint2double(0x43300000, (int)(v[S - 1][q] ^ 0x80000000u)) - 4503601774854144.0;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        if (gi >= col0 + chalf + c0 + q)
-          crow[(int64_t)(c0 + q) * a.ldc] = cv[c0 + q] - (acc[q] * si) * scol[chalf + c0 + q];
+          for (int m = S - 2; m >= 0; --m)
+            acc = fma(acc, HORNER, __hiloint2double(0x43300000, (int)(v[m][q] ^ 0x80000000u)) - 4503601774854144.0);
+          if (gi >= gj0 + c0 + q) crow[(int64_t)(c0 + q) * a.ldc] = cv[q] - (acc * si) * sj[q];
+        }
       }
     }
   }
@@ -183,13 +252,19 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tbase), "n"(TCOLS) : "memory");
 }
 
-static int oz_slices() {
-  static int s = -1;
-  if (s < 0) {
-    s = 8;
-    if (const char* e = getenv("GPK_OZAKI_SLICES")) { const int v = atoi(e); if (v == 7 || v == 8) s = v; }
+struct OzCfg { int S, RB, tpc; };
+static OzCfg oz_cfg() {
+  static OzCfg c{0, 0, 0};
+  if (c.S == 0) {
+    c.RB = 8; c.S = 7; c.tpc = 1;
+    if (const char* e = getenv("GPK_OZAKI_RADIX")) { const int v = atoi(e); if (v == 7 || v == 8) c.RB = v; }
+    if (c.RB == 7) c.S = 8;
+    if (const char* e = getenv("GPK_OZAKI_SLICES")) { const int v = atoi(e); if (v >= 6 && v <= 8) c.S = v; }
+    if (c.RB == 8 && c.S == 8) c.S = 7;
+    if (c.RB == 7 && c.S == 6) c.S = 7;
+    if (const char* e = getenv("GPK_OZAKI_TPC")) { const int v = atoi(e); if (v >= 1 && v <= 64) c.tpc = v; }
   }
-  return s;
+  return c;
 }
 
 int oz_ensure(Handle* h, int64_t n, int kw) {
@@ -200,43 +275,52 @@ int oz_ensure(Handle* h, int64_t n, int kw) {
     GPK_CK(h, cudaMalloc((void**)&h->ozSl, need));
     h->ozCap = need;
   }
-  if (h->ozExCap < (size_t)n) {
-    if (h->ozEx) cudaFree(h->ozEx);
-    h->ozEx = nullptr; h->ozExCap = 0;
-    GPK_CK(h, cudaMalloc((void**)&h->ozEx, (size_t)n * sizeof(int)));
-    h->ozExCap = (size_t)n;
+  if (h->ozScCap < (size_t)n) {
+    if (h->ozSc) cudaFree(h->ozSc);
+    h->ozSc = nullptr; h->ozScCap = 0;
+    GPK_CK(h, cudaMalloc((void**)&h->ozSc, (size_t)n * sizeof(double)));
+    h->ozScCap = (size_t)n;
   }
   return 0;
 }
 
-// slice the panel P (n rows x kw columns, column-major, lda) into h->ozSl / h->ozEx
+template <int S, int RB>
+static int oz_slice_t(Handle* h, cudaStream_t st, const double* P, int64_t lda, int n, int kw) {
+  oz_slice_kernel<S, RB><<<n / 32, 256, 0, st>>>(P, lda, n, kw, h->ozSc, h->ozSl);
+  GPK_CK(h, cudaGetLastError());
+  return 0;
+}
+
+// slice the panel P (n rows x kw columns, column-major, lda) into h->ozSl / h->ozSc
 int launch_oz_slice(Handle* h, cudaStream_t st, const double* P, int64_t lda, int n, int kw) {
   if (n % 128 != 0 || kw % 32 != 0) return GPK_ERR_ARG;
-  const int S = oz_slices();
-  oz_rowexp_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, lda, n, kw, h->ozEx);
-  dim3 g(n / 32, kw / 32);
-  if (S == 8) oz_slice_kernel<8><<<g, 256, 0, st>>>(P, lda, n, kw, h->ozEx, h->ozSl);
-  else oz_slice_kernel<7><<<g, 256, 0, st>>>(P, lda, n, kw, h->ozEx, h->ozSl);
+  const OzCfg c = oz_cfg();
+  if (c.RB == 7) return c.S == 8 ? oz_slice_t<8, 7>(h, st, P, lda, n, kw) : oz_slice_t<7, 7>(h, st, P, lda, n, kw);
+  return c.S == 7 ? oz_slice_t<7, 8>(h, st, P, lda, n, kw) : oz_slice_t<6, 8>(h, st, P, lda, n, kw);
+}
+
+template <int S, int RB>
+static int oz_syrk_t(Handle* h, cudaStream_t st, const OzArgs& a) {
+  static bool attr_done = false;
+  const size_t smem = (size_t)OZ_ST * (128 + OZ_BN) * S * 32;
+  if (!attr_done) {
+    GPK_CK(h, cudaFuncSetAttribute(oz_syrk_kernel<S, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  oz_syrk_kernel<S, RB><<<(a.ntiles + a.tpc - 1) / a.tpc, OZ_THREADS, smem, st>>>(a);
   GPK_CK(h, cudaGetLastError());
   return 0;
 }
 
-// C(lower tiles, 64-column tiles [cj0, cj1)) -= P·P' from the current slices
-int launch_oz_syrk(Handle* h, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int cj0, int cj1) {
-  const int S = oz_slices();
-  static bool attr_done = false;
-  const size_t smem8 = (size_t)OZ_ST * (128 + OZ_BN) * 8 * 32, smem7 = (size_t)OZ_ST * (128 + OZ_BN) * 7 * 32;
-  if (!attr_done) {
-    GPK_CK(h, cudaFuncSetAttribute(oz_syrk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-    GPK_CK(h, cudaFuncSetAttribute(oz_syrk_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));
-    attr_done = true;
-  }
-  OzArgs a{h->ozSl, h->ozEx, C, ldc, n, kw, cj0};
-  dim3 g(n / 128, cj1 - cj0);
-  if (S == 8) oz_syrk_kernel<8><<<g, OZ_THREADS, smem8, st>>>(a);
-  else oz_syrk_kernel<7><<<g, OZ_THREADS, smem7, st>>>(a);
-  GPK_CK(h, cudaGetLastError());
-  return 0;
+// C(lower triangle, 128-column blocks [jb0, jb1)) -= P·P' from the current slices
+int launch_oz_syrk(Handle* h, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1) {
+  const OzCfg c = oz_cfg();
+  const int nt = n / 128;
+  if (jb0 < 0 || jb1 > nt || jb0 >= jb1) return GPK_ERR_ARG;
+  const int ntiles = 2 * nt * (jb1 - jb0) - (jb1 * (jb1 - 1) - jb0 * (jb0 - 1));
+  OzArgs a{h->ozSl, h->ozSc, C, ldc, n, kw, jb0, ntiles, c.tpc};
+  if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
+  return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
 }
 
 }  // namespace gpk
@@ -263,7 +347,7 @@ extern "C" int gpk_dbg_oz_syrk(gpk_handle hh, int64_t n, int kw, const double* P
     cudaEventRecord(h->t0, st);
     if (mode == 0) {
       rc = launch_oz_slice(h, st, dP, n, (int)n, kw);
-      if (rc == 0) rc = launch_oz_syrk(h, st, dC, n, (int)n, kw, 0, (int)(n / OZ_BN));
+      if (rc == 0) rc = launch_oz_syrk(h, st, dC, n, (int)n, kw, 0, (int)(n / 128));
     } else {
       GemmArgs u{};
       u.A = dP; u.B = dP; u.C = dC; u.lda = n; u.ldb = n; u.ldc = n; u.K = kw; u.tri = 1;

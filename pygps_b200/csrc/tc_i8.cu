@@ -14,7 +14,7 @@ namespace gpk {
 // C(128 x N, int32, row-major) = A(128 x K, int8, row-major) * B(N x K, int8, row-major)^T ; one CTA, 128 threads.
 template <int N>
 __global__ void __launch_bounds__(128) i8_tile_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B,
-                                                      int32_t* __restrict__ C, int K) {
+                                                      int32_t* __restrict__ C, int K, int fmt) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint64_t mbar;
   __shared__ uint32_t tmem_base;
@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(128) i8_tile_kernel(const int8_t* __restrict__
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tbase = tmem_base;
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_i8(128, N);
+    // fmt bit 0: A holds unsigned bytes, bit 1: B holds unsigned bytes (operand format fields of the descriptor)
+    const uint32_t idesc = make_idesc_i8(128, N) & ~(((fmt & 1) ? (1u << 7) : 0u) | ((fmt & 2) ? (1u << 10) : 0u));
     for (int ks = 0; ks < K / 32; ++ks) {       // one MMA consumes 32 bytes of K = 2 chunks
       const uint64_t ad = make_smem_desc(smem_u32(sA) + ks * 2 * 128 * 16, 128 * 16, 8 * 16);
       const uint64_t bd = make_smem_desc(smem_u32(sB) + ks * 2 * N * 16, N * 16, 8 * 16);
@@ -138,7 +139,7 @@ extern "C" int gpk_bench_i8_rate(gpk_handle hh, int N, int iters, int lbo, int s
   return 0;
 }
 
-extern "C" int gpk_dbg_i8_tile(gpk_handle hh, int N, int K, const int8_t* A, const int8_t* B, int32_t* C) {
+extern "C" int gpk_dbg_i8_tile(gpk_handle hh, int N, int K, const int8_t* A, const int8_t* B, int32_t* C, int fmt) {
   Handle* h;
   GPK_TRY(check_handle(hh, &h));
   if (!A || !B || !C || (N != 64 && N != 128 && N != 256) || K % 32 != 0 || K <= 0 || K > 256) return GPK_ERR_ARG;
@@ -154,13 +155,13 @@ extern "C" int gpk_dbg_i8_tile(gpk_handle hh, int N, int K, const int8_t* A, con
   const size_t smem = (size_t)(K / 16) * (128 + N) * 16;
   if (N == 64) {
     cudaFuncSetAttribute(i8_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    i8_tile_kernel<64><<<1, 128, smem, st>>>(dA, dB, dC, K);
+    i8_tile_kernel<64><<<1, 128, smem, st>>>(dA, dB, dC, K, fmt);
   } else if (N == 128) {
     cudaFuncSetAttribute(i8_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    i8_tile_kernel<128><<<1, 128, smem, st>>>(dA, dB, dC, K);
+    i8_tile_kernel<128><<<1, 128, smem, st>>>(dA, dB, dC, K, fmt);
   } else {
     cudaFuncSetAttribute(i8_tile_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    i8_tile_kernel<256><<<1, 128, smem, st>>>(dA, dB, dC, K);
+    i8_tile_kernel<256><<<1, 128, smem, st>>>(dA, dB, dC, K, fmt);
   }
   cudaMemcpyAsync(C, dC, (size_t)128 * N * 4, cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);

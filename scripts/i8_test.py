@@ -1,16 +1,12 @@
-import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
-from pygps_b200 import _lib
-e = _lib.Engine(0)
-rng = np.random.default_rng(0)
-for N, K in ((64, 32), (64, 128), (128, 64), (256, 256)):
-    A = rng.integers(-64, 65, size=(128, K), dtype=np.int8)
-    B = rng.integers(-64, 65, size=(N, K), dtype=np.int8)
-    C = e.dbg_i8_tile(A, B)
-    ref = A.astype(np.int32) @ B.astype(np.int32).T
-    bad = int((C != ref).sum())
-    print("N=%d K=%d mismatches=%d of %d ; C[0,:4]=%s ref=%s" % (N, K, bad, C.size, C[0, :4], ref[0, :4]))
-    if bad:
-        rows = np.where((C != ref).any(1))[0]; cols = np.where((C != ref).any(0))[0]
-        print("  bad rows", rows[:10], "...", len(rows), " bad cols", cols[:10], "...", len(cols))
+import sys, numpy as np
+sys.path.insert(0, ".")
+from pygps_b200._lib import Engine
+eng = Engine()
+rng = np.random.default_rng(1)
+for (N, K) in [(64, 32), (64, 128), (128, 64), (256, 256)]:
+    for (da, db) in [(np.int8, np.int8), (np.uint8, np.int8), (np.int8, np.uint8), (np.uint8, np.uint8)]:
+        A = rng.integers(0 if da == np.uint8 else -128, 256 if da == np.uint8 else 128, size=(128, K)).astype(da)
+        B = rng.integers(0 if db == np.uint8 else -128, 256 if db == np.uint8 else 128, size=(N, K)).astype(db)
+        C = eng.dbg_i8_tile(A, B)
+        ref = A.astype(np.int64) @ B.astype(np.int64).T
+        print(f"N={N} K={K} A={da.__name__} B={db.__name__} mismatches={int((C != ref).sum())} of {C.size}", flush=True)
