@@ -185,7 +185,8 @@ int gpk_dbg_diag(gpk_handle h, const double* A128, double* L128, double* Linv128
 /* debug: C(128,N) int32 = A(128,K) int8 * B(N,K)' int8 (row-major host arrays) through one tcgen05.mma.kind::i8 tile
  * (TMEM accumulator, shared-memory descriptors) - the building block of the planned int8 emulation of the fp64
  * trailing update.  N in {64,128,256}, K a multiple of 32, K <= 256.  fmt bit 0 / bit 1: the bytes of A / B are
- * unsigned (u8) instead of signed (s8).                                          */
+ * unsigned (u8) instead of signed (s8); bit 2 / bit 3: A goes shared memory -> TMEM (tcgen05.cp) and the MMA reads
+ * it from there (bit 3: every k-step reuses the same TMEM columns).                                        */
 int gpk_dbg_i8_tile(gpk_handle h, int N, int K, const int8_t* A, const int8_t* B, int32_t* C, int fmt);
 
 /* debug/bench: C (n,n column-major, lower triangle) -= P (n,kw column-major) * P' - the trailing update of the

@@ -361,9 +361,10 @@ class Engine(object):
         self._check(rc, "gpk_dbg_gemm_nt")
         return C
 
-    def dbg_i8_tile(self, A, B):
-        """int32 C = A (128,K) @ B (N,K)^T through one tcgen05.mma.kind::i8 tile; A, B int8 or uint8 arrays."""
-        fmt = (1 if A.dtype == np.uint8 else 0) | (2 if B.dtype == np.uint8 else 0)
+    def dbg_i8_tile(self, A, B, a_tmem=0):
+        """int32 C = A (128,K) @ B (N,K)^T through one tcgen05.mma.kind::i8 tile; A, B int8 or uint8 arrays.
+        a_tmem 1: A staged through TMEM by tcgen05.cp (one region per k-step), 2: one reused region."""
+        fmt = (1 if A.dtype == np.uint8 else 0) | (2 if B.dtype == np.uint8 else 0) | (4 if a_tmem == 1 else 0) | (8 if a_tmem == 2 else 0)
         A = np.ascontiguousarray(A)
         B = np.ascontiguousarray(B)
         if A.dtype.itemsize != 1 or B.dtype.itemsize != 1:

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <vector>
 #include "gpk_internal.cuh"
 
 namespace gpk {
@@ -36,34 +37,64 @@ static int ensure_prof_events(Handle* h, size_t count) {
 
 // ---------------------------------------------------------------------------
 // Blocked right-looking Cholesky, in place on the lower triangle of A (np x np, column-major, np a multiple
-// of NB), two-level: an OUTER block of W panels (W*128 columns) is factored panel by panel on the
-// high-priority stream, then the trailing matrix gets ONE update with contraction length W*128 (fewer
-// passes over the trailing matrix than W separate rank-128 updates).  Streams:
-//   s_panel (high priority): for each panel p of the block: diag(p) -> trsm(p) -> rank-128 update of the
-//                            remaining columns of the block
-//   s_main                 : rank-(W*128) update of the next block's columns (so its panels can start)
-//                            -> update of the rest of the trailing matrix
+// of NB), with up to three levels of blocking:
+//   level 1: a block of W1 panels; when it is done the whole trailing matrix gets ONE update with contraction
+//            length W1*128.  On the int8 tensor-core path (ozaki.cu) the cost of an update tile's epilogue (TMEM ->
+//            fp64 -> C) is fixed, so long contractions are what makes it efficient: W1 = 12 while the trailing
+//            matrix is large, W1 = W2 once the factorization is bound by the panel chain anyway.
+//   level 2: sub-blocks of W2 panels inside the block; after each, the REST OF THE BLOCK'S columns are updated
+//            (contraction W2*128), on the panel stream.
+//   level 3: single panels of 128 columns: diag -> trsm -> rank-128 update of the remaining columns of the
+//            sub-block (fp64 DMMA).
+// Streams:
+//   s_panel (high priority): everything inside a level-1 block
+//   s_main                 : level-1 update: first the next block's columns (so its panels can start), then
+//                            the rest of the trailing matrix
 //   s_aux                  : single-right-hand-side forward substitution step p, off the critical path
-// Outer block j+1 therefore overlaps the bulk of trailing update j (look-ahead 1).
+// Level-1 block j+1 therefore overlaps the bulk of trailing update j (look-ahead 1).
 // ---------------------------------------------------------------------------
 static int g_potrf_w = 0;   // 0: choose from the problem size (measured on B200: 3 panels at T>64, else 2)
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info, double* b_fwd,
                  double* z_out) {
   const int T = (int)(np / NB);
   const int64_t lda = np;
   if (const char* e = getenv("GPK_POTRF_W")) { g_potrf_w = atoi(e); }
-  const int W = (g_potrf_w < 1) ? ((T > 64) ? 3 : (T > 8 ? 2 : 1)) : (g_potrf_w > 8 ? 8 : g_potrf_w);
-  const int nblk = (T + W - 1) / W;
+  const int W2 = (g_potrf_w < 1) ? ((T > 64) ? 3 : (T > 8 ? 2 : 1)) : (g_potrf_w > 8 ? 8 : g_potrf_w);
   // trailing updates with at least oz_min tile rows go to the int8 tensor cores (GPK_OZAKI=0 keeps everything on DMMA)
-  int oz = 0, oz_min = 24;
-  if (const char* e = getenv("GPK_OZAKI")) oz = atoi(e);
-  if (const char* e = getenv("GPK_OZAKI_MIN")) oz_min = atoi(e);
-  if (oz && T - W >= oz_min) GPK_TRY(oz_ensure(h, (int64_t)(T - W) * NB, W * NB));
+  const int oz = env_int("GPK_OZAKI", 1), oz_min = env_int("GPK_OZAKI_MIN", 24);
+  int W1 = env_int("GPK_POTRF_W1", 12);
+  const int w1_minrem = env_int("GPK_POTRF_W1_MINREM", 80);
+  if (W1 > 16) W1 = 16;
+  W1 = (W1 / W2) * W2;                                  // a whole number of sub-blocks
+  // plan the level-1 blocks
+  std::vector<int> bstart;
+  int64_t need0 = 0, need1 = 0; int rows0 = 0, rows1 = 0, kw0 = 0;
+  for (int pos = 0; pos < T;) {
+    const bool big = oz && W1 > W2 && T - (pos + W1) >= w1_minrem;
+    const int w = big ? W1 : W2;
+    bstart.push_back(pos);
+    const int pe = (pos + w < T) ? pos + w : T;
+    if (oz && T - pe >= oz_min) {
+      const int64_t nd = (int64_t)(T - pe) * NB * (pe - pos) * NB;
+      if (nd > need0) { need0 = nd; rows0 = (T - pe) * NB; kw0 = (pe - pos) * NB; }
+    }
+    if (big && T - (pos + W2) >= oz_min) { need1 = 1; if ((T - pos - W2) * NB > rows1) rows1 = (T - pos - W2) * NB; }
+    pos = pe;
+  }
+  bstart.push_back(T);
+  const int nblk = (int)bstart.size() - 1;
+  if (need0) GPK_TRY(oz_ensure(h, 0, rows0, kw0));
+  if (need1) GPK_TRY(oz_ensure(h, 1, rows1, W2 * NB));
   GPK_TRY(ensure_events(h, 2 * (size_t)T + 4));
   if (h->profile) GPK_TRY(ensure_prof_events(h, 2 * (size_t)T + 2));
   cudaEvent_t* ev_panel = h->ev.data();      // [T]   panel p factored and solved
-  cudaEvent_t* ev_col = h->ev.data() + T;    // [T]   columns of outer block j up to date
+  cudaEvent_t* ev_col = h->ev.data() + T;    // [T]   columns of level-1 block j up to date
   cudaEvent_t ev_fork = h->ev[2 * T], ev_join = h->ev[2 * T + 1], ev_aux = h->ev[2 * T + 2];
   h->stats.syrk_flops = 0.0;
   h->prof_pairs = 0;
@@ -72,31 +103,48 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_fork, 0));
   if (b_fwd) GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_fork, 0));
   for (int j = 0; j < nblk; ++j) {
-    const int pb = j * W;                              // first panel of the block
-    const int pe = (pb + W < T) ? pb + W : T;          // one past its last panel
+    const int pb = bstart[j], pe = bstart[j + 1];      // the level-1 block: panels [pb, pe)
     if (j > 0) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_col[j], 0));
-    for (int p = pb; p < pe; ++p) {
-      double* App = A + (int64_t)p * NB * (1 + lda);
-      double* Dp = Dinv + (int64_t)p * NB * NB;
-      const int rem = T - p - 1;                       // tile rows below panel p
-      GPK_TRY(launch_diag(h, h->s_panel, App, lda, Dp, logdet_parts + p, info, p * NB));
-      if (rem > 0) {
-        GemmArgs t{};
-        t.A = App + NB; t.B = Dp; t.C = App + NB;
-        t.lda = lda; t.ldb = NB; t.ldc = lda; t.K = NB; t.tri = 0;
-        GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, rem, 1));
+    for (int sb = pb; sb < pe; sb += W2) {
+      const int se = (sb + W2 < pe) ? sb + W2 : pe;    // the level-2 sub-block: panels [sb, se)
+      for (int p = sb; p < se; ++p) {
+        double* App = A + (int64_t)p * NB * (1 + lda);
+        double* Dp = Dinv + (int64_t)p * NB * NB;
+        const int rem = T - p - 1;                     // tile rows below panel p
+        GPK_TRY(launch_diag(h, h->s_panel, App, lda, Dp, logdet_parts + p, info, p * NB));
+        if (rem > 0) {
+          GemmArgs t{};
+          t.A = App + NB; t.B = Dp; t.C = App + NB;
+          t.lda = lda; t.ldb = NB; t.ldc = lda; t.K = NB; t.tri = 0;
+          GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, rem, 1));
+        }
+        GPK_CK(h, cudaEventRecord(ev_panel[p], h->s_panel));
+        if (b_fwd) {
+          GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_panel[p], 0));
+          GPK_TRY(launch_trsv_fwd(h, h->s_aux, A, lda, Dinv, b_fwd, z_out, p, T));
+        }
+        const int inner = se - p - 1;                  // remaining columns of this sub-block
+        if (inner > 0) {
+          GemmArgs u{};
+          u.A = App + NB; u.B = App + NB; u.C = A + (int64_t)(p + 1) * NB * (1 + lda);
+          u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = NB; u.tri = 1;
+          GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, u, rem, inner));
+        }
       }
-      GPK_CK(h, cudaEventRecord(ev_panel[p], h->s_panel));
-      if (b_fwd) {
-        GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_panel[p], 0));
-        GPK_TRY(launch_trsv_fwd(h, h->s_aux, A, lda, Dinv, b_fwd, z_out, p, T));
-      }
-      const int inner = pe - p - 1;                    // remaining columns of this block
-      if (inner > 0) {
-        GemmArgs u{};
-        u.A = App + NB; u.B = App + NB; u.C = A + (int64_t)(p + 1) * NB * (1 + lda);
-        u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = NB; u.tri = 1;
-        GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, u, rem, inner));
+      if (se < pe) {
+        // level-2 update: the block's remaining columns [se, pe), all rows below the sub-block
+        const int rows = T - se, cols = pe - se, kw2 = (se - sb) * NB;
+        double* P2 = A + (int64_t)se * NB + (int64_t)sb * NB * lda;
+        double* C2 = A + (int64_t)se * NB * (1 + lda);
+        if (oz && rows >= oz_min) {
+          GPK_TRY(launch_oz_slice(h, 1, h->s_panel, P2, lda, rows * NB, kw2));
+          GPK_TRY(launch_oz_syrk(h, 1, h->s_panel, C2, lda, rows * NB, kw2, 0, cols));
+        } else {
+          GemmArgs u{};
+          u.A = P2; u.B = P2; u.C = C2;
+          u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = kw2; u.tri = 1;
+          GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, u, rows, cols));
+        }
       }
     }
     const int rem = T - pe;                            // trailing tiles after the block
@@ -105,15 +153,16 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
       GPK_CK(h, cudaStreamWaitEvent(h->s_main, ev_join, 0));
       if (h->profile) GPK_CK(h, cudaEventRecord(h->prof_ev[2 * h->prof_pairs], h->s_main));
       const int kw = (pe - pb) * NB;
-      const int first = (W < rem) ? W : rem;           // the next block's columns go first
+      const int nextw = bstart[j + 2 <= nblk ? j + 2 : nblk] - pe;
+      const int first = (nextw < rem) ? nextw : rem;   // the next block's columns go first
       double* Pblk = A + (int64_t)pe * NB + (int64_t)pb * NB * lda;
       double* Ctr = A + (int64_t)pe * NB * (1 + lda);
       if (oz && rem >= oz_min) {
         // int8 tensor-core path (ozaki.cu): slice the panel block once, then the same two launches
-        GPK_TRY(launch_oz_slice(h, h->s_main, Pblk, lda, rem * NB, kw));
-        GPK_TRY(launch_oz_syrk(h, h->s_main, Ctr, lda, rem * NB, kw, 0, first));
+        GPK_TRY(launch_oz_slice(h, 0, h->s_main, Pblk, lda, rem * NB, kw));
+        GPK_TRY(launch_oz_syrk(h, 0, h->s_main, Ctr, lda, rem * NB, kw, 0, first));
         GPK_CK(h, cudaEventRecord(ev_col[j + 1], h->s_main));
-        if (rem > first) GPK_TRY(launch_oz_syrk(h, h->s_main, Ctr, lda, rem * NB, kw, first, rem));
+        if (rem > first) GPK_TRY(launch_oz_syrk(h, 0, h->s_main, Ctr, lda, rem * NB, kw, first, rem));
       } else {
         GemmArgs u{};
         u.A = Pblk; u.B = u.A;
@@ -197,9 +246,11 @@ static int free_all(Handle* h) {
   }
   if (h->dInfo) cudaFree(h->dInfo);
   h->dInfo = nullptr;
-  if (h->ozSl) cudaFree(h->ozSl);
-  if (h->ozSc) cudaFree(h->ozSc);
-  h->ozSl = nullptr; h->ozSc = nullptr; h->ozCap = h->ozScCap = 0;
+  for (int w = 0; w < 2; ++w) {
+    if (h->ozSl[w]) cudaFree(h->ozSl[w]);
+    if (h->ozSc[w]) cudaFree(h->ozSc[w]);
+    h->ozSl[w] = nullptr; h->ozSc[w] = nullptr; h->ozCap[w] = h->ozScCap[w] = 0;
+  }
   h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = 0;
   h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->cgA = h->cgDinv = h->cgPack = h->cgVec = h->ceK = h->ceSig = h->ceVec = h->ceSW = h->capUs = h->capLpost = h->capAlphaU = 0;
   return 0;

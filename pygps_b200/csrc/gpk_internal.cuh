@@ -113,7 +113,9 @@ struct Handle {
   double* gPack = nullptr; int64_t cgPack = 0;  // packed panel being broadcast
   double* gVec = nullptr; int64_t cgVec = 0;
   // int8 tensor-core trailing update (ozaki.cu): slices + row exponents of the current panel block
-  int8_t* ozSl = nullptr; size_t ozCap = 0; double* ozSc = nullptr; size_t ozScCap = 0;
+  // (two sets: [0] level-1 updates on s_main, [1] level-2 updates on s_panel, which run concurrently)
+  int8_t* ozSl[2] = {nullptr, nullptr}; size_t ozCap[2] = {0, 0}; double* ozSc[2] = {nullptr, nullptr}; size_t ozScCap[2] = {0, 0};
+  long long* ozDbg = nullptr;
   // fitc state
   bool has_fitc = false; int64_t M = 0, Mp = 0;
   double* dUin = nullptr; double* dUs = nullptr; double* dLpost = nullptr; double* dAlphaU = nullptr;
@@ -174,9 +176,9 @@ int gemm_init(Handle* h);
 int diag_init(Handle* h);
 
 int ensure(Handle* h, double** p, int64_t* cap, int64_t need_elems);
-int oz_ensure(Handle* h, int64_t n, int kw);
-int launch_oz_slice(Handle* h, cudaStream_t st, const double* P, int64_t lda, int n, int kw);
-int launch_oz_syrk(Handle* h, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1);
+int oz_ensure(Handle* h, int which, int64_t n, int kw);
+int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw);
+int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1);
 int dist_allreduce_sum(Handle* h, double* buf, size_t count, cudaStream_t st);
 int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::vector<double>& scale, int* divide,
                double* premul, double* sf2);

@@ -22,7 +22,9 @@
 // Short CTAs (not one persistent CTA per SM) on purpose: the high-priority panel stream of the look-ahead
 // Cholesky needs SMs to free up every few microseconds.
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include "gpk_internal.cuh"
 #include "tc_common.cuh"
 
@@ -109,6 +111,7 @@ struct OzArgs {
   int jb0;            // first 128-column block of this launch
   int ntiles;         // lower-triangle 128x64 tiles of this launch
   int tpc;            // tiles per CTA
+  long long* dbg;     // optional per-CTA clock stamps [5] (debug timing), else nullptr
 };
 
 // tile index -> (128-row tile, 64-column tile): column blocks jb0.. in order, each 128-column block jb holds
@@ -131,6 +134,7 @@ template <int S, int RB>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   constexpr uint32_t A_BYTES = 128 * S * 32, B_BYTES = OZ_BN * S * 32, STAGE = A_BYTES + B_BYTES;
   constexpr uint32_t TCOLS = 512;
+  constexpr bool ATMEM = (S * OZ_BN + S * 8 <= 512);   // room for one k-step of the A slices behind the accumulators
   constexpr double HORNER = 1.0 / (double)(1 << RB);
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint64_t full[OZ_ST], empty[OZ_ST], done, tfree;
@@ -156,6 +160,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_base;
+  long long* dbg = (a.dbg && blockIdx.x < 4096) ? a.dbg + 5 * blockIdx.x : nullptr;
+  if (dbg && tid == 0) dbg[0] = clock64();
 
   if (warp == OZ_EPI_WARPS + 1) {
     if (elect_one()) {
@@ -183,22 +189,57 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
       int it = 0, tcount = 0;
       for (int tile = tile0; tile < tile1; ++tile, ++tcount) {
         if (tcount > 0) { mbar_wait(&tfree, (tcount - 1) & 1); tc_fence_after(); }
-        for (int ks = 0; ks < nk; ++ks, ++it) {
-          const int slot = it % OZ_ST;
-          mbar_wait(&full[slot], (it / OZ_ST) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(sm + (size_t)slot * STAGE);
-          const uint64_t da = dbase | (uint64_t)(sa >> 4), db = dbase | (uint64_t)((sa + A_BYTES) >> 4);
+        if constexpr (ATMEM) {
+          // The A slices go shared memory -> TMEM once per k-step (tcgen05.cp) and every product reads them from
+          // there: shared-memory traffic per k-step drops from S(S+1)/2 x 6 KB to S x 4 KB + S(S+1)/2 x 2 KB, which
+          // takes the loop from shared-memory-bound (48 clk per product) to tensor-bound (32 clk).  The copy of
+          // slice t for the NEXT k-step is issued right behind the last product that reads slice t; tcgen05
+          // operations of one thread execute in issue order, so the single TMEM copy of A needs no extra barrier.
+          const uint32_t ta = tbase + S * OZ_BN;
+          {
+            const int slot = it % OZ_ST;
+            mbar_wait(&full[slot], (it / OZ_ST) & 1);
+            tc_fence_after();
+            if (dbg && tcount == 0) dbg[1] = clock64();
+            const uint64_t da = dbase | (uint64_t)(smem_u32(sm + (size_t)slot * STAGE) >> 4);
 #pragma unroll
-          for (int t = 0; t < S; ++t) {
-#pragma unroll
-            for (int u = 0; u < S - t; ++u) {
-              tc_mma_i8(tbase + (uint32_t)(t + u) * OZ_BN, da + 16 * t, db + 16 * u, idesc, (ks > 0 || t > 0) ? 1u : 0u);
-            }
+            for (int t = 0; t < S; ++t) tc_cp_128x256b(ta + 8 * t, da + 16 * t);
           }
-          tc_commit(&empty[slot]);
+          for (int ks = 0; ks < nk; ++ks, ++it) {
+            const int slot = it % OZ_ST, nslot = (it + 1) % OZ_ST;
+            const bool more = ks + 1 < nk;
+            const uint64_t db = dbase | (uint64_t)((smem_u32(sm + (size_t)slot * STAGE) + A_BYTES) >> 4);
+            const uint64_t dan = dbase | (uint64_t)(smem_u32(sm + (size_t)nslot * STAGE) >> 4);
+#pragma unroll
+            for (int t = 0; t < S; ++t) {
+#pragma unroll
+              for (int u = 0; u < S - t; ++u)
+                tc_mma_i8_ts(tbase + (uint32_t)(t + u) * OZ_BN, ta + 8 * t, db + 16 * u, idesc, (ks > 0 || t > 0) ? 1u : 0u);
+              if (more) {
+                if (t == 0) { mbar_wait(&full[nslot], ((it + 1) / OZ_ST) & 1); tc_fence_after(); }
+                tc_cp_128x256b(ta + 8 * t, dan + 16 * t);
+              }
+            }
+            tc_commit(&empty[slot]);
+          }
+        } else {
+          for (int ks = 0; ks < nk; ++ks, ++it) {
+            const int slot = it % OZ_ST;
+            mbar_wait(&full[slot], (it / OZ_ST) & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(sm + (size_t)slot * STAGE);
+            const uint64_t da = dbase | (uint64_t)(sa >> 4), db = dbase | (uint64_t)((sa + A_BYTES) >> 4);
+#pragma unroll
+            for (int t = 0; t < S; ++t) {
+#pragma unroll
+              for (int u = 0; u < S - t; ++u)
+                tc_mma_i8(tbase + (uint32_t)(t + u) * OZ_BN, da + 16 * t, db + 16 * u, idesc, (ks > 0 || t > 0) ? 1u : 0u);
+            }
+            tc_commit(&empty[slot]);
+          }
         }
         tc_commit(&done);
+        if (dbg) dbg[2] = clock64();
       }
     }
   } else {
@@ -219,6 +260,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
         if (gi >= gj0 + q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + (int64_t)q * a.ldc));
       mbar_wait(&done, tcount & 1);
       tc_fence_after();
+      if (dbg && tid == 0) dbg[3] = clock64();
 #pragma unroll 1
       for (int c0 = 0; c0 < OZ_BN / 2; c0 += 8) {
         uint32_t v[S][8];
@@ -245,6 +287,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
           if (gi >= gj0 + c0 + q) crow[(int64_t)(c0 + q) * a.ldc] = cv[q] - (acc * si) * sj[q];
         }
       }
+      if (dbg && tid == 0) dbg[4] = clock64();
     }
   }
   tc_fence_before();
@@ -267,36 +310,36 @@ static OzCfg oz_cfg() {
   return c;
 }
 
-int oz_ensure(Handle* h, int64_t n, int kw) {
+int oz_ensure(Handle* h, int which, int64_t n, int kw) {
   const size_t need = (size_t)n * kw * 8;
-  if (h->ozCap < need) {
-    if (h->ozSl) cudaFree(h->ozSl);
-    h->ozSl = nullptr; h->ozCap = 0;
-    GPK_CK(h, cudaMalloc((void**)&h->ozSl, need));
-    h->ozCap = need;
+  if (h->ozCap[which] < need) {
+    if (h->ozSl[which]) cudaFree(h->ozSl[which]);
+    h->ozSl[which] = nullptr; h->ozCap[which] = 0;
+    GPK_CK(h, cudaMalloc((void**)&h->ozSl[which], need));
+    h->ozCap[which] = need;
   }
-  if (h->ozScCap < (size_t)n) {
-    if (h->ozSc) cudaFree(h->ozSc);
-    h->ozSc = nullptr; h->ozScCap = 0;
-    GPK_CK(h, cudaMalloc((void**)&h->ozSc, (size_t)n * sizeof(double)));
-    h->ozScCap = (size_t)n;
+  if (h->ozScCap[which] < (size_t)n) {
+    if (h->ozSc[which]) cudaFree(h->ozSc[which]);
+    h->ozSc[which] = nullptr; h->ozScCap[which] = 0;
+    GPK_CK(h, cudaMalloc((void**)&h->ozSc[which], (size_t)n * sizeof(double)));
+    h->ozScCap[which] = (size_t)n;
   }
   return 0;
 }
 
 template <int S, int RB>
-static int oz_slice_t(Handle* h, cudaStream_t st, const double* P, int64_t lda, int n, int kw) {
-  oz_slice_kernel<S, RB><<<n / 32, 256, 0, st>>>(P, lda, n, kw, h->ozSc, h->ozSl);
+static int oz_slice_t(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw) {
+  oz_slice_kernel<S, RB><<<n / 32, 256, 0, st>>>(P, lda, n, kw, h->ozSc[which], h->ozSl[which]);
   GPK_CK(h, cudaGetLastError());
   return 0;
 }
 
 // slice the panel P (n rows x kw columns, column-major, lda) into h->ozSl / h->ozSc
-int launch_oz_slice(Handle* h, cudaStream_t st, const double* P, int64_t lda, int n, int kw) {
-  if (n % 128 != 0 || kw % 32 != 0) return GPK_ERR_ARG;
+int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw) {
+  if (n % 128 != 0 || kw % 32 != 0 || (size_t)n * kw * 8 > h->ozCap[which]) return GPK_ERR_ARG;
   const OzCfg c = oz_cfg();
-  if (c.RB == 7) return c.S == 8 ? oz_slice_t<8, 7>(h, st, P, lda, n, kw) : oz_slice_t<7, 7>(h, st, P, lda, n, kw);
-  return c.S == 7 ? oz_slice_t<7, 8>(h, st, P, lda, n, kw) : oz_slice_t<6, 8>(h, st, P, lda, n, kw);
+  if (c.RB == 7) return c.S == 8 ? oz_slice_t<8, 7>(h, which, st, P, lda, n, kw) : oz_slice_t<7, 7>(h, which, st, P, lda, n, kw);
+  return c.S == 7 ? oz_slice_t<7, 8>(h, which, st, P, lda, n, kw) : oz_slice_t<6, 8>(h, which, st, P, lda, n, kw);
 }
 
 template <int S, int RB>
@@ -313,12 +356,12 @@ static int oz_syrk_t(Handle* h, cudaStream_t st, const OzArgs& a) {
 }
 
 // C(lower triangle, 128-column blocks [jb0, jb1)) -= P·P' from the current slices
-int launch_oz_syrk(Handle* h, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1) {
+int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1) {
   const OzCfg c = oz_cfg();
   const int nt = n / 128;
   if (jb0 < 0 || jb1 > nt || jb0 >= jb1) return GPK_ERR_ARG;
   const int ntiles = 2 * nt * (jb1 - jb0) - (jb1 * (jb1 - 1) - jb0 * (jb0 - 1));
-  OzArgs a{h->ozSl, h->ozSc, C, ldc, n, kw, jb0, ntiles, c.tpc};
+  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, ntiles, c.tpc, h->ozDbg};
   if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
   return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
 }
@@ -340,14 +383,20 @@ extern "C" int gpk_dbg_oz_syrk(gpk_handle hh, int64_t n, int kw, const double* P
   GPK_CK(h, cudaMalloc((void**)&dC, (size_t)n * n * 8));
   int rc = 0;
   cudaMemcpyAsync(dP, P, (size_t)n * kw * 8, cudaMemcpyHostToDevice, st);
-  if (mode == 0) rc = oz_ensure(h, n, kw);
+  if (mode == 0) rc = oz_ensure(h, 0, n, kw);
+  long long* dDbg = nullptr;
+  if (mode == 0 && getenv("GPK_OZ_TIMING")) {
+    cudaMalloc((void**)&dDbg, 4096 * 5 * sizeof(long long));
+    cudaMemset(dDbg, 0, 4096 * 5 * sizeof(long long));
+    h->ozDbg = dDbg;
+  }
   float total = 0.f;
   for (int r = 0; r < reps && rc == 0; ++r) {
     cudaMemcpyAsync(dC, C, (size_t)n * n * 8, cudaMemcpyHostToDevice, st);
     cudaEventRecord(h->t0, st);
     if (mode == 0) {
-      rc = launch_oz_slice(h, st, dP, n, (int)n, kw);
-      if (rc == 0) rc = launch_oz_syrk(h, st, dC, n, (int)n, kw, 0, (int)(n / 128));
+      rc = launch_oz_slice(h, 0, st, dP, n, (int)n, kw);
+      if (rc == 0) rc = launch_oz_syrk(h, 0, st, dC, n, (int)n, kw, 0, (int)(n / 128));
     } else {
       GemmArgs u{};
       u.A = dP; u.B = dP; u.C = dC; u.lda = n; u.ldb = n; u.ldc = n; u.K = kw; u.tri = 1;
@@ -361,6 +410,19 @@ extern "C" int gpk_dbg_oz_syrk(gpk_handle hh, int64_t n, int kw, const double* P
   }
   if (rc == 0) cudaMemcpyAsync(C, dC, (size_t)n * n * 8, cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
+  if (dDbg) {
+    std::vector<long long> v(4096 * 5);
+    cudaMemcpy(v.data(), dDbg, v.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double s1 = 0, s2 = 0, s3 = 0, s4 = 0; int cnt = 0;
+    for (int b = 0; b < 4096; ++b) {
+      const long long* d = &v[5 * b];
+      if (!d[0] || !d[4]) continue;
+      s1 += d[1] - d[0]; s2 += d[2] - d[0]; s3 += d[3] - d[0]; s4 += d[4] - d[0]; ++cnt;
+    }
+    if (cnt) fprintf(stderr, "oz timing (clk, mean over %d CTAs): first stage landed +%.0f, all MMAs issued +%.0f, accumulators complete +%.0f, epilogue end +%.0f\n", cnt, s1 / cnt, s2 / cnt, s3 / cnt, s4 / cnt);
+    cudaFree(dDbg);
+    h->ozDbg = nullptr;
+  }
   cudaFree(dP); cudaFree(dC);
   if (rc) return rc;
   GPK_CK(h, e);

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) i8_tile_kernel(const int8_t* __restrict__
     *reinterpret_cast<int4*>(sB + ((size_t)kc * N + r) * 16) = *reinterpret_cast<const int4*>(B + (size_t)r * K + kc * 16);
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(N < 32 ? 32 : N) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (tid == 0) {
@@ -49,7 +49,14 @@ __global__ void __launch_bounds__(128) i8_tile_kernel(const int8_t* __restrict__
     for (int ks = 0; ks < K / 32; ++ks) {       // one MMA consumes 32 bytes of K = 2 chunks
       const uint64_t ad = make_smem_desc(smem_u32(sA) + ks * 2 * 128 * 16, 128 * 16, 8 * 16);
       const uint64_t bd = make_smem_desc(smem_u32(sB) + ks * 2 * N * 16, N * 16, 8 * 16);
-      tc_mma_i8(tbase, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      if (fmt & 12) {
+        // A staged through TMEM columns 256.. by tcgen05.cp; bit 3: every k-step reuses the same 8 columns
+        const uint32_t ta = tbase + 256 + ((fmt & 8) ? 0 : ks * 8);
+        tc_cp_128x256b(ta, ad);
+        tc_mma_i8_ts(tbase, ta, bd, idesc, ks > 0 ? 1u : 0u);
+      } else {
+        tc_mma_i8(tbase, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      }
     }
     tc_commit(&mbar);
   }
@@ -66,7 +73,7 @@ __global__ void __launch_bounds__(128) i8_tile_kernel(const int8_t* __restrict__
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tbase), "n"(N < 32 ? 32 : N) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tbase), "n"(512) : "memory");
 }
 
 // issue-rate probe: `iters` back-to-back MMAs (128 x N x 32, int8) from one thread per CTA, operands anywhere in a
