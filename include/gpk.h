@@ -194,9 +194,10 @@ int gpk_dbg_i8_tile(gpk_handle h, int N, int K, const int8_t* A, const int8_t* B
  * (Ozaki split, tcgen05 + TMEM) path, mode 1: fp64 DMMA path.  n, kw multiples of 128.  *ms = mean device time
  * of the update over `reps` repetitions (each starts from the given C).                                          */
 /* bench: issue rate of tcgen05.mma.kind::i8 (128 x N x 32) for a given shared-memory descriptor geometry
- * (leading/stride byte offsets, per-MMA operand step), max clocks per MMA over `ctas` concurrent CTAs.        */
+ * (leading/stride byte offsets, per-MMA operand step), max clocks per MMA over `ctas` concurrent CTAs; *tops =
+ * int8 tensor throughput (2*128*N*32 ops per MMA) of the whole launch by CUDA events, in TOP/s.             */
 int gpk_bench_i8_rate(gpk_handle h, int N, int iters, int lbo, int sbo, int astep, int same_acc, int ctas,
-                      double* clk_per_mma);
+                      double* clk_per_mma, double* tops);
 
 int gpk_dbg_oz_syrk(gpk_handle h, int64_t n, int kw, const double* P, double* C, int mode, int reps, double* ms);
 

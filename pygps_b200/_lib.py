@@ -75,7 +75,7 @@ PROTOTYPES = [
     ("gpk_dbg_gemm_nt", _I, [_H, _I, _L, _L, _L, c_double_p, c_double_p, c_double_p]),
     ("gpk_dbg_diag", _I, [_H, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]),
     ("gpk_dbg_i8_tile", _I, [_H, _I, _I, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _I]),
-    ("gpk_bench_i8_rate", _I, [_H, _I, _I, _I, _I, _I, _I, _I, c_double_p]),
+    ("gpk_bench_i8_rate", _I, [_H, _I, _I, _I, _I, _I, _I, _I, c_double_p, c_double_p]),
     ("gpk_dbg_oz_syrk", _I, [_H, _L, _I, c_double_p, c_double_p, _I, _I, c_double_p]),
 ]
 
@@ -375,10 +375,12 @@ class Engine(object):
         return C
 
     def bench_i8_rate(self, N, iters, lbo, sbo, astep=0, same_acc=0, ctas=148):
+        """(clocks per MMA, int8 TOP/s) of back-to-back tcgen05.mma.kind::i8 128xNx32 from `ctas` CTAs."""
         v = ctypes.c_double(0)
-        rc = self._lib.gpk_bench_i8_rate(self._h, N, iters, lbo, sbo, astep, same_acc, ctas, ctypes.byref(v))
+        t = ctypes.c_double(0)
+        rc = self._lib.gpk_bench_i8_rate(self._h, N, iters, lbo, sbo, astep, same_acc, ctas, ctypes.byref(v), ctypes.byref(t))
         self._check(rc, "gpk_bench_i8_rate")
-        return v.value
+        return v.value, t.value
 
     def dbg_oz_syrk(self, P, C, mode=0, reps=1):
         """lower(C) - P P' through the int8 tensor-core path (mode 0) or the DMMA path (mode 1); returns (C_new, ms)."""

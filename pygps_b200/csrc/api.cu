@@ -40,7 +40,7 @@ static int ensure_prof_events(Handle* h, size_t count) {
 // of NB), with up to three levels of blocking:
 //   level 1: a block of W1 panels; when it is done the whole trailing matrix gets ONE update with contraction
 //            length W1*128.  On the int8 tensor-core path (ozaki.cu) the cost of an update tile's epilogue (TMEM ->
-//            fp64 -> C) is fixed, so long contractions are what makes it efficient: W1 = 12 while the trailing
+//            fp64 -> C) is fixed, so long contractions are what makes it efficient: W1 = 9 while the trailing
 //            matrix is large, W1 = W2 once the factorization is bound by the panel chain anyway.
 //   level 2: sub-blocks of W2 panels inside the block; after each, the REST OF THE BLOCK'S columns are updated
 //            (contraction W2*128), on the panel stream.
@@ -68,8 +68,8 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   const int W2 = (g_potrf_w < 1) ? ((T > 64) ? 3 : (T > 8 ? 2 : 1)) : (g_potrf_w > 8 ? 8 : g_potrf_w);
   // trailing updates with at least oz_min tile rows go to the int8 tensor cores (GPK_OZAKI=0 keeps everything on DMMA)
   const int oz = env_int("GPK_OZAKI", 1), oz_min = env_int("GPK_OZAKI_MIN", 24);
-  int W1 = env_int("GPK_POTRF_W1", 12);
-  const int w1_minrem = env_int("GPK_POTRF_W1_MINREM", 80);
+  int W1 = env_int("GPK_POTRF_W1", 9);
+  const int w1_minrem = env_int("GPK_POTRF_W1_MINREM", 64);
   if (W1 > 16) W1 = 16;
   W1 = (W1 / W2) * W2;                                  // a whole number of sub-blocks
   // plan the level-1 blocks

@@ -9,5 +9,5 @@ for N in (64, 128, 256):
     for (lbo, sbo, astep, name) in cfgs:
         for ctas in (1, 148):
             for same in (0, 1):
-                c = eng.bench_i8_rate(N, 4000, lbo, sbo, astep=astep, same_acc=same, ctas=ctas)
-                print(f"N={N:3d} {name:58s} ctas={ctas:3d} same_acc={same}: {c:7.1f} clk/MMA  (floor {128*N/256:.0f})", flush=True)
+                c, tops = eng.bench_i8_rate(N, 40000, lbo, sbo, astep=astep, same_acc=same, ctas=ctas)
+                print(f"N={N:3d} {name:58s} ctas={ctas:3d} same_acc={same}: {c:7.1f} clk/MMA  (floor {128*N/256:.0f})  {tops:8.1f} TOP/s", flush=True)

@@ -6,7 +6,7 @@ from pygps_b200._lib import Engine
 eng = Engine()
 rng = np.random.default_rng(0)
 import os
-for n, kw in ([(15616, 384)] if os.environ.get("OZ_BIG") else [(256, 128), (1024, 384), (4096, 384), (15616, 384)]):
+for n, kw in ([(int(os.environ.get("OZ_N", 15616)), int(os.environ.get("OZ_KW", 384)))] if os.environ.get("OZ_BIG") else [(256, 128), (1024, 384), (4096, 384), (15616, 384)]):
     P = rng.standard_normal((n, kw)) * np.exp(rng.uniform(-6, 6, size=(n, 1)))   # rows of very different scale
     if n <= 4096:
         C = rng.standard_normal((n, n)); C = C + C.T

@@ -101,8 +101,44 @@ def trsv_bwd(A, Dinv, z, x, k, T):
         z[j * NB:(j + 1) * NB] -= A[k * NB:(k + 1) * NB, j * NB:(j + 1) * NB].T @ xk
 
 
-def potrf_device(A, b=None, W=2):
-    """api.cu potrf_device (stream order flattened): two-level blocking, outer blocks of W panels.
+def oz_split(P, S=7, RB=8):
+    """ozaki.cu oz_slice_kernel: per-row exponent, then balanced radix-2^RB digits (all int8).
+    Returns (digits [S, n, k] int8, row scale 2^(e_i-RB))."""
+    m = np.abs(P).max(axis=1)
+    _, ex = np.frexp(m)                      # m = f * 2^ex, f in [0.5, 1)  ->  ilogb(m) = ex - 1
+    e = np.where(m > 0, ex + 1, 0).astype(np.int64)
+    e = e + ((m > 0) & (np.ldexp(m, -e) > 0.48))
+    e = np.maximum(e, -500)
+    x = np.ldexp(P, -e[:, None])             # exact
+    q = np.rint(x * 2.0 ** (S * RB)).astype(np.int64)
+    d = np.empty((S,) + P.shape, dtype=np.int8)
+    for t in range(S - 1, -1, -1):
+        lo = q & ((1 << RB) - 1)
+        dd = np.where(lo >= (1 << (RB - 1)), lo - (1 << RB), lo)
+        d[t] = dd
+        q = (q - dd) >> RB
+    assert (q == 0).all(), "carry out of the leading digit"
+    return d, np.ldexp(1.0, e - RB)
+
+
+def oz_syrk(C, P, S=7, RB=8):
+    """ozaki.cu oz_syrk_kernel: lower(C) -= P P' through exact integer products of the digit slices; the S
+    accumulators G_m = sum_{t+u=m} d_t d_u' are int32 on the device (checked here), Horner in fp64."""
+    d, sc = oz_split(P, S, RB)
+    di = d.astype(np.int64)
+    acc = np.zeros(C.shape)
+    for m in range(S - 1, -1, -1):
+        G = sum(di[t] @ di[m - t].T for t in range(m + 1))
+        assert np.abs(G).max() < 2 ** 31
+        acc = acc * 2.0 ** -RB + G
+    upd = (acc * sc[:, None]) * sc[None, :]
+    L = np.tril_indices(C.shape[0])
+    C[L] -= upd[L]
+
+
+def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False):
+    """api.cu potrf_device (stream order flattened): three-level blocking - level-1 blocks of W1 panels (W1=0: same as
+    the sub-blocks), sub-blocks of W panels, single panels.  oz: trailing updates through oz_syrk.
     A: padded (np,np) F-order, lower triangle valid; the factor overwrites it.
     Returns Dinv list, logdet parts, info, z."""
     np_ = A.shape[0]
@@ -111,35 +147,59 @@ def potrf_device(A, b=None, W=2):
     parts = np.zeros(T)
     info = 0
     z = np.zeros(np_) if b is not None else None
-    nblk = (T + W - 1) // W
-    for j in range(nblk):
-        pb, pe = j * W, min(j * W + W, T)
-        for p in range(pb, pe):
-            s = slice(p * NB, (p + 1) * NB)
-            L, Li, ld, inf_p = diag_block(A[s, s])
-            A[s, s] = L
-            Dinv[p], parts[p] = Li, ld
-            if inf_p and not info:
-                info = p * NB + inf_p
-            rem = T - p - 1
-            if rem > 0:
-                pan = A[(p + 1) * NB:, s]
-                gemm_nt(0, pan, pan.copy(), Li, NB, rem, 1)
-            if b is not None:
-                trsv_fwd(A, Dinv, b, z, p, T)
-            inner = pe - p - 1
-            if inner > 0:
-                pan = A[(p + 1) * NB:, s]
-                gemm_nt(1, A[(p + 1) * NB:, (p + 1) * NB:], pan, pan, NB, rem, inner, tri=1)
-        rem = T - pe
-        if rem > 0:
-            kw = (pe - pb) * NB
-            pan = A[pe * NB:, pb * NB:pe * NB]
-            Ct = A[pe * NB:, pe * NB:]
-            first = min(W, rem)
-            gemm_nt(1, Ct, pan, pan, kw, rem, first, tri=1)
-            if rem > first:
-                gemm_nt(1, Ct[:, first * NB:], pan, pan[first * NB:], kw, rem, rem - first, tri=1, tj_off=first)
+    W1 = (W1 // W) * W
+    bstart = []
+    pos = 0
+    while pos < T:
+        big = W1 > W and T - (pos + W1) >= w1_minrem
+        bstart.append(pos)
+        pos = min(pos + (W1 if big else W), T)
+    bstart.append(T)
+
+    def update(rows0, cols_end, k0, k1):
+        """lower tiles of A[rows0:, rows0:cols_end] -= A[rows0:, k0:k1] A[rows0:cols_end, k0:k1]' (tile units)"""
+        pan = A[rows0 * NB:, k0 * NB:k1 * NB]
+        Ct = A[rows0 * NB:, rows0 * NB:]
+        ncols = cols_end - rows0
+        if oz:
+            full = Ct.copy()
+            oz_syrk(full, pan)
+            for tj in range(ncols):
+                for ti in range(tj, T - rows0):
+                    blk = (slice(ti * NB, (ti + 1) * NB), slice(tj * NB, (tj + 1) * NB))
+                    if ti == tj:
+                        mask = np.tril(np.ones((NB, NB), dtype=bool))
+                        Ct[blk][mask] = full[blk][mask]
+                    else:
+                        Ct[blk] = full[blk]
+        else:
+            gemm_nt(1, Ct, pan, pan, (k1 - k0) * NB, T - rows0, ncols, tri=1)
+
+    for j in range(len(bstart) - 1):
+        pb, pe = bstart[j], bstart[j + 1]
+        for sb in range(pb, pe, W):
+            se = min(sb + W, pe)
+            for p in range(sb, se):
+                s = slice(p * NB, (p + 1) * NB)
+                L, Li, ld, inf_p = diag_block(A[s, s])
+                A[s, s] = L
+                Dinv[p], parts[p] = Li, ld
+                if inf_p and not info:
+                    info = p * NB + inf_p
+                rem = T - p - 1
+                if rem > 0:
+                    pan = A[(p + 1) * NB:, s]
+                    gemm_nt(0, pan, pan.copy(), Li, NB, rem, 1)
+                if b is not None:
+                    trsv_fwd(A, Dinv, b, z, p, T)
+                inner = se - p - 1
+                if inner > 0:
+                    pan = A[(p + 1) * NB:, s]
+                    gemm_nt(1, A[(p + 1) * NB:, (p + 1) * NB:], pan, pan, NB, rem, inner, tri=1)
+            if se < pe:
+                update(se, pe, sb, se)          # level-2: the rest of the block's columns
+        if T - pe > 0:
+            update(pe, T, pb, pe)               # level-1: the whole trailing matrix (device: next block's columns first)
     return Dinv, parts, info, z
 
 

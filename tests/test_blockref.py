@@ -82,3 +82,55 @@ def test_inverse_through_upper_factor():
     W = br.inverse_lower(U)
     Ainv = np.linalg.inv(A)
     np.testing.assert_allclose(np.tril(W)[:n, :n], np.tril(Ainv), rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,W,W1", [(1100, 2, 4), (1100, 1, 3), (900, 3, 6)])
+def test_three_level_potrf_with_int8_sliced_updates(n, W, W1):
+    """api.cu potrf_device with level-1 blocks of W1 panels and the trailing updates through the Ozaki split."""
+    A = _spd(n, 5)
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal(n)
+    for oz in (False, True):
+        P = br.pad_spd(A)
+        b = np.zeros(P.shape[0]); b[:n] = y
+        Dinv, parts, info, z = br.potrf_device(P, b, W=W, W1=W1, w1_minrem=0, oz=oz)
+        Lref = np.linalg.cholesky(A)
+        assert info == 0
+        np.testing.assert_allclose(np.tril(P)[:n, :n], Lref, rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(parts.sum(), np.log(np.diag(Lref)).sum(), rtol=1e-12)
+        np.testing.assert_allclose(z[:n], sla.solve_triangular(Lref, y, lower=True), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("S,RB", [(7, 8), (8, 7), (7, 7), (6, 8)])
+def test_ozaki_split_is_exact_to_the_last_slice(S, RB):
+    """ozaki.cu: balanced radix-2^RB digits reconstruct every entry to 2^(e_i - S*RB - 1), digits fit int8, and the
+    leading digit never overflows (rows whose maximum is just below a power of two included)."""
+    rng = np.random.default_rng(S * 10 + RB)
+    P = rng.standard_normal((64, 96)) * np.exp(rng.uniform(-30, 30, size=(64, 1)))
+    P[0, 0] = np.nextafter(2.0 ** 7, 0.0)          # largest mantissa
+    P[1, :] = 0.0                                   # an all-zero row
+    P[2, 5] = -np.nextafter(2.0 ** -3, 0.0)
+    d, sc = br.oz_split(P, S, RB)
+    assert d.dtype == np.int8 and d.min() >= -(1 << (RB - 1)) and d.max() <= (1 << (RB - 1)) - 1
+    rec = sum(d[t].astype(np.float64) * 2.0 ** (-RB * t) for t in range(S)) * sc[:, None]
+    tol = sc * 2.0 ** RB * 2.0 ** (-S * RB - 1)     # 2^e_i * 2^(-S*RB-1)
+    assert np.all(np.abs(rec - P) <= tol[:, None] * (1 + 1e-12))
+
+
+def test_ozaki_syrk_matches_fp64_product():
+    """The int8-sliced update is at least as accurate as an fp64 accumulation of the same contraction."""
+    rng = np.random.default_rng(3)
+    n, k = 96, 384
+    P = rng.standard_normal((n, k)) * np.exp(rng.uniform(-6, 6, size=(n, 1)))
+    C0 = rng.standard_normal((n, n)); C0 = C0 + C0.T
+    C = C0.copy()
+    br.oz_syrk(C, P)
+    # exact reference in long double is not enough (x87 64-bit mantissa at best): use exact rationals on a sample
+    from fractions import Fraction
+    idx = [(0, 0), (5, 3), (40, 17), (95, 95), (70, 2), (33, 32)]
+    den = np.abs(P) @ np.abs(P).T
+    for (i, j) in idx:
+        exact = sum(Fraction(P[i, q]) * Fraction(P[j, q]) for q in range(k))
+        want = float(Fraction(C0[i, j]) - exact)
+        assert abs(C[i, j] - want) <= 4e-16 * den[i, j] + 2e-16 * abs(C0[i, j])
+    assert np.array_equal(np.triu(C, 1), np.triu(C0, 1))      # strictly upper part untouched

@@ -178,3 +178,43 @@ def test_tcgen05_int8_tile_is_exact(eng, N, K):
     B = rng.integers(-64, 65, size=(N, K), dtype=np.int8)
     C = eng.dbg_i8_tile(A, B)
     assert np.array_equal(C, A.astype(np.int32) @ B.astype(np.int32).T)
+
+
+@pytest.mark.parametrize("a_tmem", [1, 2])
+@pytest.mark.parametrize("N,K", [(64, 32), (64, 256), (128, 64)])
+def test_tcgen05_int8_a_operand_through_tmem(eng, N, K, a_tmem):
+    """A staged shared memory -> TMEM by tcgen05.cp.128x256b and read from there by the MMA (mode 2: one TMEM
+    region reused by every k-step, the production pattern of oz_syrk_kernel)."""
+    rng = np.random.default_rng(N * K + a_tmem)
+    A = rng.integers(-128, 128, size=(128, K)).astype(np.int8)
+    B = rng.integers(-128, 128, size=(N, K)).astype(np.int8)
+    C = eng.dbg_i8_tile(A, B, a_tmem=a_tmem)
+    assert np.array_equal(C, A.astype(np.int32) @ B.astype(np.int32).T)
+
+
+def test_tcgen05_int8_mixed_signedness(eng):
+    rng = np.random.default_rng(5)
+    A = rng.integers(0, 256, size=(128, 64)).astype(np.uint8)
+    B = rng.integers(-128, 128, size=(64, 64)).astype(np.int8)
+    assert np.array_equal(eng.dbg_i8_tile(A, B), A.astype(np.int32) @ B.astype(np.int32).T)
+    assert np.array_equal(eng.dbg_i8_tile(B[:, :32].repeat(2, 0), A[:64, :32]),
+                          B[:, :32].repeat(2, 0).astype(np.int32) @ A[:64, :32].astype(np.int32).T)
+
+
+@pytest.mark.parametrize("n,kw", [(128, 128), (384, 256), (1024, 384), (2048, 1152)])
+def test_int8_sliced_trailing_update_matches_fp64(eng, n, kw):
+    """ozaki.cu: lower(C) -= P P' on the int8 tensor cores (7 balanced radix-256 slices, exact int32 accumulation in
+    TMEM) against numpy fp64 and against the DMMA kernel; rows of very different scale; upper triangle untouched."""
+    rng = np.random.default_rng(n + kw)
+    P = rng.standard_normal((n, kw)) * np.exp(rng.uniform(-8, 8, size=(n, 1)))
+    P[3, :] = 0.0
+    C = rng.standard_normal((n, n)); C = C + C.T
+    ref = C - P @ P.T
+    den = np.abs(P) @ np.abs(P).T + np.abs(C)
+    out, _ = eng.dbg_oz_syrk(P, C, mode=0)
+    dm, _ = eng.dbg_oz_syrk(P, C, mode=1)
+    L = np.tril_indices(n)
+    # numpy's own fp64 dot carries ~sqrt(kw)*u relative to |P||P|'; the sliced product itself is exact to 2^-56
+    assert np.max(np.abs(out[L] - ref[L]) / den[L]) < 2e-14
+    assert np.max(np.abs(out[L] - dm[L]) / den[L]) < 2e-14
+    assert np.array_equal(np.triu(out, 1), np.triu(C, 1))

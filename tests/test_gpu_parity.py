@@ -267,3 +267,24 @@ def test_reference_shape_and_type_contract():
     m.optimize(x, y)
     ym, ys2, fm, fs2, lp = m.predict(z)
     assert ym.shape == ys2.shape == fm.shape == fs2.shape == (10, 1) and lp is None
+
+
+def test_int8_tensor_core_and_dmma_updates_agree(monkeypatch):
+    """The same evaluation with the trailing updates on the int8 tensor cores (default) and on fp64 DMMA
+    (GPK_OZAKI=0): nlZ and alpha agree far inside the 1e-6 parity bar."""
+    import math
+    from pygps_b200 import _lib
+    rng = np.random.default_rng(11)
+    N = 6144
+    X = rng.standard_normal((N, 6))
+    y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    eng = _lib.Engine(0)
+    eng.set_data(X)
+    res = {}
+    for oz in ("1", "0"):
+        monkeypatch.setenv("GPK_OZAKI", oz)
+        monkeypatch.setenv("GPK_POTRF_W1_MINREM", "8")     # make the three-level path run at this size
+        out = eng.exact_eval(_lib.COV_RBF, 3, [math.log(1.5), 0.0], math.log(0.1), y, False)
+        res[oz] = (out[0], np.array(out[1]))
+    assert abs(res["1"][0] - res["0"][0]) <= 1e-11 * abs(res["0"][0])
+    assert np.max(np.abs(res["1"][1] - res["0"][1])) <= 1e-8 * np.max(np.abs(res["0"][1]))
