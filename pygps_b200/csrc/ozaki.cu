@@ -41,15 +41,26 @@ constexpr int OZ_THREADS = (OZ_EPI_WARPS + 2) * 32;
 // Balanced digits keep the dropped cross terms (t+u > S-1) at random-walk size; unsigned digits would add them
 // coherently (measured: 10x larger error).  RB=8,S=7 and RB=7,S=8 both carry 56 bits; the former needs 28 instead
 // of 36 tensor-core products per k-step.
+// Returns the S digits packed one per byte, slice t in byte S-1-t (bit patterns of int8).
 template <int S, int RB>
-__device__ __forceinline__ void oz_digits(double x, int8_t (&d)[S]) {
+__device__ __forceinline__ unsigned long long oz_digits(double x) {
   long long q = __double2ll_rn(x * (double)(1ll << (S * RB)));
+  if constexpr (RB == 8) {
+    // q + sum_t 128*256^t has the unsigned base-256 digits d_t + 128: no carry loop, the xor removes the offset
+    unsigned long long B = 0;
 #pragma unroll
-  for (int t = S - 1; t >= 0; --t) {
-    const int lo = (int)(q & ((1 << RB) - 1));
-    const int dd = (lo >= (1 << (RB - 1))) ? lo - (1 << RB) : lo;
-    d[t] = (int8_t)dd;
-    q = (q - dd) >> RB;
+    for (int t = 0; t < S; ++t) B |= 0x80ull << (8 * t);
+    return ((unsigned long long)q + B) ^ B;
+  } else {
+    unsigned long long out = 0;
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+      const int lo = (int)(q & ((1 << RB) - 1));
+      const int dd = (lo >= (1 << (RB - 1))) ? lo - (1 << RB) : lo;
+      out |= (unsigned long long)(dd & 0xff) << (8 * t);
+      q = (q - dd) >> RB;
+    }
+    return out;
   }
 }
 
@@ -87,14 +98,20 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   const size_t kstride = (size_t)n * S * 32;
   int4* dst4 = reinterpret_cast<int4*>(sl + (size_t)r0 * S * 32);
   const int4* src4 = reinterpret_cast<const int4*>(&out[0][0][0][0][0]);
+  uint32_t* out32 = reinterpret_cast<uint32_t*>(&out[0][0][0][0][0]);
+  // this thread: row r, the four k positions 4*kq .. 4*kq+3 of every k-step -> one 32-bit word per slice
+  const int wbase = ((r >> 3) * S * 256 + ((4 * kq) >> 4) * 128 + (r & 7) * 16 + ((4 * kq) & 15)) >> 2;
   for (int ks = 0; ks < kw / 32; ++ks) {
+    unsigned long long qq[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int kk = kq + 8 * j;
-      int8_t d[S];
-      oz_digits<S, RB>(scalbn(prow[(int64_t)(ks * 32 + kk) * lda], -e), d);   // scaling exact; |x| <= 0.48
+    for (int j = 0; j < 4; ++j)
+      qq[j] = oz_digits<S, RB>(scalbn(prow[(int64_t)(ks * 32 + 4 * kq + j) * lda], -e));   // scaling exact; |x| <= 0.48
 #pragma unroll
-      for (int t = 0; t < S; ++t) out[r >> 3][t][kk >> 4][r & 7][kk & 15] = d[t];
+    for (int t = 0; t < S; ++t) {
+      const int sh = 8 * (S - 1 - t);
+      const uint32_t w = (uint32_t)((qq[0] >> sh) & 0xff) | ((uint32_t)((qq[1] >> sh) & 0xff) << 8) |
+                         ((uint32_t)((qq[2] >> sh) & 0xff) << 16) | ((uint32_t)((qq[3] >> sh) & 0xff) << 24);
+      out32[wbase + t * 64] = w;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < 4 * S * 16; c += 256) dst4[ks * (kstride / 16) + c] = src4[c];
