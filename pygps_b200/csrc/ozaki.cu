@@ -125,26 +125,44 @@ struct OzArgs {
   double* C;          // trailing matrix origin (row 0 / col 0 of the sliced rows), column-major
   int64_t ldc;
   int n, kw;          // sliced rows, contraction length
-  int jb0;            // first 128-column block of this launch
+  int jb0, jb1;       // 128-column blocks [jb0, jb1) of this launch
   int ntiles;         // lower-triangle 128x64 tiles of this launch
   int tpc;            // tiles per CTA
   long long* dbg;     // optional per-CTA clock stamps [5] (debug timing), else nullptr
 };
 
-// tile index -> (128-row tile, 64-column tile): column blocks jb0.. in order, each 128-column block jb holds
-// 2*(nt-jb) tiles (two 64-column halves x the row tiles jb..nt-1)
-__device__ __forceinline__ void oz_decode(int idx, int nt, int jb0, int& ti, int& tj) {
-  // f(jb) = tiles before block jb = 2*nt*(jb-jb0) - (jb*(jb-1) - jb0*(jb0-1))
-  const double bb = 2.0 * nt + 1.0, cc = (double)idx + 2.0 * nt * jb0 - (double)jb0 * (jb0 - 1);
-  int jb = (int)((bb - sqrt(fmax(bb * bb - 4.0 * cc, 0.0))) * 0.5);
-  if (jb < jb0) jb = jb0;
-  if (jb > nt - 1) jb = nt - 1;
-  auto f = [&](int b) { return 2 * nt * (b - jb0) - (b * (b - 1) - jb0 * (jb0 - 1)); };
-  while (jb > jb0 && f(jb) > idx) --jb;
-  while (jb + 1 < nt && f(jb + 1) <= idx) ++jb;
-  const int rem = idx - f(jb), cnt = nt - jb;
-  tj = 2 * jb + rem / cnt;
-  ti = jb + rem % cnt;
+// tile index -> (128-row tile ti, 64-column tile tj) over the lower-triangular tile set {jb0 <= jb < jb1, ti >= jb}.
+// Rasterised in BANDS of OZ_BAND row tiles: inside a band the column blocks run left to right and the band's rows
+// innermost, so the ~148 concurrently running CTAs share OZ_BAND A-operand tiles and a handful of B tiles.  The A
+// tiles of a band stay in L2 for the whole band; every B tile is fetched from HBM once per band instead of once
+// per column block (ncu: 6.6 GB of DRAM reads per update with the column-major order, against 0.9 GB of C).
+constexpr int OZ_BAND = 16;
+__device__ __forceinline__ void oz_decode(int idx, int nt, int jb0, int jb1, int& ti, int& tj) {
+  int r_lo = jb0;
+  for (;;) {
+    const int r_hi = min(r_lo + OZ_BAND, nt), rows = r_hi - r_lo;
+    const int nfull = max(min(jb1, r_lo + 1) - jb0, 0);        // column blocks that see all rows of the band
+    const int cnt_full = 2 * rows * nfull;
+    const int t0 = max(jb0, r_lo + 1), t1 = min(jb1, r_hi);    // column blocks that cut the band diagonally
+    const int nt_ = max(t1 - t0, 0);
+    const int cnt_tri = 2 * nt_ * r_hi - (t0 + t1 - 1) * nt_;
+    if (idx < cnt_full + cnt_tri || r_hi >= nt) {
+      if (idx < cnt_full) {
+        tj = 2 * jb0 + idx / rows;
+        ti = r_lo + idx % rows;
+      } else {
+        idx -= cnt_full;
+        int jb = t0;
+        while (jb < t1 - 1 && idx >= 2 * (r_hi - jb)) { idx -= 2 * (r_hi - jb); ++jb; }
+        const int c = r_hi - jb;
+        tj = 2 * jb + idx / c;
+        ti = jb + idx % c;
+      }
+      return;
+    }
+    idx -= cnt_full + cnt_tri;
+    r_lo = r_hi;
+  }
 }
 
 template <int S, int RB>
@@ -185,7 +203,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
       int it = 0;
       for (int tile = tile0; tile < tile1; ++tile) {
         int ti, tj;
-        oz_decode(tile, nt, a.jb0, ti, tj);
+        oz_decode(tile, nt, a.jb0, a.jb1, ti, tj);
         const int8_t* gA = a.sl + (size_t)ti * 128 * S * 32;
         const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
         for (int ks = 0; ks < nk; ++ks, ++it) {
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
     int tcount = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++tcount) {
       int ti, tj;
-      oz_decode(tile, nt, a.jb0, ti, tj);
+      oz_decode(tile, nt, a.jb0, a.jb1, ti, tj);
       const int gi = ti * 128 + q4 * 32 + lane, gj0 = tj * OZ_BN + chalf;
       const double si = a.sc[gi];
       double* crow = a.C + gi + (int64_t)gj0 * a.ldc;
@@ -378,7 +396,7 @@ int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc
   const int nt = n / 128;
   if (jb0 < 0 || jb1 > nt || jb0 >= jb1) return GPK_ERR_ARG;
   const int ntiles = 2 * nt * (jb1 - jb0) - (jb1 * (jb1 - 1) - jb0 * (jb0 - 1));
-  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, ntiles, c.tpc, h->ozDbg};
+  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, h->ozDbg};
   if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
   return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
 }

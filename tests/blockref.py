@@ -101,6 +101,37 @@ def trsv_bwd(A, Dinv, z, x, k, T):
         z[j * NB:(j + 1) * NB] -= A[k * NB:(k + 1) * NB, j * NB:(j + 1) * NB].T @ xk
 
 
+def oz_decode(idx, nt, jb0, jb1, band=16):
+    """ozaki.cu oz_decode: CTA index -> (128-row tile, 64-column tile) of the lower-triangular tile set
+    {jb0 <= jb < jb1, ti >= jb}, rasterised in bands of `band` row tiles (L2 reuse of the operand slices)."""
+    r_lo = jb0
+    while True:
+        r_hi = min(r_lo + band, nt)
+        rows = r_hi - r_lo
+        nfull = max(min(jb1, r_lo + 1) - jb0, 0)
+        cnt_full = 2 * rows * nfull
+        t0, t1 = max(jb0, r_lo + 1), min(jb1, r_hi)
+        n_ = max(t1 - t0, 0)
+        cnt_tri = 2 * n_ * r_hi - (t0 + t1 - 1) * n_
+        if idx < cnt_full + cnt_tri or r_hi >= nt:
+            if idx < cnt_full:
+                return r_lo + idx % rows, 2 * jb0 + idx // rows
+            idx -= cnt_full
+            jb = t0
+            while jb < t1 - 1 and idx >= 2 * (r_hi - jb):
+                idx -= 2 * (r_hi - jb)
+                jb += 1
+            c = r_hi - jb
+            return jb + idx % c, 2 * jb + idx // c
+        idx -= cnt_full + cnt_tri
+        r_lo = r_hi
+
+
+def oz_ntiles(nt, jb0, jb1):
+    """launch_oz_syrk: number of 128x64 tiles (= CTAs) of a launch."""
+    return 2 * nt * (jb1 - jb0) - (jb1 * (jb1 - 1) - jb0 * (jb0 - 1))
+
+
 def oz_split(P, S=7, RB=8):
     """ozaki.cu oz_slice_kernel: per-row exponent, then balanced radix-2^RB digits (all int8).
     Returns (digits [S, n, k] int8, row scale 2^(e_i-RB))."""

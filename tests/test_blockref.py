@@ -134,3 +134,12 @@ def test_ozaki_syrk_matches_fp64_product():
         want = float(Fraction(C0[i, j]) - exact)
         assert abs(C[i, j] - want) <= 4e-16 * den[i, j] + 2e-16 * abs(C0[i, j])
     assert np.array_equal(np.triu(C, 1), np.triu(C0, 1))      # strictly upper part untouched
+
+
+@pytest.mark.parametrize("nt,jb0,jb1", [(1, 0, 1), (5, 0, 5), (40, 0, 40), (40, 0, 3), (40, 3, 40), (33, 9, 33),
+                                         (17, 0, 17), (16, 0, 16), (119, 0, 9), (119, 9, 119)])
+def test_update_tile_rasterisation_covers_each_tile_once(nt, jb0, jb1):
+    n = br.oz_ntiles(nt, jb0, jb1)
+    got = [br.oz_decode(i, nt, jb0, jb1) for i in range(n)]
+    want = {(ti, tj) for jb in range(jb0, jb1) for ti in range(jb, nt) for tj in (2 * jb, 2 * jb + 1)}
+    assert len(set(got)) == n and set(got) == want
