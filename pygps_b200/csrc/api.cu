@@ -61,7 +61,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info, double* b_fwd,
-                 double* z_out) {
+                 double* z_out, const CovArgs* lazy_cov) {
   const int T = (int)(np / NB);
   const int64_t lda = np;
   if (const char* e = getenv("GPK_POTRF_W")) { g_potrf_w = atoi(e); }
@@ -75,21 +75,28 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   // plan the level-1 blocks
   std::vector<int> bstart;
   int64_t need0 = 0, need1 = 0; int rows0 = 0, rows1 = 0, kw0 = 0;
+  // optional short first block (GPK_POTRF_FIRST panels): nothing overlaps the first block's panel chain
+  const int wfirst = env_int("GPK_POTRF_FIRST", 0);   // 0 = off (measured: a short first block costs more in the low-K update than it saves)
   for (int pos = 0; pos < T;) {
     const bool big = oz && W1 > W2 && T - (pos + W1) >= w1_minrem;
-    const int w = big ? W1 : W2;
+    int w = big ? W1 : W2;
+    if (pos == 0 && big && wfirst >= 1 && wfirst < w) w = ((wfirst + W2 - 1) / W2) * W2;
     bstart.push_back(pos);
     const int pe = (pos + w < T) ? pos + w : T;
     if (oz && T - pe >= oz_min) {
       const int64_t nd = (int64_t)(T - pe) * NB * (pe - pos) * NB;
-      if (nd > need0) { need0 = nd; rows0 = (T - pe) * NB; kw0 = (pe - pos) * NB; }
+      if (nd > need0) need0 = nd;
+      if ((T - pe) * NB > rows0) rows0 = (T - pe) * NB;   // row scales: the tallest sliced panel block
     }
     if (big && T - (pos + W2) >= oz_min) { need1 = 1; if ((T - pos - W2) * NB > rows1) rows1 = (T - pos - W2) * NB; }
     pos = pe;
   }
   bstart.push_back(T);
   const int nblk = (int)bstart.size() - 1;
-  if (need0) GPK_TRY(oz_ensure(h, 0, rows0, kw0));
+  if (need0) {
+    kw0 = (int)((need0 + rows0 - 1) / rows0);             // capacity rows0 x kw0 covers every block's slices
+    GPK_TRY(oz_ensure(h, 0, rows0, kw0));
+  }
   if (need1) GPK_TRY(oz_ensure(h, 1, rows1, W2 * NB));
   GPK_TRY(ensure_events(h, 2 * (size_t)T + 4));
   if (h->profile) GPK_TRY(ensure_prof_events(h, 2 * (size_t)T + 2));
@@ -99,7 +106,25 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   h->stats.syrk_flops = 0.0;
   h->prof_pairs = 0;
 
-  GPK_CK(h, cudaEventRecord(ev_fork, h->s_main));
+  if (lazy_cov) {
+    // The matrix is still to be generated (cov_kernel writes K/sn2 + I straight into A): build the columns of the
+    // first level-1 block, let the panel stream start on them, and build the rest underneath the first panels.
+    const int64_t c1 = (int64_t)bstart[1] * NB;
+    CovArgs c = *lazy_cov;
+    c.pS = c1;
+    GPK_TRY(launch_cov(h, h->s_main, c));
+    GPK_CK(h, cudaEventRecord(ev_fork, h->s_main));
+    if (c1 < np) {
+      CovArgs r = *lazy_cov;
+      r.out = lazy_cov->out + c1 * lazy_cov->ld;
+      r.s_bstride = 1; r.s_boff = (int)(c1 / NB);
+      r.pS = np - c1;
+      GPK_TRY(launch_cov(h, h->s_main, r));
+    }
+    GPK_CK(h, cudaEventRecord(h->t1, h->s_main));
+  } else {
+    GPK_CK(h, cudaEventRecord(ev_fork, h->s_main));
+  }
   GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_fork, 0));
   if (b_fwd) GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_fork, 0));
   for (int j = 0; j < nblk; ++j) {
@@ -246,6 +271,8 @@ static int free_all(Handle* h) {
   }
   if (h->dInfo) cudaFree(h->dInfo);
   h->dInfo = nullptr;
+  if (h->dFlags) cudaFree(h->dFlags);
+  h->dFlags = nullptr;
   for (int w = 0; w < 2; ++w) {
     if (h->ozSl[w]) cudaFree(h->ozSl[w]);
     if (h->ozSc[w]) cudaFree(h->ozSc[w]);
@@ -473,6 +500,7 @@ int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int
   GPK_CK(h, cudaMemcpyAsync(h->dScale, h->hPinned, D * sizeof(double), cudaMemcpyHostToDevice, st));
   GPK_CK(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), st));
   GPK_TRY(launch_prescale(h, st, h->dX, n, np, D, h->dScale, divide, premul, h->dXs));
+  CovArgs lazy{};
   {
     CovArgs c{};
     c.F = h->dXs; c.S = h->dXs; c.out = h->dA; c.ld = np;
@@ -480,18 +508,25 @@ int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int
     c.kind = kind; c.matern_d = matern_d; c.epi = EPI_COV; c.ard_dim = 0;
     c.sf2 = sf2; c.scale = 1.0 / sn2; c.diag_add = 1.0;
     c.same_set = 1; c.lower_only = 1; c.pad_identity = 1;
-    GPK_TRY(launch_cov(h, st, c));
+    lazy = c;
   }
-  GPK_CK(h, cudaEventRecord(h->t1, st));
   // right-hand side y - m, zero padded; dB is the forward-solve work copy
   GPK_CK(h, cudaMemsetAsync(h->dR, 0, (size_t)np * sizeof(double), st));
   GPK_CK(h, cudaMemcpyAsync(h->dR, ymm, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
   GPK_CK(h, cudaMemcpyAsync(h->dB, h->dR, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, st));
   h->stats.h2d_bytes += (n + D) * (int64_t)sizeof(double);
 
-  GPK_TRY(potrf_device(h, h->dA, np, h->dDinv, h->dScal, h->dInfo, h->dB, h->dZ));
+  // the matrix build is issued by potrf_device (first block's columns, then the rest under the first panels);
+  // stats.kbuild_ms is the time until the whole matrix exists, potrf_ms the rest of the factorisation
+  if (env_int("GPK_LAZY_COV", 1)) {
+    GPK_TRY(potrf_device(h, h->dA, np, h->dDinv, h->dScal, h->dInfo, h->dB, h->dZ, &lazy));
+  } else {                 // A/B switch: whole matrix first, then the factorisation
+    GPK_TRY(launch_cov(h, st, lazy));
+    GPK_CK(h, cudaEventRecord(h->t1, st));
+    GPK_TRY(potrf_device(h, h->dA, np, h->dDinv, h->dScal, h->dInfo, h->dB, h->dZ));
+  }
   GPK_CK(h, cudaEventRecord(h->t2, st));
-  for (int k = T - 1; k >= 0; --k) GPK_TRY(launch_trsv_bwd(h, st, h->dA, np, h->dDinv, h->dZ, h->dB, k, T));
+  GPK_TRY(launch_trsv_bwd_all(h, st, h->dA, np, h->dDinv, h->dZ, h->dB, T));
   double* res = h->dScal + T;  // [0]=r'alpha [1]=logdet ; [8..] derivative results
   GPK_TRY(launch_finish_alpha(h, st, h->dB, h->dR, 1.0 / sn2, np, h->dAlpha, h->dScal, T, res));
   GPK_CK(h, cudaEventRecord(h->t3, st));

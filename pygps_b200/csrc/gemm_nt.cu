@@ -48,36 +48,40 @@ __device__ __forceinline__ void dmma_16x8x8(double (&c)[4], const double (&a)[4]
 //   BN   column width of the CTA tile (rows are always 128)
 //   WN   warps along N (4 along M): CTA = 128*WN threads, warp tile 32 x BN/WN
 //   BK   k-slab per pipeline stage, ST stages, MINB CTAs per SM the register budget is sized for
-template <int MODE, int BN, int WN, int BK, int ST, int MINB>
-__global__ void __launch_bounds__(128 * WN, MINB) dgemm_nt_kernel(const GemmArgs p) {
-  constexpr int THREADS = 128 * WN;
+//   WM   warps along M: the CTA tile has BM = 32*WM rows (4 -> 128 rows; 1 -> 32-row strips for the latency-critical,
+//        in-place panel TRSM: four times as many CTAs per 128-row tile, each reading and writing only its own rows)
+template <int MODE, int BN, int WN, int BK, int ST, int MINB, int WM = 4>
+__global__ void __launch_bounds__(32 * WM * WN, MINB) dgemm_nt_kernel(const GemmArgs p) {
+  constexpr int THREADS = 32 * WM * WN;
+  constexpr int BM = 32 * WM;
+  constexpr int LDA_S = BM + 4;          // == 4 mod 16 for 32, 64, 128
   constexpr int WTN = BN / WN;           // warp tile width
   constexpr int NT = WTN / 8;            // 8-wide MMA tiles per warp along N
   constexpr int LDB = BN + 4;            // == 4 mod 16 for 64 and 128
-  constexpr int A_STAGE = BK * GEMM_LDS;
+  constexpr int A_STAGE = BK * LDA_S;
   constexpr int B_STAGE = BK * LDB;
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + ST * A_STAGE;
 
   const int ti = blockIdx.x, tjs = blockIdx.y;          // tjs counts BN-wide column tiles
-  const int gi = ti + p.ti_off;
+  const int grow0 = ti * BM + p.ti_off * NB;           // first global row of this tile
+  const int gi = grow0 / NB;                            // its 128-row tile index
   constexpr int SUBS = NB / BN;                         // BN-wide sub-tiles per 128-wide column tile
   const int tc = tjs / SUBS, sub = tjs % SUBS;
   const int cs = (p.cstride > 1) ? p.cstride : 1;
   const int gcol0 = (p.tj_off + tc * cs) * NB + sub * BN;   // first global column of this tile
-  const int grow0 = gi * NB;
-  if (p.tri && grow0 + NB - 1 < gcol0) return;          // tile entirely above the diagonal
+  if (p.tri && grow0 + BM - 1 < gcol0) return;          // tile entirely above the diagonal
   const bool diag_tile = (p.tri != 0) && (gcol0 + BN - 1 > grow0);   // crosses the diagonal
   const int dshift = gcol0 - grow0;                     // store (r,c) iff r >= c + dshift
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 3, wn = warp >> 2;
+  const int wm = warp % WM, wn = warp / WM;
   const int g = lane >> 2, t = lane & 3;
 
-  const double* __restrict__ Ag = p.A + (int64_t)ti * NB;
+  const double* __restrict__ Ag = p.A + (int64_t)ti * BM;
   const double* __restrict__ Bg = p.B + (int64_t)(tc * cs) * NB + sub * BN;
-  double* __restrict__ Cg = p.C + (int64_t)ti * NB + (int64_t)tjs * BN * p.ldc;
+  double* __restrict__ Cg = p.C + (int64_t)ti * BM + (int64_t)tjs * BN * p.ldc;
 
   const int kbeg = (p.tri == 2) ? gi * NB : 0;
   const int nkt = (p.K - kbeg) / BK;
@@ -85,11 +89,11 @@ __global__ void __launch_bounds__(128 * WN, MINB) dgemm_nt_kernel(const GemmArgs
   auto load_stage = [&](int slot, int kt) {
     const int k0 = kbeg + kt * BK;
 #pragma unroll
-    for (int i = 0; i < (BK * 64) / THREADS; ++i) {
-      const int c = tid + i * THREADS;       // BK*64 16-byte chunks of A (64 per column)
-      const int col = c >> 6;
-      const int r = (c & 63) * 2;
-      cp_async16(As + slot * A_STAGE + col * GEMM_LDS + r, Ag + r + (int64_t)(k0 + col) * p.lda);
+    for (int i = 0; i < (BK * BM / 2) / THREADS; ++i) {
+      const int c = tid + i * THREADS;       // BM/2 16-byte chunks per column of A
+      const int col = c / (BM / 2);
+      const int r = (c % (BM / 2)) * 2;
+      cp_async16(As + slot * A_STAGE + col * LDA_S + r, Ag + r + (int64_t)(k0 + col) * p.lda);
     }
 #pragma unroll
     for (int i = 0; i < (BK * BN / 2) / THREADS; ++i) {
@@ -145,8 +149,8 @@ __global__ void __launch_bounds__(128 * WN, MINB) dgemm_nt_kernel(const GemmArgs
 #pragma unroll
     for (int kk = 0; kk < BK / 8; ++kk) {
       double a[2][4];
-      const double* a_lo = as + (kk * 8 + t) * GEMM_LDS + wm * 32 + g;
-      const double* a_hi = a_lo + 4 * GEMM_LDS;
+      const double* a_lo = as + (kk * 8 + t) * LDA_S + wm * 32 + g;
+      const double* a_hi = a_lo + 4 * LDA_S;
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
         a[mi][0] = a_lo[mi * 16];
@@ -189,9 +193,9 @@ __global__ void __launch_bounds__(128 * WN, MINB) dgemm_nt_kernel(const GemmArgs
     }
 }
 
-template <int BN, int BK, int ST>
+template <int BN, int BK, int ST, int WM = 4>
 constexpr size_t gemm_smem() {
-  return size_t(ST) * BK * (GEMM_LDS + BN + 4) * sizeof(double);
+  return size_t(ST) * BK * (32 * WM + 4 + BN + 4) * sizeof(double);
 }
 
 // variant table:      BN   WN  BK  ST  MINB
@@ -200,29 +204,32 @@ constexpr size_t gemm_smem() {
 #define GPK_V2 128, 4, 16, 4, 1     /* 128x128, 16 warps, one CTA per SM                  */
 #define GPK_V3 128, 4, 32, 3, 1     /* 128x128, 16 warps, 32-deep k-slabs, 3 stages       */
 #define GPK_V4 64, 2, 32, 2, 2      /* 128x64, 8 warps, two CTAs per SM, 32-deep k-slabs  */
+#define GPK_V5 128, 4, 16, 4, 2, 1  /* 32x128 row strips, 4 warps, two CTAs per SM: in-place products (panel TRSM) */
 
 static int g_gemm_variant = 0;
+static int g_trsm_strip = 1;     // in-place products in 32-row strips (V5) instead of whole 128-row tiles (V1)
 
-template <int BN, int WN, int BK, int ST, int MINB>
+template <int BN, int WN, int BK, int ST, int MINB, int WM = 4>
 static int variant_init(Handle* h) {
-  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<0, BN, WN, BK, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)gemm_smem<BN, BK, ST>()));
-  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<1, BN, WN, BK, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)gemm_smem<BN, BK, ST>()));
-  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<2, BN, WN, BK, ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)gemm_smem<BN, BK, ST>()));
+  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<0, BN, WN, BK, ST, MINB, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)gemm_smem<BN, BK, ST, WM>()));
+  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<1, BN, WN, BK, ST, MINB, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)gemm_smem<BN, BK, ST, WM>()));
+  GPK_CK(h, cudaFuncSetAttribute(dgemm_nt_kernel<2, BN, WN, BK, ST, MINB, WM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)gemm_smem<BN, BK, ST, WM>()));
   return 0;
 }
 
-template <int BN, int WN, int BK, int ST, int MINB>
+template <int BN, int WN, int BK, int ST, int MINB, int WM = 4>
 static void variant_launch(cudaStream_t st, int mode, const GemmArgs& a, int tiles_m, int tiles_n) {
-  dim3 grid((unsigned)tiles_m, (unsigned)(tiles_n * (NB / BN)));
+  dim3 grid((unsigned)(tiles_m * (4 / WM)), (unsigned)(tiles_n * (NB / BN)));
+  constexpr int TH = 32 * WM * WN;
   if (mode == 0)
-    dgemm_nt_kernel<0, BN, WN, BK, ST, MINB><<<grid, 128 * WN, gemm_smem<BN, BK, ST>(), st>>>(a);
+    dgemm_nt_kernel<0, BN, WN, BK, ST, MINB, WM><<<grid, TH, gemm_smem<BN, BK, ST, WM>(), st>>>(a);
   else if (mode == 1)
-    dgemm_nt_kernel<1, BN, WN, BK, ST, MINB><<<grid, 128 * WN, gemm_smem<BN, BK, ST>(), st>>>(a);
+    dgemm_nt_kernel<1, BN, WN, BK, ST, MINB, WM><<<grid, TH, gemm_smem<BN, BK, ST, WM>(), st>>>(a);
   else
-    dgemm_nt_kernel<2, BN, WN, BK, ST, MINB><<<grid, 128 * WN, gemm_smem<BN, BK, ST>(), st>>>(a);
+    dgemm_nt_kernel<2, BN, WN, BK, ST, MINB, WM><<<grid, TH, gemm_smem<BN, BK, ST, WM>(), st>>>(a);
 }
 
 int gemm_init(Handle* h) {
@@ -233,6 +240,8 @@ int gemm_init(Handle* h) {
   GPK_TRY((variant_init<GPK_V2>(h)));
   GPK_TRY((variant_init<GPK_V3>(h)));
   GPK_TRY((variant_init<GPK_V4>(h)));
+  GPK_TRY((variant_init<GPK_V5>(h)));
+  if (const char* e = getenv("GPK_TRSM_STRIP")) g_trsm_strip = atoi(e);
   return 0;
 }
 
@@ -243,7 +252,11 @@ int launch_gemm_nt(Handle* h, cudaStream_t st, int mode, const GemmArgs& a, int 
   // are only safe when ONE CTA owns a whole 128-row tile of A: it finishes reading the tile before its
   // epilogue writes it.  Column-split tiles (BN=64) would let a sibling CTA overwrite columns still being read.
   const bool inplace = (static_cast<const double*>(a.C) == a.A);
-  switch (inplace ? 1 : g_gemm_variant) {
+  // Either ONE CTA owns the whole 128-row tile (V1), or - the default - four CTAs own 32-row strips of it (V5): a
+  // strip's CTA reads only its own rows of A, so the in-place product is still race-free, and the latency-critical
+  // TRSM of the Cholesky panel chain spreads over four times as many SMs.
+  switch (inplace ? (g_trsm_strip ? 5 : 1) : g_gemm_variant) {
+    case 5: variant_launch<GPK_V5>(st, mode, a, tiles_m, tiles_n); break;
     case 1: variant_launch<GPK_V1>(st, mode, a, tiles_m, tiles_n); break;
     case 2: variant_launch<GPK_V2>(st, mode, a, tiles_m, tiles_n); break;
     case 3: variant_launch<GPK_V3>(st, mode, a, tiles_m, tiles_n); break;

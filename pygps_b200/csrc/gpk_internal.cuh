@@ -90,6 +90,7 @@ struct Handle {
   double* dR = nullptr;      // (np) y - m
   double* dScal = nullptr;   // scalars: [0..T) logdet parts, then results
   int* dInfo = nullptr;
+  int* dFlags = nullptr; int flag_epoch = 0;   // epoch-stamped ready flags of the persistent backward substitution
   double* hPinned = nullptr; // small pinned staging
   // posterior state
   bool has_post = false; int kind = 0, matern_d = 3, nhyp = 0; double sn2 = 1.0, sf2 = 1.0;
@@ -152,6 +153,8 @@ int launch_trsv_fwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, co
                     double* z, int k, int T);
 int launch_trsv_bwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* z,
                     double* x, int k, int T);
+int launch_trsv_bwd_all(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* z,
+                        double* x, int T);   // all T steps; one cooperative launch when T <= #SMs
 int launch_finish_alpha(Handle* h, cudaStream_t st, const double* x, const double* r, double inv_sn2, int64_t np,
                         double* alpha, const double* parts, int T, double* res);
 int launch_sum_parts(Handle* h, cudaStream_t st, const double* parts, int T, double* res);
@@ -188,6 +191,7 @@ int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_ti
                   const double* Dinv, int T);
 int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv);
 int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info,
-                 double* b_fwd /*nullable: fused forward solve in/out*/, double* z_out);
+                 double* b_fwd /*nullable: fused forward solve in/out*/, double* z_out,
+                 const CovArgs* lazy_cov = nullptr /*generate the matrix inside, overlapped with the first panels*/);
 
 }  // namespace gpk

@@ -165,7 +165,7 @@ __device__ __forceinline__ void oz_decode(int idx, int nt, int jb0, int jb1, int
   }
 }
 
-template <int S, int RB>
+template <int S, int RB, int EPI>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   constexpr uint32_t A_BYTES = 128 * S * 32, B_BYTES = OZ_BN * S * 32, STAGE = A_BYTES + B_BYTES;
   constexpr uint32_t TCOLS = 512;
@@ -289,37 +289,79 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
       const int gi = ti * 128 + q4 * 32 + lane, gj0 = tj * OZ_BN + chalf;
       const double si = a.sc[gi];
       double* crow = a.C + gi + (int64_t)gj0 * a.ldc;
-      // pull this thread's 32 C entries towards L2 now; they are read after the accumulators are complete
+      if constexpr (EPI == 0) {
+        // pull this thread's 32 C entries towards L2 now; they are read after the accumulators are complete
 #pragma unroll
-      for (int q = 0; q < OZ_BN / 2; ++q)
-        if (gi >= gj0 + q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + (int64_t)q * a.ldc));
-      mbar_wait(&done, tcount & 1);
-      tc_fence_after();
-      if (dbg && tid == 0) dbg[3] = clock64();
+        for (int q = 0; q < OZ_BN / 2; ++q)
+          if (gi >= gj0 + q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + (int64_t)q * a.ldc));
+        mbar_wait(&done, tcount & 1);
+        tc_fence_after();
+        if (dbg && tid == 0) dbg[3] = clock64();
 #pragma unroll 1
-      for (int c0 = 0; c0 < OZ_BN / 2; c0 += 8) {
-        uint32_t v[S][8];
+        for (int c0 = 0; c0 < OZ_BN / 2; c0 += 8) {
+          uint32_t v[S][8];
 #pragma unroll
-        for (int m = 0; m < S; ++m) tc_ld8(tw + (uint32_t)m * OZ_BN + c0, v[m]);
-        double cv[8], sj[8];
+          for (int m = 0; m < S; ++m) tc_ld8(tw + (uint32_t)m * OZ_BN + c0, v[m]);
+          double cv[8], sj[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          cv[q] = (gi >= gj0 + c0 + q) ? crow[(int64_t)(c0 + q) * a.ldc] : 0.0;
-          sj[q] = __ldg(a.sc + gj0 + c0 + q);
+          for (int q = 0; q < 8; ++q) {
+            cv[q] = (gi >= gj0 + c0 + q) ? crow[(int64_t)(c0 + q) * a.ldc] : 0.0;
+            sj[q] = __ldg(a.sc + gj0 + c0 + q);
+          }
+          tc_wait_ld();
+          if (c0 + 8 == OZ_BN / 2) {           // all accumulator reads of this tile are done: hand TMEM back
+            tc_fence_before();
+            mbar_arrive(&tfree);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            // int32 -> fp64 without the (slow) conversion unit: 2^52 + 2^31 + v is exactly representable
+            double acc = __hiloint2double(0x43300000, (int)(v[S - 1][q] ^ 0x80000000u)) - 4503601774854144.0;
+#pragma unroll
+            for (int m = S - 2; m >= 0; --m)
+              acc = fma(acc, HORNER, __hiloint2double(0x43300000, (int)(v[m][q] ^ 0x80000000u)) - 4503601774854144.0);
+            if (gi >= gj0 + c0 + q) crow[(int64_t)(c0 + q) * a.ldc] = cv[q] - (acc * si) * sj[q];
+          }
         }
-        tc_wait_ld();
-        if (c0 + 8 == OZ_BN / 2) {           // all accumulator reads of this tile are done: hand TMEM back
-          tc_fence_before();
-          mbar_arrive(&tfree);
-        }
+      } else {
+        // EPI 1: the first 8 of this thread's 32 C entries are loaded into registers NOW (they arrive while the MMA
+        // loop runs), the other 24 are pulled towards L2 now and loaded one 8-column round ahead of their use
+        double cv[8], cn[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          // int32 -> fp64 without the (slow) conversion unit: 2^52 + 2^31 + v is exactly representable
-          double acc = __hiloint2double(0x43300000, (int)(v[S - 1][q] ^ 0x80000000u)) - 4503601774854144.0;
+        for (int q = 0; q < 8; ++q) cv[q] = (gi >= gj0 + q) ? crow[(int64_t)q * a.ldc] : 0.0;
 #pragma unroll
-          for (int m = S - 2; m >= 0; --m)
-            acc = fma(acc, HORNER, __hiloint2double(0x43300000, (int)(v[m][q] ^ 0x80000000u)) - 4503601774854144.0);
-          if (gi >= gj0 + c0 + q) crow[(int64_t)(c0 + q) * a.ldc] = cv[q] - (acc * si) * sj[q];
+        for (int q = 8; q < OZ_BN / 2; ++q)
+          if (gi >= gj0 + q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + (int64_t)q * a.ldc));
+        mbar_wait(&done, tcount & 1);
+        tc_fence_after();
+        if (dbg && tid == 0) dbg[3] = clock64();
+#pragma unroll 1
+        for (int c0 = 0; c0 < OZ_BN / 2; c0 += 8) {
+          if (c0 + 8 < OZ_BN / 2) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cn[q] = (gi >= gj0 + c0 + 8 + q) ? crow[(int64_t)(c0 + 8 + q) * a.ldc] : 0.0;
+          }
+          uint32_t v[S][8];
+#pragma unroll
+          for (int m = 0; m < S; ++m) tc_ld8(tw + (uint32_t)m * OZ_BN + c0, v[m]);
+          double sj[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) sj[q] = __ldg(a.sc + gj0 + c0 + q);
+          tc_wait_ld();
+          if (c0 + 8 == OZ_BN / 2) {
+            tc_fence_before();
+            mbar_arrive(&tfree);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            double acc = __hiloint2double(0x43300000, (int)(v[S - 1][q] ^ 0x80000000u)) - 4503601774854144.0;
+#pragma unroll
+            for (int m = S - 2; m >= 0; --m)
+              acc = fma(acc, HORNER, __hiloint2double(0x43300000, (int)(v[m][q] ^ 0x80000000u)) - 4503601774854144.0);
+            if (gi >= gj0 + c0 + q) crow[(int64_t)(c0 + q) * a.ldc] = cv[q] - (acc * si) * sj[q];
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) cv[q] = cn[q];
         }
       }
       if (dbg && tid == 0) dbg[4] = clock64();
@@ -330,11 +372,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tbase), "n"(TCOLS) : "memory");
 }
 
-struct OzCfg { int S, RB, tpc; };
+struct OzCfg { int S, RB, tpc, epi; };
 static OzCfg oz_cfg() {
-  static OzCfg c{0, 0, 0};
+  static OzCfg c{0, 0, 0, 0};
   if (c.S == 0) {
-    c.RB = 8; c.S = 7; c.tpc = 1;
+    c.RB = 8; c.S = 7; c.tpc = 1; c.epi = 0;
+    if (const char* e = getenv("GPK_OZAKI_EPI")) c.epi = atoi(e) ? 1 : 0;
     if (const char* e = getenv("GPK_OZAKI_RADIX")) { const int v = atoi(e); if (v == 7 || v == 8) c.RB = v; }
     if (c.RB == 7) c.S = 8;
     if (const char* e = getenv("GPK_OZAKI_SLICES")) { const int v = atoi(e); if (v >= 6 && v <= 8) c.S = v; }
@@ -377,17 +420,22 @@ int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int6
   return c.S == 7 ? oz_slice_t<7, 8>(h, which, st, P, lda, n, kw) : oz_slice_t<6, 8>(h, which, st, P, lda, n, kw);
 }
 
-template <int S, int RB>
-static int oz_syrk_t(Handle* h, cudaStream_t st, const OzArgs& a) {
+template <int S, int RB, int EPI>
+static int oz_syrk_e(Handle* h, cudaStream_t st, const OzArgs& a) {
   static bool attr_done = false;
   const size_t smem = (size_t)OZ_ST * (128 + OZ_BN) * S * 32;
   if (!attr_done) {
-    GPK_CK(h, cudaFuncSetAttribute(oz_syrk_kernel<S, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CK(h, cudaFuncSetAttribute(oz_syrk_kernel<S, RB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  oz_syrk_kernel<S, RB><<<(a.ntiles + a.tpc - 1) / a.tpc, OZ_THREADS, smem, st>>>(a);
+  oz_syrk_kernel<S, RB, EPI><<<(a.ntiles + a.tpc - 1) / a.tpc, OZ_THREADS, smem, st>>>(a);
   GPK_CK(h, cudaGetLastError());
   return 0;
+}
+
+template <int S, int RB>
+static int oz_syrk_t(Handle* h, cudaStream_t st, const OzArgs& a) {
+  return oz_cfg().epi ? oz_syrk_e<S, RB, 1>(h, st, a) : oz_syrk_e<S, RB, 0>(h, st, a);
 }
 
 // C(lower triangle, 128-column blocks [jb0, jb1)) -= P·P' from the current slices

@@ -107,9 +107,15 @@ potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ D
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
-    const int r = idx % DB, c = idx / DB;
-    S_(r, c) = (r >= c) ? Ablk[r + (int64_t)c * lda] : 0.0;
+  // 16-byte loads, all 64 KB of the lower triangle requested before the first use (the block is L2-resident:
+  // the update that produced it has just finished)
+#pragma unroll 8
+  for (int idx = tid; idx < DB * DB / 2; idx += DIAG_THREADS) {
+    const int r = (idx % (DB / 2)) * 2, c = idx / (DB / 2);
+    double2 v = make_double2(0.0, 0.0);
+    if (r + 1 >= c) v = *reinterpret_cast<const double2*>(Ablk + r + (int64_t)c * lda);
+    if (r < c) v.x = 0.0;
+    *reinterpret_cast<double2*>(&S_(r, c)) = v;
   }
   if (tid == 0) { s_logdet = 0.0; s_info = 0; }
   __syncthreads();
@@ -118,59 +124,85 @@ potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ D
   // ---------------- phase 1: blocked Cholesky, inner block 32 ----------------
   for (int jb = 0; jb < DB / IB; ++jb) {
     const int j0 = jb * IB;
-    {
-      // 32x32 diagonal block: one matrix row per lane, pivots and multipliers by warp shuffle.
-      // EVERY warp runs it (redundantly) so the shuffles sit in uniform control flow; warp 0 publishes.
+    if (warp == 0) {
+      // 32x32 diagonal block: ONE warp, one matrix row per lane in registers, square-root-free (LDL') elimination.
+      // Measured on B200 (scripts/lat_probe.cu): DFMA latency 8 clk, but a warp issues only one SHFL per 6.5 clk
+      // (37 clk latency) - the 992 shuffles per block of the first version cost 11k clk, and eight warps running it
+      // redundantly shared one shuffle unit.  Here column j travels through shared memory instead: every lane stores
+      // its (unscaled) entry straight into its final place S(:, j), and reads the column back with broadcast
+      // 16-byte loads.  Dependent chain per column: STS -> LDS (pivot) -> MUFU seed + cubic Newton step -> multiplier
+      // -> update of the next column, about 100 clk; the square roots are taken once at the end, one per lane.
       double a[IB];
 #pragma unroll
       for (int c = 0; c < IB; ++c) a[c] = S_(j0 + lane, j0 + c);
-      __syncthreads();               // everyone has read the block before warp 0 overwrites it
-      double lsum = 0.0, prod = 1.0;
+      __syncwarp();
+      double dmine = 1.0;
       int bad = 0;
 #pragma unroll
       for (int j = 0; j < IB; ++j) {
-        const double d = __shfl_sync(FULL, a[j], j);
+        const double aj = (lane >= j) ? a[j] : 0.0;      // column j of L * sqrt(d_j); zero above the diagonal
+        double* colj = &S_(j0, j0 + j);
+        colj[lane] = aj;
+        __syncwarp();
+        const double d = colj[j];
         if (!(d > 0.0) && bad == 0) bad = j + 1;
-        const double rinv = rsqrt(d);
-        const double l = d * rinv;
-        prod *= l;
-        if ((j & 7) == 7) { lsum += log(prod); prod = 1.0; }
-        if (tid == j) rdiag[j0 + j] = rinv;
-        const double v = (lane == j) ? l : a[j] * rinv;
-        a[j] = (lane >= j) ? v : 0.0;
+        if (lane == j) dmine = d;
+        double x0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(d));
+        const double e = fma(-d, x0, 1.0);
+        const double inv = fma(x0, fma(e, e, e), x0);      // x0 (1 + e + e^2): relative error e^3 < 2^-58
+        const double w = -aj * inv;
+        if (((j + 1) & 1) && j + 1 < IB) a[j + 1] = fma(w, colj[j + 1], a[j + 1]);
 #pragma unroll
-        for (int c = j + 1; c < IB; ++c) {
-          const double lc = __shfl_sync(FULL, a[j], c);
-          a[c] = fma(-a[j], lc, a[c]);
+        for (int c = (j + 2) & ~1; c < IB; c += 2) {
+          const double2 lc = *reinterpret_cast<const double2*>(colj + c);
+          a[c] = fma(w, lc.x, a[c]);
+          a[c + 1] = fma(w, lc.y, a[c + 1]);
         }
       }
-      if (warp == 0) {
+      const double rs = rsqrt(dmine);                      // 1 / L_jj of this lane's column
+      double lg = 0.5 * log(dmine);
 #pragma unroll
-        for (int c = 0; c < IB; ++c) S_(j0 + lane, j0 + c) = (lane >= c) ? a[c] : 0.0;
-        if (lane == 0) {
-          s_logdet += lsum;
-          if (bad != 0 && s_info == 0) s_info = gidx0 + j0 + bad;
-        }
+      for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(FULL, lg, o);
+      rdiag[j0 + lane] = rs;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < IB; c += 2) {
+        const double2 rc = *reinterpret_cast<const double2*>(rdiag + j0 + c);
+        // entries above the diagonal were stored as zeros already; the unscaled columns are re-read from S
+        const double v0 = (lane == c) ? dmine * rs : S_(j0 + lane, j0 + c) * rc.x;
+        const double v1 = (lane == c + 1) ? dmine * rs : S_(j0 + lane, j0 + c + 1) * rc.y;
+        S_(j0 + lane, j0 + c) = v0;
+        S_(j0 + lane, j0 + c + 1) = v1;
+      }
+      if (lane == 0) {
+        s_logdet += lg;
+        if (bad != 0 && s_info == 0) s_info = gidx0 + j0 + bad;
       }
     }
     __syncthreads();
     DBG_T();
     const int nrb = DB / IB - 1 - jb;  // 32-row blocks below the diagonal block
     if (nrb > 0) {
-      // sub-panel: X * L_jj^T = Y by forward substitution, one row per thread, row kept in registers
+      // sub-panel: X * L_jj^T = Y, one row per thread kept in registers, right-looking so that the factor is read
+      // down its columns (broadcast 16-byte loads) and the dependent chain per column is one DMUL + one DFMA
       if (tid < nrb * IB) {
         const int r = j0 + IB + tid;
         double x[IB];
 #pragma unroll
-        for (int c = 0; c < IB; ++c) {
-          double s0 = S_(r, j0 + c), s1 = 0.0;
+        for (int c = 0; c < IB; ++c) x[c] = S_(r, j0 + c);
 #pragma unroll
-          for (int k = 0; k < c; ++k) {
-            const double lck = S_(j0 + c, j0 + k);      // warp-uniform address: broadcast
-            if (k & 1) s1 = fma(-x[k], lck, s1);
-            else s0 = fma(-x[k], lck, s0);
+        for (int k = 0; k < IB; ++k) {
+          const double xk = x[k] * rdiag[j0 + k];
+          x[k] = xk;
+          const double* colk = &S_(j0, j0 + k);
+          if (((k + 1) & 1) && k + 1 < IB) x[k + 1] = fma(-xk, colk[k + 1], x[k + 1]);
+#pragma unroll
+          for (int c = (k + 2) & ~1; c < IB; c += 2) {
+            const double2 lc = *reinterpret_cast<const double2*>(colk + c);
+            x[c] = fma(-xk, lc.x, x[c]);
+            x[c + 1] = fma(-xk, lc.y, x[c + 1]);
           }
-          x[c] = (s0 + s1) * rdiag[j0 + c];
         }
 #pragma unroll
         for (int c = 0; c < IB; ++c) S_(r, j0 + c) = x[c];
@@ -217,9 +249,12 @@ potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ D
 #pragma unroll
     for (int i = 0; i < IB; ++i) T_(warp, i, lane) = w[i];
   } else {
-    for (int idx = tid - 4 * 32; idx < DB * DB; idx += DIAG_THREADS - 4 * 32) {
-      const int r = idx % DB, c = idx / DB;
-      Ablk[r + (int64_t)c * lda] = (r >= c) ? S_(r, c) : 0.0;
+    for (int idx = tid - 4 * 32; idx < DB * DB / 2; idx += DIAG_THREADS - 4 * 32) {
+      const int r = (idx % (DB / 2)) * 2, c = idx / (DB / 2);
+      double2 v = *reinterpret_cast<const double2*>(&S_(r, c));
+      if (r < c) v.x = 0.0;
+      if (r + 1 < c) v.y = 0.0;
+      *reinterpret_cast<double2*>(Ablk + r + (int64_t)c * lda) = v;
     }
   }
   if (tid == 0) {
@@ -266,9 +301,9 @@ potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ D
 
   DBG_T();
   // ---------------- phase 4: inverse to global (dense 128x128, pitch 128) --------
-  for (int idx = tid; idx < DB * DB; idx += DIAG_THREADS) {
-    const int r = idx % DB, c = idx / DB;
-    Dinv[idx] = S_(r, c);
+  for (int idx = tid; idx < DB * DB / 2; idx += DIAG_THREADS) {
+    const int r = (idx % (DB / 2)) * 2, c = idx / (DB / 2);
+    *reinterpret_cast<double2*>(Dinv + r + c * DB) = *reinterpret_cast<const double2*>(&S_(r, c));
   }
   __syncthreads();
   DBG_T();
@@ -371,10 +406,124 @@ __global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_bwd_kernel(const double*
   }
 }
 
+// ---------------------------------------------------------------------------
+// Whole backward substitution x = L^-T z in ONE cooperative launch (T <= number of SMs).
+// CTA j owns block j: it streams the tiles L[k, j], k = T-1 .. j+1, of its block column through a ring of
+// 32-column chunks (cp.async, prefetched as far as the ring allows - the factor is complete, only the x_k are
+// not), applies z_j -= L[k,j]' x_k as soon as CTA k has published x_k (epoch-stamped flag, release/acquire), and
+// finishes with x_j = Dinv_j' z_j.  The dependent chain per block step is flag -> x_k -> two 128x128 transposed
+// GEMVs from shared memory -> publish: a few microseconds, against ~10 us per step for one launch per step.
+// ---------------------------------------------------------------------------
+constexpr int BW_CH = 32;                                  // columns per chunk
+constexpr int BW_RING = 6;                                 // chunks in flight
+constexpr size_t BW_SMEM = size_t(BW_RING) * BW_CH * NB * sizeof(double);   // 192 KB
+
+__global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_bwd_persistent_kernel(
+    const double* __restrict__ A, int64_t lda, const double* __restrict__ Dinv, const double* __restrict__ z,
+    double* __restrict__ x, int* __restrict__ flags, int epoch, int T) {
+  extern __shared__ __align__(16) double ring[];
+  __shared__ double zacc[NB], zfin[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x;
+  const int ntiles = T - 1 - j;                            // tiles of L in this block column, then Dinv_j
+  const int nchunks = 4 * (ntiles + 1);
+  if (tid < NB) zacc[tid] = 0.0;
+
+  auto issue = [&](int g) {
+    if (g < nchunks) {
+      const int t = g >> 2, q = g & 3;
+      const double* src; int64_t pitch;
+      if (t < ntiles) { const int k = T - 1 - t; src = A + (int64_t)k * NB + (int64_t)(j * NB + q * BW_CH) * lda; pitch = lda; }
+      else { src = Dinv + (int64_t)j * NB * NB + (int64_t)q * BW_CH * NB; pitch = NB; }
+      double* dst = ring + (size_t)(g % BW_RING) * BW_CH * NB;
+#pragma unroll
+      for (int i = 0; i < (BW_CH * NB / 2) / TRSV_THREADS; ++i) {
+        const int ch = tid + i * TRSV_THREADS;             // 16-byte piece: 64 per column
+        const int c = ch >> 6, r = (ch & 63) * 2;
+        unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r + c * NB);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + r + (int64_t)c * pitch) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+#pragma unroll
+  for (int g = 0; g < BW_RING - 1; ++g) issue(g);
+
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;           // this lane's entries of the current vector (x_k or z_j)
+  for (int g = 0; g < nchunks; ++g) {
+    const int t = g >> 2, q = g & 3;
+    if (q == 0) {
+      if (t < ntiles) {
+        const int k = T - 1 - t;
+        if (tid == 0) {
+          int f;
+          do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(f) : "l"(flags + k) : "memory"); } while (f != epoch);
+        }
+        __syncthreads();
+        const double* xk = x + (int64_t)k * NB;
+        v0 = __ldcg(xk + lane); v1 = __ldcg(xk + lane + 32); v2 = __ldcg(xk + lane + 64); v3 = __ldcg(xk + lane + 96);
+      } else {
+        __syncthreads();                                   // all updates of z_j are in zacc
+        if (tid < NB) zfin[tid] = z[(int64_t)j * NB + tid] - zacc[tid];
+        __syncthreads();
+        v0 = zfin[lane]; v1 = zfin[lane + 32]; v2 = zfin[lane + 64]; v3 = zfin[lane + 96];
+      }
+    }
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(BW_RING - 2) : "memory");
+    __syncthreads();                                       // chunk g has landed; chunk g-1's slot is free
+    issue(g + BW_RING - 1);
+    const double* ch = ring + (size_t)(g % BW_RING) * BW_CH * NB;
+#pragma unroll
+    for (int i = 0; i < BW_CH / (TRSV_THREADS / 32); ++i) {
+      const int c = warp * (BW_CH / (TRSV_THREADS / 32)) + i;
+      const double* col = ch + c * NB;
+      double sacc = fma(col[lane], v0, fma(col[lane + 32], v1, fma(col[lane + 64], v2, col[lane + 96] * v3)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(FULL, sacc, o);
+      if (lane == 0) {
+        if (t < ntiles) zacc[q * BW_CH + c] += sacc;
+        else x[(int64_t)j * NB + q * BW_CH + c] = sacc;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(flags + j), "r"(epoch) : "memory");
+  }
+}
+
+int launch_trsv_bwd_all(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* z,
+                        double* x, int T) {
+  static int persist = -1, sms = 0;
+  if (persist < 0) {
+    const char* e = getenv("GPK_TRSV_PERSIST");
+    persist = e ? atoi(e) : 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  }
+  if (!persist || T > sms || T < 2) {
+    for (int k = T - 1; k >= 0; --k) GPK_TRY(launch_trsv_bwd(h, st, A, lda, Dinv, z, x, k, T));
+    return 0;
+  }
+  if (!h->dFlags) {
+    GPK_CK(h, cudaMalloc((void**)&h->dFlags, 1024 * sizeof(int)));
+    GPK_CK(h, cudaMemsetAsync(h->dFlags, 0, 1024 * sizeof(int), st));
+    h->flag_epoch = 0;
+  }
+  int epoch = ++h->flag_epoch;
+  int* flags = h->dFlags;
+  void* args[] = {(void*)&A, (void*)&lda, (void*)&Dinv, (void*)&z, (void*)&x, (void*)&flags, (void*)&epoch, (void*)&T};
+  GPK_CK(h, cudaLaunchCooperativeKernel((const void*)trsv_bwd_persistent_kernel, dim3(T), dim3(TRSV_THREADS), args,
+                                        BW_SMEM, st));
+  h->stats.launches++;
+  return 0;
+}
+
 int diag_init(Handle* h) {
   GPK_CK(h, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
   GPK_CK(h, cudaFuncSetAttribute(trsv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM));
   GPK_CK(h, cudaFuncSetAttribute(trsv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM));
+  GPK_CK(h, cudaFuncSetAttribute(trsv_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SMEM));
   return 0;
 }
 
