@@ -98,11 +98,21 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
     GPK_TRY(oz_ensure(h, 0, rows0, kw0));
   }
   if (need1) GPK_TRY(oz_ensure(h, 1, rows1, W2 * NB));
-  GPK_TRY(ensure_events(h, 2 * (size_t)T + 4));
+  GPK_TRY(ensure_events(h, 5 * (size_t)T + 4));
   if (h->profile) GPK_TRY(ensure_prof_events(h, 2 * (size_t)T + 2));
   cudaEvent_t* ev_panel = h->ev.data();      // [T]   panel p factored and solved
   cudaEvent_t* ev_col = h->ev.data() + T;    // [T]   columns of level-1 block j up to date
   cudaEvent_t ev_fork = h->ev[2 * T], ev_join = h->ev[2 * T + 1], ev_aux = h->ev[2 * T + 2];
+  cudaEvent_t* ev_diag = h->ev.data() + 2 * T + 4;   // [T] diagonal block p factored and inverted   (split chain)
+  cudaEvent_t* ev_head = ev_diag + T;                // [T] head of panel p: tile (p+1,p) solved, tile (p+1,p+1) updated
+  cudaEvent_t* ev_tail = ev_head + T;                // [T] tail of panel p: rows p+2.. solved, rest of the sub-block updated
+  // Split panel chain (GPK_POTRF_SPLIT, default on).  The next diagonal block only needs tile (p+1,p) solved and tile
+  // (p+1,p+1) updated, so those two small products (the "head", 4 CTAs each) run on the panel stream right behind the
+  // diagonal kernel, while the TRSM of the rows below and the rest of the rank-128 update (the "tail") run on s_tail,
+  // one panel behind.  The dependent chain per panel shrinks from diag + full TRSM + full inner update to
+  // diag + two 32-row-strip products.
+  const int split = env_int("GPK_POTRF_SPLIT", 1);
+
   h->stats.syrk_flops = 0.0;
   h->prof_pairs = 0;
 
@@ -126,6 +136,7 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
     GPK_CK(h, cudaEventRecord(ev_fork, h->s_main));
   }
   GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_fork, 0));
+  if (split) GPK_CK(h, cudaStreamWaitEvent(h->s_tail, ev_fork, 0));
   if (b_fwd) GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_fork, 0));
   for (int j = 0; j < nblk; ++j) {
     const int pb = bstart[j], pe = bstart[j + 1];      // the level-1 block: panels [pb, pe)
@@ -136,26 +147,65 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
         double* App = A + (int64_t)p * NB * (1 + lda);
         double* Dp = Dinv + (int64_t)p * NB * NB;
         const int rem = T - p - 1;                     // tile rows below panel p
+        const int inner = se - p - 1;                  // remaining columns of this sub-block
+        if (split && p >= sb + 2) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_tail[p - 2], 0));
         GPK_TRY(launch_diag(h, h->s_panel, App, lda, Dp, logdet_parts + p, info, p * NB));
-        if (rem > 0) {
+        if (!split || inner == 0 || rem < 2) {
+          // whole panel on the panel stream: TRSM of all rows below, then the rank-128 update of the sub-block
+          if (split && p > sb) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_tail[p - 1], 0));
+          if (rem > 0) {
+            GemmArgs t{};
+            t.A = App + NB; t.B = Dp; t.C = App + NB;
+            t.lda = lda; t.ldb = NB; t.ldc = lda; t.K = NB; t.tri = 0;
+            GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, rem, 1));
+          }
+          GPK_CK(h, cudaEventRecord(ev_panel[p], h->s_panel));
+          if (inner > 0) {
+            GemmArgs u{};
+            u.A = App + NB; u.B = App + NB; u.C = A + (int64_t)(p + 1) * NB * (1 + lda);
+            u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = NB; u.tri = 1;
+            GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, u, rem, inner));
+          }
+          if (split) GPK_CK(h, cudaEventRecord(ev_tail[p], h->s_panel));   // nothing of panel p is left for s_tail
+        } else {
+          GPK_CK(h, cudaEventRecord(ev_diag[p], h->s_panel));
+          // head (panel stream): tile (p+1,p) <- tile * Dinv_p', then tile (p+1,p+1) -= L(p+1,p) L(p+1,p)'
+          if (p > sb) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_tail[p - 1], 0));
           GemmArgs t{};
           t.A = App + NB; t.B = Dp; t.C = App + NB;
           t.lda = lda; t.ldb = NB; t.ldc = lda; t.K = NB; t.tri = 0;
-          GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, rem, 1));
+          GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, 1, 1));
+          GemmArgs hs{};
+          hs.A = App + NB; hs.B = App + NB; hs.C = A + (int64_t)(p + 1) * NB * (1 + lda);
+          hs.lda = lda; hs.ldb = lda; hs.ldc = lda; hs.K = NB; hs.tri = 1; hs.strips = 1;
+          GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, hs, 1, 1));
+          GPK_CK(h, cudaEventRecord(ev_head[p], h->s_panel));
+          // tail (s_tail): TRSM of rows p+2.., then column p+1 below its diagonal tile, then columns p+2..se-1
+          GPK_CK(h, cudaStreamWaitEvent(h->s_tail, ev_diag[p], 0));
+          GemmArgs tt = t;
+          tt.A = App + 2 * NB; tt.C = App + 2 * NB;
+          GPK_TRY(launch_gemm_nt(h, h->s_tail, 0, tt, rem - 1, 1));
+          GPK_CK(h, cudaStreamWaitEvent(h->s_tail, ev_head[p], 0));
+          GPK_CK(h, cudaEventRecord(ev_panel[p], h->s_tail));
+          GemmArgs u1{};
+          u1.A = App + 2 * NB; u1.B = App + NB; u1.C = A + (int64_t)(p + 2) * NB + (int64_t)(p + 1) * NB * lda;
+          u1.lda = lda; u1.ldb = lda; u1.ldc = lda; u1.K = NB; u1.tri = 0;
+          GPK_TRY(launch_gemm_nt(h, h->s_tail, 1, u1, rem - 1, 1));
+          if (inner > 1) {
+            GemmArgs u2{};
+            u2.A = App + 2 * NB; u2.B = App + 2 * NB; u2.C = A + (int64_t)(p + 2) * NB * (1 + lda);
+            u2.lda = lda; u2.ldb = lda; u2.ldc = lda; u2.K = NB; u2.tri = 1;
+            GPK_TRY(launch_gemm_nt(h, h->s_tail, 1, u2, rem - 1, inner - 1));
+          }
+          GPK_CK(h, cudaEventRecord(ev_tail[p], h->s_tail));
         }
-        GPK_CK(h, cudaEventRecord(ev_panel[p], h->s_panel));
         if (b_fwd) {
           GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_panel[p], 0));
           GPK_TRY(launch_trsv_fwd(h, h->s_aux, A, lda, Dinv, b_fwd, z_out, p, T));
         }
-        const int inner = se - p - 1;                  // remaining columns of this sub-block
-        if (inner > 0) {
-          GemmArgs u{};
-          u.A = App + NB; u.B = App + NB; u.C = A + (int64_t)(p + 1) * NB * (1 + lda);
-          u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = NB; u.tri = 1;
-          GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, u, rem, inner));
-        }
       }
+      // the sub-block is complete when its last panel's tail is (the panel stream runs the level-2 / level-1 hand-over)
+      if (split && se - 1 >= sb) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_tail[se - 1], 0));
       if (se < pe) {
         // level-2 update: the block's remaining columns [se, pe), all rows below the sub-block
         const int rows = T - se, cols = pe - se, kw2 = (se - sb) * NB;
@@ -408,6 +458,8 @@ int gpk_create(int device, gpk_handle* out) {
   if (cudaStreamCreateWithPriority(&h->s_panel, cudaStreamNonBlocking, hi) != cudaSuccess) return fail(GPK_ERR_CUDA);
   if (cudaStreamCreateWithPriority(&h->s_aux, cudaStreamNonBlocking, (hi < lo) ? hi + 1 : lo) != cudaSuccess)
     return fail(GPK_ERR_CUDA);
+  if (cudaStreamCreateWithPriority(&h->s_tail, cudaStreamNonBlocking, (hi < lo) ? hi + 1 : lo) != cudaSuccess)
+    return fail(GPK_ERR_CUDA);
   cudaEvent_t* te[] = {&h->t0, &h->t1, &h->t2, &h->t3, &h->t4};
   for (auto e : te)
     if (cudaEventCreate(e) != cudaSuccess) return fail(GPK_ERR_CUDA);
@@ -435,6 +487,7 @@ int gpk_destroy(gpk_handle hh) {
   if (h->s_main) cudaStreamDestroy(h->s_main);
   if (h->s_panel) cudaStreamDestroy(h->s_panel);
   if (h->s_aux) cudaStreamDestroy(h->s_aux);
+  if (h->s_tail) cudaStreamDestroy(h->s_tail);
   delete h;
   return 0;
 }

@@ -255,7 +255,7 @@ int launch_gemm_nt(Handle* h, cudaStream_t st, int mode, const GemmArgs& a, int 
   // Either ONE CTA owns the whole 128-row tile (V1), or - the default - four CTAs own 32-row strips of it (V5): a
   // strip's CTA reads only its own rows of A, so the in-place product is still race-free, and the latency-critical
   // TRSM of the Cholesky panel chain spreads over four times as many SMs.
-  switch (inplace ? (g_trsm_strip ? 5 : 1) : g_gemm_variant) {
+  switch (inplace ? (g_trsm_strip ? 5 : 1) : (a.strips ? 5 : g_gemm_variant)) {
     case 5: variant_launch<GPK_V5>(st, mode, a, tiles_m, tiles_n); break;
     case 1: variant_launch<GPK_V1>(st, mode, a, tiles_m, tiles_n); break;
     case 2: variant_launch<GPK_V2>(st, mode, a, tiles_m, tiles_n); break;

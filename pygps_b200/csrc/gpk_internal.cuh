@@ -35,6 +35,7 @@ struct GemmArgs {
   int tj_off;       // global tile index of grid column 0
   int tri;          // 0: all tiles; 1: only gi>=gj, diagonal tiles store row>=col;
                     // 2: as 1, and the contraction starts at k = gi*NB (U*U^T of an upper-triangular U)
+  int strips;       // 1: compute in 32-row strips (four CTAs per 128-row tile) even when the product is not in place
   int cstride;      // block-cyclic columns (multi-GPU): grid column tile tc is GLOBAL column tile tj_off + tc*cstride;
                     // B rows advance by cstride*NB per tc while C columns stay packed.  0/1 = contiguous.
 };
@@ -66,7 +67,7 @@ struct CovArgs {
 // ---- handle ---------------------------------------------------------------
 struct Handle {
   int device = 0;
-  cudaStream_t s_main = nullptr, s_panel = nullptr, s_aux = nullptr;
+  cudaStream_t s_main = nullptr, s_panel = nullptr, s_aux = nullptr, s_tail = nullptr;
   std::vector<cudaEvent_t> ev;          // dependency events (no timing)
   cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr, t4 = nullptr;
   cudaError_t last_cuda = cudaSuccess;
