@@ -67,21 +67,28 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   if (const char* e = getenv("GPK_POTRF_W")) { g_potrf_w = atoi(e); }
   const int W2 = (g_potrf_w < 1) ? ((T > 64) ? 3 : (T > 8 ? 2 : 1)) : (g_potrf_w > 8 ? 8 : g_potrf_w);
   // trailing updates with at least oz_min tile rows go to the int8 tensor cores (GPK_OZAKI=0 keeps everything on DMMA)
-  const int oz = env_int("GPK_OZAKI", 1), oz_min = env_int("GPK_OZAKI_MIN", 24);
+  const int oz = env_int("GPK_OZAKI", 1), oz_min = env_int("GPK_OZAKI_MIN", 16);
   int W1 = env_int("GPK_POTRF_W1", 9);
-  const int w1_minrem = env_int("GPK_POTRF_W1_MINREM", 64);
+  const int w1_minrem = env_int("GPK_POTRF_W1_MINREM", 48);
   if (W1 > 16) W1 = 16;
   W1 = (W1 / W2) * W2;                                  // a whole number of sub-blocks
   // plan the level-1 blocks
-  std::vector<int> bstart;
+  std::vector<int> bstart, bsub, bbig;                       // block starts; sub-block width of each block
+  // small blocks (the panel-chain-bound tail of the factorisation) are ONE sub-block of W2B panels: fewer
+  // hand-overs between the panel chain and the trailing update per panel
+  int W2B = env_int("GPK_POTRF_W2B", T > 64 ? 4 : W2);   // measured at N=16384: 4 (3: +0.15 ms, 6: +0.3 ms)
+  if (W2B < 1) W2B = 1;
+  if (W2B > 8) W2B = 8;
   int64_t need0 = 0, need1 = 0; int rows0 = 0, rows1 = 0, kw0 = 0;
   // optional short first block (GPK_POTRF_FIRST panels): nothing overlaps the first block's panel chain
   const int wfirst = env_int("GPK_POTRF_FIRST", 0);   // 0 = off (measured: a short first block costs more in the low-K update than it saves)
   for (int pos = 0; pos < T;) {
     const bool big = oz && W1 > W2 && T - (pos + W1) >= w1_minrem;
-    int w = big ? W1 : W2;
+    int w = big ? W1 : W2B;
     if (pos == 0 && big && wfirst >= 1 && wfirst < w) w = ((wfirst + W2 - 1) / W2) * W2;
     bstart.push_back(pos);
+    bsub.push_back(big ? W2 : w);
+    bbig.push_back(big ? 1 : 0);
     const int pe = (pos + w < T) ? pos + w : T;
     if (oz && T - pe >= oz_min) {
       const int64_t nd = (int64_t)(T - pe) * NB * (pe - pos) * NB;
@@ -138,11 +145,20 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_fork, 0));
   if (split) GPK_CK(h, cudaStreamWaitEvent(h->s_tail, ev_fork, 0));
   if (b_fwd) GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_fork, 0));
+  const int head_l1_on = env_int("GPK_POTRF_HEADL1", 1);
+  bool head_l1 = false;                                 // the last hand-over updated the next diagonal tile itself
   for (int j = 0; j < nblk; ++j) {
     const int pb = bstart[j], pe = bstart[j + 1];      // the level-1 block: panels [pb, pe)
-    if (j > 0) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_col[j], 0));
-    for (int sb = pb; sb < pe; sb += W2) {
-      const int se = (sb + W2 < pe) ? sb + W2 : pe;    // the level-2 sub-block: panels [sb, se)
+    // block j's columns are up to date after ev_col[j]; when the hand-over already updated the first diagonal tile on
+    // the panel stream (head_l1), only the kernels after the first diagonal block have to wait for it
+    bool col_pending = false;
+    if (j > 0) {
+      if (head_l1) col_pending = true;
+      else GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_col[j], 0));
+    }
+    const int w2 = bsub[j];
+    for (int sb = pb; sb < pe; sb += w2) {
+      const int se = (sb + w2 < pe) ? sb + w2 : pe;    // the level-2 sub-block: panels [sb, se)
       for (int p = sb; p < se; ++p) {
         double* App = A + (int64_t)p * NB * (1 + lda);
         double* Dp = Dinv + (int64_t)p * NB * NB;
@@ -150,6 +166,11 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
         const int inner = se - p - 1;                  // remaining columns of this sub-block
         if (split && p >= sb + 2) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_tail[p - 2], 0));
         GPK_TRY(launch_diag(h, h->s_panel, App, lda, Dp, logdet_parts + p, info, p * NB));
+        if (col_pending) {
+          GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_col[j], 0));
+          GPK_CK(h, cudaStreamWaitEvent(h->s_tail, ev_col[j], 0));
+          col_pending = false;
+        }
         if (!split || inner == 0 || rem < 2) {
           // whole panel on the panel stream: TRSM of all rows below, then the rank-128 update of the sub-block
           if (split && p > sb) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_tail[p - 1], 0));
@@ -232,10 +253,19 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
       const int first = (nextw < rem) ? nextw : rem;   // the next block's columns go first
       double* Pblk = A + (int64_t)pe * NB + (int64_t)pb * NB * lda;
       double* Ctr = A + (int64_t)pe * NB * (1 + lda);
+      // Panel-chain-bound blocks: the next block's first diagonal tile gets its update on the PANEL stream (four
+      // 32-row strips), so the next diagonal kernel starts at once and overlaps the update of the other tiles.
+      head_l1 = split && head_l1_on && !bbig[j];
+      if (head_l1) {
+        GemmArgs hl{};
+        hl.A = Pblk; hl.B = Pblk; hl.C = Ctr;
+        hl.lda = lda; hl.ldb = lda; hl.ldc = lda; hl.K = kw; hl.tri = 1; hl.strips = 1;
+        GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, hl, 1, 1));
+      }
       if (oz && rem >= oz_min) {
         // int8 tensor-core path (ozaki.cu): slice the panel block once, then the same two launches
         GPK_TRY(launch_oz_slice(h, 0, h->s_main, Pblk, lda, rem * NB, kw));
-        GPK_TRY(launch_oz_syrk(h, 0, h->s_main, Ctr, lda, rem * NB, kw, 0, first));
+        GPK_TRY(launch_oz_syrk(h, 0, h->s_main, Ctr, lda, rem * NB, kw, 0, first, head_l1 ? 1 : 0));
         GPK_CK(h, cudaEventRecord(ev_col[j + 1], h->s_main));
         if (rem > first) GPK_TRY(launch_oz_syrk(h, 0, h->s_main, Ctr, lda, rem * NB, kw, first, rem));
       } else {
@@ -243,7 +273,19 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
         u.A = Pblk; u.B = u.A;
         u.C = Ctr;
         u.lda = lda; u.ldb = lda; u.ldc = lda; u.K = kw; u.tri = 1; u.ti_off = 0; u.tj_off = 0;
-        GPK_TRY(launch_gemm_nt(h, h->s_main, 1, u, rem, first));
+        if (!head_l1) {
+          GPK_TRY(launch_gemm_nt(h, h->s_main, 1, u, rem, first));
+        } else if (rem > 1) {
+          // everything but tile (0,0): column 0 below its diagonal tile, then columns 1..first-1 (lower triangle)
+          GemmArgs c0 = u;
+          c0.A = Pblk + NB; c0.C = Ctr + NB; c0.tri = 0;
+          GPK_TRY(launch_gemm_nt(h, h->s_main, 1, c0, rem - 1, 1));
+          if (first > 1) {
+            GemmArgs c1 = u;
+            c1.A = Pblk + NB; c1.B = Pblk + NB; c1.C = Ctr + (int64_t)NB * (1 + lda);
+            GPK_TRY(launch_gemm_nt(h, h->s_main, 1, c1, rem - 1, first - 1));
+          }
+        }
         GPK_CK(h, cudaEventRecord(ev_col[j + 1], h->s_main));
         if (rem > first) {
           GemmArgs v = u;

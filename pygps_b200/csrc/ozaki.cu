@@ -128,6 +128,7 @@ struct OzArgs {
   int jb0, jb1;       // 128-column blocks [jb0, jb1) of this launch
   int ntiles;         // lower-triangle 128x64 tiles of this launch
   int tpc;            // tiles per CTA
+  int skip00;         // leave the first diagonal tile (rows/cols 0..127) alone: the panel stream updates it itself
   long long* dbg;     // optional per-CTA clock stamps [5] (debug timing), else nullptr
 };
 
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   constexpr double HORNER = 1.0 / (double)(1 << RB);
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint64_t full[OZ_ST], empty[OZ_ST], done, tfree;
+  __shared__ double sjs[OZ_BN];
   __shared__ uint32_t tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -180,16 +182,40 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   const size_t kstride = (size_t)a.n * S * 32;
   const int tile0 = blockIdx.x * a.tpc;
   const int tile1 = min(tile0 + a.tpc, a.ntiles);
+  if (a.skip00) {                                          // (host guarantees tpc == 1 with skip00)
+    int ti0, tj0;
+    oz_decode(tile0, nt, a.jb0, a.jb1, ti0, tj0);
+    if (ti0 == 0 && tj0 < 2) return;
+  }
 
+  if (warp == OZ_EPI_WARPS + 1) {
+    // the producer initialises the barriers itself and requests the first OZ_ST stages (all of the first tile:
+    // nk >= OZ_ST) BEFORE the CTA-wide barrier, so their latency overlaps the TMEM allocation
+    if (elect_one()) {
+      for (int s = 0; s < OZ_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      mbar_init(&done, 1);
+      mbar_init(&tfree, OZ_EPI_WARPS * 32);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      if (tile0 < tile1) {
+        int ti, tj;
+        oz_decode(tile0, nt, a.jb0, a.jb1, ti, tj);
+        const int8_t* gA = a.sl + (size_t)ti * 128 * S * 32;
+        const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
+#pragma unroll
+        for (int ks = 0; ks < OZ_ST; ++ks) {
+          mbar_expect_tx(&full[ks], STAGE);
+          uint8_t* sdst = sm + (size_t)ks * STAGE;
+          bulk_g2s(sdst, gA + ks * kstride, A_BYTES, &full[ks]);
+          bulk_g2s(sdst + A_BYTES, gB + ks * kstride, B_BYTES, &full[ks]);
+        }
+      }
+    }
+    __syncwarp();
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
-  if (tid == 32) {
-    for (int s = 0; s < OZ_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(&done, 1);
-    mbar_init(&tfree, OZ_EPI_WARPS * 32);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -208,7 +234,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
         const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
         for (int ks = 0; ks < nk; ++ks, ++it) {
           const int slot = it % OZ_ST;
-          if (it >= OZ_ST) mbar_wait(&empty[slot], ((it / OZ_ST) - 1) & 1);
+          if (it < OZ_ST) continue;                      // requested before the CTA barrier (see above)
+          mbar_wait(&empty[slot], ((it / OZ_ST) - 1) & 1);
           mbar_expect_tx(&full[slot], STAGE);
           uint8_t* s = sm + (size_t)slot * STAGE;
           bulk_g2s(s, gA + ks * kstride, A_BYTES, &full[slot]);
@@ -324,44 +351,52 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
           }
         }
       } else {
-        // EPI 1: the first 8 of this thread's 32 C entries are loaded into registers NOW (they arrive while the MMA
-        // loop runs), the other 24 are pulled towards L2 now and loaded one 8-column round ahead of their use
-        double cv[8], cn[8];
+        // EPI 1: software-pipelined drain.  The accumulators are read in rounds of 4 columns (7 x tcgen05.ld.x4); round
+        // r+1's TMEM loads and round r+2's C loads are in flight while round r is converted and stored, so the TMEM
+        // read (the longest part of the epilogue), the fp64 conversion and the global latency overlap.
+        constexpr int NR = OZ_BN / 2 / 4;               // rounds per thread
+        uint32_t v[2][S][4];
+        double cvb[3][4];
+        // the tile's 64 column scales go to shared memory once (ncu: the epilogue's largest stall was the global
+        // load of the first column scale of every round)
+        if (tid < OZ_BN) sjs[tid] = a.sc[tj * OZ_BN + tid];
+        asm volatile("bar.sync 1, %0;\n" ::"n"(OZ_EPI_WARPS * 32) : "memory");
 #pragma unroll
-        for (int q = 0; q < 8; ++q) cv[q] = (gi >= gj0 + q) ? crow[(int64_t)q * a.ldc] : 0.0;
-#pragma unroll
-        for (int q = 8; q < OZ_BN / 2; ++q)
+        for (int q = 0; q < OZ_BN / 2; ++q)
           if (gi >= gj0 + q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + (int64_t)q * a.ldc));
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cvb[r][q] = (gi >= gj0 + 4 * r + q) ? crow[(int64_t)(4 * r + q) * a.ldc] : 0.0;
         mbar_wait(&done, tcount & 1);
         tc_fence_after();
         if (dbg && tid == 0) dbg[3] = clock64();
-#pragma unroll 1
-        for (int c0 = 0; c0 < OZ_BN / 2; c0 += 8) {
-          if (c0 + 8 < OZ_BN / 2) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) cn[q] = (gi >= gj0 + c0 + 8 + q) ? crow[(int64_t)(c0 + 8 + q) * a.ldc] : 0.0;
-          }
-          uint32_t v[S][8];
+        for (int m = 0; m < S; ++m) tc_ld4(tw + (uint32_t)m * OZ_BN, v[0][m]);
 #pragma unroll
-          for (int m = 0; m < S; ++m) tc_ld8(tw + (uint32_t)m * OZ_BN + c0, v[m]);
-          double sj[8];
+        for (int r = 0; r < NR; ++r) {
+          tc_wait_ld();                                  // round r has landed
+          if (r + 1 < NR) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) sj[q] = __ldg(a.sc + gj0 + c0 + q);
-          tc_wait_ld();
-          if (c0 + 8 == OZ_BN / 2) {
+            for (int m = 0; m < S; ++m) tc_ld4(tw + (uint32_t)m * OZ_BN + 4 * (r + 1), v[(r + 1) & 1][m]);
+          } else {                                       // all accumulator reads of this tile are done: hand TMEM back
             tc_fence_before();
             mbar_arrive(&tfree);
           }
+          if (r + 2 < NR) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            double acc = __hiloint2double(0x43300000, (int)(v[S - 1][q] ^ 0x80000000u)) - 4503601774854144.0;
-#pragma unroll
-            for (int m = S - 2; m >= 0; --m)
-              acc = fma(acc, HORNER, __hiloint2double(0x43300000, (int)(v[m][q] ^ 0x80000000u)) - 4503601774854144.0);
-            if (gi >= gj0 + c0 + q) crow[(int64_t)(c0 + q) * a.ldc] = cv[q] - (acc * si) * sj[q];
+            for (int q = 0; q < 4; ++q)
+              cvb[(r + 2) % 3][q] = (gi >= gj0 + 4 * (r + 2) + q) ? crow[(int64_t)(4 * (r + 2) + q) * a.ldc] : 0.0;
           }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) cv[q] = cn[q];
+          for (int q = 0; q < 4; ++q) {
+            const int c = 4 * r + q;
+            double acc = __hiloint2double(0x43300000, (int)(v[r & 1][S - 1][q] ^ 0x80000000u)) - 4503601774854144.0;
+#pragma unroll
+            for (int m = S - 2; m >= 0; --m)
+              acc = fma(acc, HORNER, __hiloint2double(0x43300000, (int)(v[r & 1][m][q] ^ 0x80000000u)) - 4503601774854144.0);
+            if (gi >= gj0 + c) crow[(int64_t)c * a.ldc] = cvb[r % 3][q] - (acc * si) * sjs[chalf + c];
+          }
         }
       }
       if (dbg && tid == 0) dbg[4] = clock64();
@@ -376,7 +411,7 @@ struct OzCfg { int S, RB, tpc, epi; };
 static OzCfg oz_cfg() {
   static OzCfg c{0, 0, 0, 0};
   if (c.S == 0) {
-    c.RB = 8; c.S = 7; c.tpc = 1; c.epi = 0;
+    c.RB = 8; c.S = 7; c.tpc = 1; c.epi = 1;   // epi 0: the first, unpipelined epilogue (kept for A/B runs)
     if (const char* e = getenv("GPK_OZAKI_EPI")) c.epi = atoi(e) ? 1 : 0;
     if (const char* e = getenv("GPK_OZAKI_RADIX")) { const int v = atoi(e); if (v == 7 || v == 8) c.RB = v; }
     if (c.RB == 7) c.S = 8;
@@ -439,12 +474,14 @@ static int oz_syrk_t(Handle* h, cudaStream_t st, const OzArgs& a) {
 }
 
 // C(lower triangle, 128-column blocks [jb0, jb1)) -= P·P' from the current slices
-int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1) {
+int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
+                   int skip00) {
   const OzCfg c = oz_cfg();
   const int nt = n / 128;
   if (jb0 < 0 || jb1 > nt || jb0 >= jb1) return GPK_ERR_ARG;
   const int ntiles = 2 * nt * (jb1 - jb0) - (jb1 * (jb1 - 1) - jb0 * (jb0 - 1));
-  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, h->ozDbg};
+  if (skip00 && (c.tpc != 1 || jb0 != 0)) return GPK_ERR_ARG;
+  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, skip00, h->ozDbg};
   if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
   return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
 }
