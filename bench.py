@@ -332,8 +332,20 @@ def run_ours(args):
             else:
                 peak = 2.0 * 1590.0
                 src = "2 x the profiling guide's fallback bf16 figure (1.59 PFLOP/s); MEASURED_PEAKS.json absent: of fallback"
-            roof = {"bound": "tensor", "kernel": "oz_syrk_kernel<7,8> (trailing SYRK update: tcgen05.mma.kind::i8, TMEM accumulators)",
-                    "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak, "traffic": None,
+            # DRAM traffic of the dominant launch (largest oz_syrk launch of an evaluation) from the committed ncu --set full
+            # capture, next to the algorithmic bytes of that same launch (C lower triangle read + written once, slices once)
+            traffic, traffic_note = None, None
+            try:
+                with open(os.path.join(ROOT, "profiles", "r1_oz_syrk_traffic.json")) as f:
+                    tj = json.load(f)
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_note = {"launch": tj["launch"], "algorithmic_bytes": tj["algorithmic_bytes"]["total"],
+                                "ratio": traffic / float(tj["algorithmic_bytes"]["total"]), "source": tj["source"]}
+            except Exception:
+                pass
+            roof = {"bound": "tensor", "kernel": "oz_syrk_kernel<7,8,1> (trailing SYRK update: tcgen05.mma.kind::i8, TMEM accumulators)",
+                    "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_note": traffic_note,
                     "peak_source": src,
                     "int8_probe": {"clk_per_mma_128x256x32": probe_clk, "tops": probe_tops},
                     "fp64_equivalent": {"achieved_tflops": fp64_equiv, "fp64_pipe_peak_tflops": fp64_peak,
