@@ -33,6 +33,40 @@ def gemm_nt(mode, C, A, B, K, tiles_m, tiles_n, tri=0, ti_off=0, tj_off=0):
                 c[...] = new
 
 
+def rcp_newton(d):
+    """The diagonal kernel's reciprocal: a 20-bit seed (MUFU.RCP64H reads only the upper word of d; modelled by
+    rounding 1/d to 20 mantissa bits) and ONE cubic Newton step x0 (1 + e + e^2), e = 1 - d x0: relative error e^3."""
+    with np.errstate(all="ignore"):
+        m, ex = np.frexp(1.0 / d)
+        x0 = np.ldexp(np.round(m * 2.0 ** 21) / 2.0 ** 21, ex)
+        e = 1.0 - d * x0
+        return x0 + x0 * (e * e + e)
+
+
+def ldl_block(a):
+    """One 32x32 diagonal sub-block as potrf_diag_kernel's warp 0 factors it: square-root-free elimination (row r's
+    multiplier is a[r,j] / d_j), the unscaled column kept until the end, then L[:,c] = column / sqrt(d_c).
+    Returns (L lower, sum log diag L, 1-based index of the first non-positive pivot or 0)."""
+    n = a.shape[0]
+    a = a.copy()
+    d = np.ones(n)
+    bad = 0
+    for j in range(n):
+        d[j] = a[j, j]
+        if not d[j] > 0 and bad == 0:
+            bad = j + 1
+        a[:j, j] = 0.0
+        w = a[:, j] * rcp_newton(d[j])
+        for c in range(j + 1, n):
+            a[:, c] -= w * a[c, j]
+    with np.errstate(all="ignore"):
+        rs = 1.0 / np.sqrt(d)
+        L = np.tril(a * rs[None, :])
+        L[np.arange(n), np.arange(n)] = d * rs
+        lg = 0.5 * np.sum(np.log(d))
+    return L, lg, bad
+
+
 def diag_block(Ablk):
     """potrf_diag_kernel: returns (L, inv(L), sum log diag, info) for one 128x128 block,
     following the kernel's 32-wide inner blocking and its in-place inversion order."""
@@ -44,17 +78,10 @@ def diag_block(Ablk):
     for jb in range(nblk):
         j0 = jb * IB
         a = S[j0:j0 + IB, j0:j0 + IB].copy()
-        for j in range(IB):            # the warp-shuffle column loop
-            d = a[j, j]
-            if not d > 0 and info == 0:
-                info = j0 + j + 1
-            l = np.sqrt(d)
-            a[j:, j] = a[j:, j] / l
-            a[j, j] = l
-            a[:j, j] = 0.0
-            logdet += np.log(l)
-            for c in range(j + 1, IB):
-                a[:, c] -= a[:, j] * a[c, j]
+        a, lg, bad = ldl_block(a)
+        logdet += lg
+        if bad and info == 0:
+            info = j0 + bad
         a = np.tril(a)
         S[j0:j0 + IB, j0:j0 + IB] = a
         W = np.zeros((IB, IB))
@@ -167,7 +194,7 @@ def oz_syrk(C, P, S=7, RB=8):
     C[L] -= upd[L]
 
 
-def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False):
+def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=None):
     """api.cu potrf_device (stream order flattened): three-level blocking - level-1 blocks of W1 panels (W1=0: same as
     the sub-blocks), sub-blocks of W panels, single panels.  oz: trailing updates through oz_syrk.
     A: padded (np,np) F-order, lower triangle valid; the factor overwrites it.
@@ -179,12 +206,15 @@ def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False):
     info = 0
     z = np.zeros(np_) if b is not None else None
     W1 = (W1 // W) * W
-    bstart = []
+    W2B = W if W2B is None else W2B      # small (chain-bound) blocks are ONE sub-block of W2B panels
+    bstart, bsub, bbig = [], [], []
     pos = 0
     while pos < T:
         big = W1 > W and T - (pos + W1) >= w1_minrem
         bstart.append(pos)
-        pos = min(pos + (W1 if big else W), T)
+        bsub.append(W if big else W2B)
+        bbig.append(big)
+        pos = min(pos + (W1 if big else W2B), T)
     bstart.append(T)
 
     def update(rows0, cols_end, k0, k1):
@@ -206,10 +236,12 @@ def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False):
         else:
             gemm_nt(1, Ct, pan, pan, (k1 - k0) * NB, T - rows0, ncols, tri=1)
 
+    head_l1 = False
     for j in range(len(bstart) - 1):
         pb, pe = bstart[j], bstart[j + 1]
-        for sb in range(pb, pe, W):
-            se = min(sb + W, pe)
+        w2 = bsub[j]
+        for sb in range(pb, pe, w2):
+            se = min(sb + w2, pe)
             for p in range(sb, se):
                 s = slice(p * NB, (p + 1) * NB)
                 L, Li, ld, inf_p = diag_block(A[s, s])
@@ -218,19 +250,45 @@ def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False):
                 if inf_p and not info:
                     info = p * NB + inf_p
                 rem = T - p - 1
-                if rem > 0:
-                    pan = A[(p + 1) * NB:, s]
-                    gemm_nt(0, pan, pan.copy(), Li, NB, rem, 1)
+                inner = se - p - 1
+                if not split or inner == 0 or rem < 2:
+                    if rem > 0:
+                        pan = A[(p + 1) * NB:, s]
+                        gemm_nt(0, pan, pan.copy(), Li, NB, rem, 1)
+                    if inner > 0:
+                        pan = A[(p + 1) * NB:, s]
+                        gemm_nt(1, A[(p + 1) * NB:, (p + 1) * NB:], pan, pan, NB, rem, inner, tri=1)
+                else:
+                    # head (panel stream): tile (p+1,p) solved, tile (p+1,p+1) updated
+                    h = slice((p + 1) * NB, (p + 2) * NB)
+                    gemm_nt(0, A[h, s], A[h, s].copy(), Li, NB, 1, 1)
+                    gemm_nt(1, A[h, h], A[h, s], A[h, s], NB, 1, 1, tri=1)
+                    # tail (s_tail): rows p+2.. solved; column p+1 below its diagonal tile; columns p+2..se-1
+                    t0 = (p + 2) * NB
+                    pan = A[t0:, s]
+                    gemm_nt(0, pan, pan.copy(), Li, NB, rem - 1, 1)
+                    gemm_nt(1, A[t0:, h], pan, A[h, s], NB, rem - 1, 1)
+                    if inner > 1:
+                        gemm_nt(1, A[t0:, t0:], pan, pan, NB, rem - 1, inner - 1, tri=1)
                 if b is not None:
                     trsv_fwd(A, Dinv, b, z, p, T)
-                inner = se - p - 1
-                if inner > 0:
-                    pan = A[(p + 1) * NB:, s]
-                    gemm_nt(1, A[(p + 1) * NB:, (p + 1) * NB:], pan, pan, NB, rem, inner, tri=1)
             if se < pe:
                 update(se, pe, sb, se)          # level-2: the rest of the block's columns
-        if T - pe > 0:
-            update(pe, T, pb, pe)               # level-1: the whole trailing matrix (device: next block's columns first)
+        rem = T - pe
+        if rem > 0:
+            head_l1 = split and not bbig[j]
+            if head_l1:
+                # the next diagonal tile is updated on the panel stream; the level-1 update leaves it alone
+                h = slice(pe * NB, (pe + 1) * NB)
+                pan0 = A[h, pb * NB:pe * NB]
+                saved = A[h, h].copy()
+                gemm_nt(1, A[h, h], pan0, pan0, (pe - pb) * NB, 1, 1, tri=1)
+                mine = A[h, h].copy()
+                A[h, h] = saved
+                update(pe, T, pb, pe)
+                A[h, h] = mine                  # (device: oz_syrk skip00 / the split DMMA launches never touch the tile)
+            else:
+                update(pe, T, pb, pe)           # level-1: the whole trailing matrix (device: next block's columns first)
     return Dinv, parts, info, z
 
 

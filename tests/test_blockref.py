@@ -143,3 +143,41 @@ def test_update_tile_rasterisation_covers_each_tile_once(nt, jb0, jb1):
     got = [br.oz_decode(i, nt, jb0, jb1) for i in range(n)]
     want = {(ti, tj) for jb in range(jb0, jb1) for ti in range(jb, nt) for tj in (2 * jb, 2 * jb + 1)}
     assert len(set(got)) == n and set(got) == want
+
+
+def test_ldl_block_with_newton_reciprocal_matches_cholesky():
+    """The 32x32 sub-block factorisation of potrf_diag_kernel (square-root-free elimination, 20-bit reciprocal seed + one
+    cubic Newton step, square roots at the end) against LAPACK, also on a badly scaled block."""
+    rng = np.random.default_rng(5)
+    for scale in (1.0, 1e-8, 1e8):
+        B = rng.standard_normal((32, 40))
+        A = (B @ B.T + 0.5 * np.eye(32)) * scale
+        L, lg, bad = br.ldl_block(A)
+        Lref = np.linalg.cholesky(A)
+        assert bad == 0
+        assert np.max(np.abs(L - Lref)) <= 1e-13 * np.max(np.abs(Lref))
+        assert abs(lg - np.log(np.diag(Lref)).sum()) <= 1e-12 * max(1.0, abs(lg))
+    x = rng.uniform(1e-3, 1e3, size=1000)
+    assert np.max(np.abs(br.rcp_newton(x) * x - 1.0)) < 2.0 ** -50
+
+
+def test_ldl_block_flags_first_bad_pivot():
+    A = np.eye(32)
+    A[7, 7] = -1.0
+    assert br.ldl_block(A)[2] == 8
+
+
+@pytest.mark.parametrize("n,W,W1,W2B", [(1536, 3, 0, None), (2048, 3, 9, 4), (1280, 2, 4, 3)])
+def test_split_panel_chain_and_head_update_give_the_same_factor(n, W, W1, W2B):
+    """The split panel chain (head on the panel stream, tail one panel behind) and the head of the level-1 hand-over
+    touch every tile exactly once: same factor as the unsplit order, and as LAPACK."""
+    A0 = _spd(n, seed=3)
+    Ls = []
+    for split in (False, True):
+        A = br.pad_spd(A0)
+        Dinv, parts, info, _ = br.potrf_device(A, W=W, W1=W1, w1_minrem=2, split=split, W2B=W2B)
+        assert info == 0
+        Ls.append(np.tril(A[:n, :n]))
+    Lref = np.linalg.cholesky(A0)
+    assert np.max(np.abs(Ls[1] - Lref)) <= 1e-11 * np.max(np.abs(Lref))
+    assert np.max(np.abs(Ls[1] - Ls[0])) <= 1e-12 * np.max(np.abs(Lref))
