@@ -455,6 +455,40 @@ int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int
   return 0;
 }
 
+// The same U = L^-T with the O(N^3) part on the int8 tensor cores: column blocks of WB panels are finished with the DMMA
+// sweep above (restricted to the block), then ALL later columns get one update of contraction length WB*128,
+//   U[0:ke, ke:] -= U[0:ke, kb:ke] * L[ke:, kb:ke]',
+// computed by the sliced SYRK kernel on the two operands stacked as [L rows; U rows] (launch_oz_gemm_stacked).
+int inverse_factor_T_oz(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv) {
+  const int T = (int)(np / NB);
+  const int WB = 8;
+  GPK_TRY(oz_ensure(h, 0, np, WB * NB));
+  GPK_TRY(launch_set_identity(h, st, U, np, np, np));
+  for (int kb = 0; kb < T; kb += WB) {
+    const int ke = (kb + WB < T) ? kb + WB : T;
+    for (int k = kb; k < ke; ++k) {
+      GemmArgs t{};
+      t.A = U + (int64_t)k * NB * np; t.B = Dinv + (int64_t)k * NB * NB; t.C = U + (int64_t)k * NB * np;
+      t.lda = np; t.ldb = NB; t.ldc = np; t.K = NB; t.tri = 0;
+      GPK_TRY(launch_gemm_nt(h, st, 0, t, k + 1, 1));
+      if (k + 1 < ke) {
+        GemmArgs u{};
+        u.A = U + (int64_t)k * NB * np; u.B = A + (int64_t)(k + 1) * NB + (int64_t)k * NB * np;
+        u.C = U + (int64_t)(k + 1) * NB * np;
+        u.lda = np; u.ldb = np; u.ldc = np; u.K = NB; u.tri = 0;
+        GPK_TRY(launch_gemm_nt(h, st, 1, u, k + 1, ke - k - 1));
+      }
+    }
+    if (ke < T) {
+      const int nb = (T - ke) * NB, na = ke * NB, kw = (ke - kb) * NB;
+      GPK_TRY(launch_oz_slice(h, 0, st, A + (int64_t)ke * NB + (int64_t)kb * NB * np, np, nb, kw, 0, nb + na));
+      GPK_TRY(launch_oz_slice(h, 0, st, U + (int64_t)kb * NB * np, np, na, kw, nb, nb + na));
+      GPK_TRY(launch_oz_gemm_stacked(h, 0, st, U + (int64_t)ke * NB * np, np, nb, na, kw));
+    }
+  }
+  return 0;
+}
+
 }  // namespace gpk
 
 using namespace gpk;
@@ -632,11 +666,21 @@ int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int
     const int64_t g = (n + 63) / 64;
     const int64_t part_need = g * g * 34;
     GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, part_need));
-    GPK_TRY(inverse_factor_T(h, st, h->dU, h->dA, np, h->dDinv));
-    GemmArgs v{};
-    v.A = h->dU; v.B = h->dU; v.C = h->dW; v.lda = np; v.ldb = np; v.ldc = np;
-    v.K = (int)np; v.tri = 2;
-    GPK_TRY(launch_gemm_nt(h, st, 0, v, T, T));
+    // (K/sn2+I)^-1 = U U' with U = L^-T.  Both O(N^3) products run on the int8 tensor cores when the matrix is large
+    // enough for it to pay and the int32 accumulators cannot overflow (7 N 2^14 < 2^31); else on DMMA.
+    const bool der_oz = env_int("GPK_OZAKI", 1) && env_int("GPK_OZAKI_DER", 1) && T >= 16 && np < 18432;
+    if (der_oz) {
+      GPK_TRY(inverse_factor_T_oz(h, st, h->dU, h->dA, np, h->dDinv));
+      GPK_TRY(oz_ensure(h, 1, np, (int)np));
+      GPK_TRY(launch_oz_slice(h, 1, st, h->dU, np, (int)np, (int)np));
+      GPK_TRY(launch_oz_ex(h, 1, st, h->dW, np, (int)np, (int)np, 0, T, 0, 0, /*trap*/ 1, /*set*/ 1));
+    } else {
+      GPK_TRY(inverse_factor_T(h, st, h->dU, h->dA, np, h->dDinv));
+      GemmArgs v{};
+      v.A = h->dU; v.B = h->dU; v.C = h->dW; v.lda = np; v.ldb = np; v.ldc = np;
+      v.K = (int)np; v.tri = 2;
+      GPK_TRY(launch_gemm_nt(h, st, 0, v, T, T));
+    }
     GPK_TRY(launch_dnlz(h, st, h->dXs, n, D, h->dW, np, h->dAlpha, 1.0 / sn2, sf2, kind, matern_d, h->dTmp,
                         h->capTmp, res + 8));
   }

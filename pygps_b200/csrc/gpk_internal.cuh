@@ -181,7 +181,11 @@ int diag_init(Handle* h);
 
 int ensure(Handle* h, double** p, int64_t* cap, int64_t need_elems);
 int oz_ensure(Handle* h, int which, int64_t n, int kw);
-int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw);
+int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw, int row0 = 0,
+                    int ntot = 0);
+int launch_oz_ex(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
+                 int skip00, int ti_min, int trap, int set);
+int launch_oz_gemm_stacked(Handle* h, int which, cudaStream_t st, double* Cab, int64_t ldc, int nb, int na, int kw);
 int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
                    int skip00 = 0);
 int dist_allreduce_sum(Handle* h, double* buf, size_t count, cudaStream_t st);

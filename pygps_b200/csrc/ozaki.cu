@@ -68,7 +68,8 @@ __device__ __forceinline__ unsigned long long oz_digits(double x) {
 // tensor core's canonical order so that the CTA's output per k-step (4 row groups x S x 256 B) is contiguous.
 template <int S, int RB>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t lda, int n, int kw,
-                                                        double* __restrict__ sc, int8_t* __restrict__ sl) {
+                                                        double* __restrict__ sc, int8_t* __restrict__ sl, int row0) {
+  // n: rows of the whole slice buffer (k-step stride); this launch fills rows [row0, row0 + 32*gridDim.x) from P
   __shared__ __align__(16) int8_t out[4][S][2][8][16];
   __shared__ double red[8][32];
   __shared__ int sh_e[32];
@@ -91,12 +92,12 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     }
     if (e < -500) e = -500;
     sh_e[r] = e;
-    sc[r0 + r] = scalbn(1.0, e - RB);
+    sc[row0 + r0 + r] = scalbn(1.0, e - RB);
   }
   __syncthreads();
   const int e = sh_e[r];
   const size_t kstride = (size_t)n * S * 32;
-  int4* dst4 = reinterpret_cast<int4*>(sl + (size_t)r0 * S * 32);
+  int4* dst4 = reinterpret_cast<int4*>(sl + (size_t)(row0 + r0) * S * 32);
   const int4* src4 = reinterpret_cast<const int4*>(&out[0][0][0][0][0]);
   uint32_t* out32 = reinterpret_cast<uint32_t*>(&out[0][0][0][0][0]);
   // this thread: row r, the four k positions 4*kq .. 4*kq+3 of every k-step -> one 32-bit word per slice
@@ -129,6 +130,9 @@ struct OzArgs {
   int ntiles;         // lower-triangle 128x64 tiles of this launch
   int tpc;            // tiles per CTA
   int skip00;         // leave the first diagonal tile (rows/cols 0..127) alone: the panel stream updates it itself
+  int ti_min;         // only row tiles >= ti_min (rectangular products: operand rows stacked [B; A], see launch_oz_gemm)
+  int trap;           // contraction of row tile ti starts at k = 128*ti (U U' of an upper-triangular U)
+  int set;            // 1: C = +P P' (C is not read) instead of C -= P P'   (pipelined epilogue only)
   long long* dbg;     // optional per-CTA clock stamps [5] (debug timing), else nullptr
 };
 
@@ -138,8 +142,8 @@ struct OzArgs {
 // tiles of a band stay in L2 for the whole band; every B tile is fetched from HBM once per band instead of once
 // per column block (ncu: 6.6 GB of DRAM reads per update with the column-major order, against 0.9 GB of C).
 constexpr int OZ_BAND = 16;
-__device__ __forceinline__ void oz_decode(int idx, int nt, int jb0, int jb1, int& ti, int& tj) {
-  int r_lo = jb0;
+__device__ __forceinline__ void oz_decode(int idx, int nt, int jb0, int jb1, int ti_min, int& ti, int& tj) {
+  int r_lo = max(jb0, ti_min);
   for (;;) {
     const int r_hi = min(r_lo + OZ_BAND, nt), rows = r_hi - r_lo;
     const int nfull = max(min(jb1, r_lo + 1) - jb0, 0);        // column blocks that see all rows of the band
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
   const int tile1 = min(tile0 + a.tpc, a.ntiles);
   if (a.skip00) {                                          // (host guarantees tpc == 1 with skip00)
     int ti0, tj0;
-    oz_decode(tile0, nt, a.jb0, a.jb1, ti0, tj0);
+    oz_decode(tile0, nt, a.jb0, a.jb1, a.ti_min, ti0, tj0);
     if (ti0 == 0 && tj0 < 2) return;
   }
 
@@ -199,15 +203,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       if (tile0 < tile1) {
         int ti, tj;
-        oz_decode(tile0, nt, a.jb0, a.jb1, ti, tj);
+        oz_decode(tile0, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
         const int8_t* gA = a.sl + (size_t)ti * 128 * S * 32;
         const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
+        const int ks0 = a.trap ? 4 * ti : 0;             // (the last row tile still has nk - ks0 = 4 = OZ_ST k-steps)
 #pragma unroll
         for (int ks = 0; ks < OZ_ST; ++ks) {
           mbar_expect_tx(&full[ks], STAGE);
           uint8_t* sdst = sm + (size_t)ks * STAGE;
-          bulk_g2s(sdst, gA + ks * kstride, A_BYTES, &full[ks]);
-          bulk_g2s(sdst + A_BYTES, gB + ks * kstride, B_BYTES, &full[ks]);
+          bulk_g2s(sdst, gA + (ks0 + ks) * kstride, A_BYTES, &full[ks]);
+          bulk_g2s(sdst + A_BYTES, gB + (ks0 + ks) * kstride, B_BYTES, &full[ks]);
         }
       }
     }
@@ -229,10 +234,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
       int it = 0;
       for (int tile = tile0; tile < tile1; ++tile) {
         int ti, tj;
-        oz_decode(tile, nt, a.jb0, a.jb1, ti, tj);
+        oz_decode(tile, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
         const int8_t* gA = a.sl + (size_t)ti * 128 * S * 32;
         const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
-        for (int ks = 0; ks < nk; ++ks, ++it) {
+        for (int ks = a.trap ? 4 * ti : 0; ks < nk; ++ks, ++it) {
           const int slot = it % OZ_ST;
           if (it < OZ_ST) continue;                      // requested before the CTA barrier (see above)
           mbar_wait(&empty[slot], ((it / OZ_ST) - 1) & 1);
@@ -251,6 +256,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
       int it = 0, tcount = 0;
       for (int tile = tile0; tile < tile1; ++tile, ++tcount) {
         if (tcount > 0) { mbar_wait(&tfree, (tcount - 1) & 1); tc_fence_after(); }
+        int ks0 = 0;
+        if (a.trap) {
+          int ti, tj;
+          oz_decode(tile, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
+          ks0 = 4 * ti;
+        }
         if constexpr (ATMEM) {
           // The A slices go shared memory -> TMEM once per k-step (tcgen05.cp) and every product reads them from
           // there: shared-memory traffic per k-step drops from S(S+1)/2 x 6 KB to S x 4 KB + S(S+1)/2 x 2 KB, which
@@ -267,7 +278,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
 #pragma unroll
             for (int t = 0; t < S; ++t) tc_cp_128x256b(ta + 8 * t, da + 16 * t);
           }
-          for (int ks = 0; ks < nk; ++ks, ++it) {
+          for (int ks = ks0; ks < nk; ++ks, ++it) {
             const int slot = it % OZ_ST, nslot = (it + 1) % OZ_ST;
             const bool more = ks + 1 < nk;
             const uint64_t db = dbase | (uint64_t)((smem_u32(sm + (size_t)slot * STAGE) + A_BYTES) >> 4);
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
             for (int t = 0; t < S; ++t) {
 #pragma unroll
               for (int u = 0; u < S - t; ++u)
-                tc_mma_i8_ts(tbase + (uint32_t)(t + u) * OZ_BN, ta + 8 * t, db + 16 * u, idesc, (ks > 0 || t > 0) ? 1u : 0u);
+                tc_mma_i8_ts(tbase + (uint32_t)(t + u) * OZ_BN, ta + 8 * t, db + 16 * u, idesc, (ks > ks0 || t > 0) ? 1u : 0u);
               if (more) {
                 if (t == 0) { mbar_wait(&full[nslot], ((it + 1) / OZ_ST) & 1); tc_fence_after(); }
                 tc_cp_128x256b(ta + 8 * t, dan + 16 * t);
@@ -285,7 +296,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
             tc_commit(&empty[slot]);
           }
         } else {
-          for (int ks = 0; ks < nk; ++ks, ++it) {
+          for (int ks = ks0; ks < nk; ++ks, ++it) {
             const int slot = it % OZ_ST;
             mbar_wait(&full[slot], (it / OZ_ST) & 1);
             tc_fence_after();
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
             for (int t = 0; t < S; ++t) {
 #pragma unroll
               for (int u = 0; u < S - t; ++u)
-                tc_mma_i8(tbase + (uint32_t)(t + u) * OZ_BN, da + 16 * t, db + 16 * u, idesc, (ks > 0 || t > 0) ? 1u : 0u);
+                tc_mma_i8(tbase + (uint32_t)(t + u) * OZ_BN, da + 16 * t, db + 16 * u, idesc, (ks > ks0 || t > 0) ? 1u : 0u);
             }
             tc_commit(&empty[slot]);
           }
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
     int tcount = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++tcount) {
       int ti, tj;
-      oz_decode(tile, nt, a.jb0, a.jb1, ti, tj);
+      oz_decode(tile, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
       const int gi = ti * 128 + q4 * 32 + lane, gj0 = tj * OZ_BN + chalf;
       const double si = a.sc[gi];
       double* crow = a.C + gi + (int64_t)gj0 * a.ldc;
@@ -361,13 +372,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
         // load of the first column scale of every round)
         if (tid < OZ_BN) sjs[tid] = a.sc[tj * OZ_BN + tid];
         asm volatile("bar.sync 1, %0;\n" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+        const bool rd = (a.set == 0);                    // C is read (update) or only written (set)
+        const double sg = rd ? 1.0 : -1.0;
+        if (rd) {
 #pragma unroll
-        for (int q = 0; q < OZ_BN / 2; ++q)
-          if (gi >= gj0 + q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + (int64_t)q * a.ldc));
+          for (int q = 0; q < OZ_BN / 2; ++q)
+            if (gi >= gj0 + q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(crow + (int64_t)q * a.ldc));
+        }
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) cvb[r][q] = (gi >= gj0 + 4 * r + q) ? crow[(int64_t)(4 * r + q) * a.ldc] : 0.0;
+          for (int q = 0; q < 4; ++q) cvb[r][q] = (rd && gi >= gj0 + 4 * r + q) ? crow[(int64_t)(4 * r + q) * a.ldc] : 0.0;
         mbar_wait(&done, tcount & 1);
         tc_fence_after();
         if (dbg && tid == 0) dbg[3] = clock64();
@@ -386,7 +401,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
           if (r + 2 < NR) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              cvb[(r + 2) % 3][q] = (gi >= gj0 + 4 * (r + 2) + q) ? crow[(int64_t)(4 * (r + 2) + q) * a.ldc] : 0.0;
+              cvb[(r + 2) % 3][q] = (rd && gi >= gj0 + 4 * (r + 2) + q) ? crow[(int64_t)(4 * (r + 2) + q) * a.ldc] : 0.0;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -395,7 +410,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
 #pragma unroll
             for (int m = S - 2; m >= 0; --m)
               acc = fma(acc, HORNER, __hiloint2double(0x43300000, (int)(v[r & 1][m][q] ^ 0x80000000u)) - 4503601774854144.0);
-            if (gi >= gj0 + c) crow[(int64_t)c * a.ldc] = cvb[r % 3][q] - (acc * si) * sjs[chalf + c];
+            if (gi >= gj0 + c) crow[(int64_t)c * a.ldc] = cvb[r % 3][q] - sg * ((acc * si) * sjs[chalf + c]);
           }
         }
       }
@@ -441,18 +456,25 @@ int oz_ensure(Handle* h, int which, int64_t n, int kw) {
 }
 
 template <int S, int RB>
-static int oz_slice_t(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw) {
-  oz_slice_kernel<S, RB><<<n / 32, 256, 0, st>>>(P, lda, n, kw, h->ozSc[which], h->ozSl[which]);
+static int oz_slice_t(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw, int row0,
+                      int ntot) {
+  oz_slice_kernel<S, RB><<<n / 32, 256, 0, st>>>(P, lda, ntot, kw, h->ozSc[which], h->ozSl[which], row0);
   GPK_CK(h, cudaGetLastError());
   return 0;
 }
 
 // slice the panel P (n rows x kw columns, column-major, lda) into h->ozSl / h->ozSc
-int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw) {
-  if (n % 128 != 0 || kw % 32 != 0 || (size_t)n * kw * 8 > h->ozCap[which]) return GPK_ERR_ARG;
+// rows [row0, row0+n) of a slice buffer of ntot rows (0: n) <- P (n rows x kw columns, column-major, lda)
+int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw, int row0,
+                    int ntot) {
+  if (ntot <= 0) ntot = n;
+  if (n % 128 != 0 || kw % 32 != 0 || row0 % 128 != 0 || row0 + n > ntot || (size_t)ntot * kw * 8 > h->ozCap[which] ||
+      (size_t)ntot > h->ozScCap[which])
+    return GPK_ERR_ARG;
   const OzCfg c = oz_cfg();
-  if (c.RB == 7) return c.S == 8 ? oz_slice_t<8, 7>(h, which, st, P, lda, n, kw) : oz_slice_t<7, 7>(h, which, st, P, lda, n, kw);
-  return c.S == 7 ? oz_slice_t<7, 8>(h, which, st, P, lda, n, kw) : oz_slice_t<6, 8>(h, which, st, P, lda, n, kw);
+  if (c.RB == 7)
+    return c.S == 8 ? oz_slice_t<8, 7>(h, which, st, P, lda, n, kw, row0, ntot) : oz_slice_t<7, 7>(h, which, st, P, lda, n, kw, row0, ntot);
+  return c.S == 7 ? oz_slice_t<7, 8>(h, which, st, P, lda, n, kw, row0, ntot) : oz_slice_t<6, 8>(h, which, st, P, lda, n, kw, row0, ntot);
 }
 
 template <int S, int RB, int EPI>
@@ -474,16 +496,37 @@ static int oz_syrk_t(Handle* h, cudaStream_t st, const OzArgs& a) {
 }
 
 // C(lower triangle, 128-column blocks [jb0, jb1)) -= P·P' from the current slices
-int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
-                   int skip00) {
+// General form: tiles {jb0 <= jb < jb1, ti >= max(jb, ti_min)} of C(stacked row, stacked column) (-)= P P' from the current
+// slices (n rows).  trap: the contraction of row tile ti starts at k = 128 ti.  set: C = +P P' instead of C -= P P'.
+int launch_oz_ex(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
+                 int skip00, int ti_min, int trap, int set) {
   const OzCfg c = oz_cfg();
   const int nt = n / 128;
-  if (jb0 < 0 || jb1 > nt || jb0 >= jb1) return GPK_ERR_ARG;
-  const int ntiles = 2 * nt * (jb1 - jb0) - (jb1 * (jb1 - 1) - jb0 * (jb0 - 1));
-  if (skip00 && (c.tpc != 1 || jb0 != 0)) return GPK_ERR_ARG;
-  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, skip00, h->ozDbg};
+  if (jb0 < 0 || jb1 > nt || jb0 >= jb1 || ti_min < 0 || ti_min >= nt) return GPK_ERR_ARG;
+  if (skip00 && (c.tpc != 1 || jb0 != 0 || ti_min != 0)) return GPK_ERR_ARG;
+  if (trap && (kw != n || jb0 != 0 || ti_min != 0)) return GPK_ERR_ARG;
+  if (set && !c.epi) return GPK_ERR_ARG;                                 // only the pipelined epilogue knows "set"
+  if ((size_t)kw * 7 * 16384 >= 2147483648ull) return GPK_ERR_ARG;      // int32 accumulators: 7 kw 2^14 < 2^31
+  long long nt64 = 0;
+  for (int jb = jb0; jb < jb1; ++jb) nt64 += 2 * (nt - (jb > ti_min ? jb : ti_min));
+  const int ntiles = (int)nt64;
+  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, skip00, ti_min, trap, set, h->ozDbg};
   if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
   return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
+}
+
+// C(lower triangle, 128-column blocks [jb0, jb1)) -= P·P' from the current slices
+int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
+                   int skip00) {
+  return launch_oz_ex(h, which, st, C, ldc, n, kw, jb0, jb1, skip00, 0, 0, 0);
+}
+
+// C(rows of A, rows of B) -= A·B' for two operands sliced into ONE buffer as [B (nb rows); A (na rows)]: in stacked
+// indices every wanted tile lies below the diagonal, so the SYRK kernel computes exactly the nb x na rectangle.
+// Cab points at the entry (first A row, first B row) of the target, column-major with pitch ldc.
+int launch_oz_gemm_stacked(Handle* h, int which, cudaStream_t st, double* Cab, int64_t ldc, int nb, int na, int kw) {
+  if (nb % 128 != 0 || na % 128 != 0 || nb <= 0 || na <= 0) return GPK_ERR_ARG;
+  return launch_oz_ex(h, which, st, Cab - nb, ldc, nb + na, kw, 0, nb / 128, 0, nb / 128, 0, 0);
 }
 
 }  // namespace gpk
