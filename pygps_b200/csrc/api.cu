@@ -55,10 +55,6 @@ static int ensure_prof_events(Handle* h, size_t count) {
 // ---------------------------------------------------------------------------
 static int g_potrf_w = 0;   // 0: choose from the problem size (measured on B200: 3 panels at T>64, else 2)
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 
 int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info, double* b_fwd,
                  double* z_out, const CovArgs* lazy_cov) {
@@ -450,6 +446,43 @@ int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int
       u.C = U + (int64_t)(k + 1) * NB * np;
       u.lda = np; u.ldb = np; u.ldc = np; u.K = NB; u.tri = 0;
       GPK_TRY(launch_gemm_nt(h, st, 1, u, k + 1, T - k - 1));
+    }
+  }
+  return 0;
+}
+
+// sweep_forward with the O(M^2 n) part on the int8 tensor cores: column blocks of WB panels are finished with the DMMA
+// sweep restricted to the block, then ALL later columns get one update of contraction length WB*128,
+//   P[:, ke:] -= P[:, kb:ke] * L[ke:, kb:ke]',   operands stacked as [L rows; P rows] (launch_oz_gemm_stacked).
+int sweep_forward_oz(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A, int64_t lda,
+                     const double* Dinv, int T) {
+  // block width: the in-block DMMA share of the work is ~WB/T, the int8 update wants a long contraction
+  int WB = env_int("GPK_SWEEP_WB", T <= 48 ? 4 : 8);
+  if (WB < 1) WB = 1;
+  if (WB > 16) WB = 16;
+  const int na = row_tiles * NB;
+  if (T <= WB) return sweep_forward(h, st, P, ldp, row_tiles, A, lda, Dinv, T);
+  GPK_TRY(oz_ensure(h, 0, (int64_t)(T - WB) * NB + na, WB * NB));
+  for (int kb = 0; kb < T; kb += WB) {
+    const int ke = (kb + WB < T) ? kb + WB : T;
+    for (int k = kb; k < ke; ++k) {
+      GemmArgs t{};
+      t.A = P + (int64_t)k * NB * ldp; t.B = Dinv + (int64_t)k * NB * NB; t.C = P + (int64_t)k * NB * ldp;
+      t.lda = ldp; t.ldb = NB; t.ldc = ldp; t.K = NB; t.tri = 0;
+      GPK_TRY(launch_gemm_nt(h, st, 0, t, row_tiles, 1));
+      if (k + 1 < ke) {
+        GemmArgs u{};
+        u.A = P + (int64_t)k * NB * ldp; u.B = A + (int64_t)(k + 1) * NB + (int64_t)k * NB * lda;
+        u.C = P + (int64_t)(k + 1) * NB * ldp;
+        u.lda = ldp; u.ldb = lda; u.ldc = ldp; u.K = NB; u.tri = 0;
+        GPK_TRY(launch_gemm_nt(h, st, 1, u, row_tiles, ke - k - 1));
+      }
+    }
+    if (ke < T) {
+      const int nb = (T - ke) * NB, kw = (ke - kb) * NB;
+      GPK_TRY(launch_oz_slice(h, 0, st, A + (int64_t)ke * NB + (int64_t)kb * NB * lda, lda, nb, kw, 0, nb + na));
+      GPK_TRY(launch_oz_slice(h, 0, st, P + (int64_t)kb * NB * ldp, ldp, na, kw, nb, nb + na));
+      GPK_TRY(launch_oz_gemm_stacked(h, 0, st, P + (int64_t)ke * NB * ldp, ldp, nb, na, kw));
     }
   }
   return 0;

@@ -329,7 +329,11 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
   // 2. Luu
   GPK_TRY(potrf_device(h, h->fKuu, Mp, h->fDinvU, partsU, h->dInfo, nullptr, nullptr));
   // 3b. V = Luu^-1 Ku   as   Vt = Kut * Luu^-T                                   :413
-  GPK_TRY(sweep_forward(h, st, h->fVt, np, Tn, h->fKuu, Mp, h->fDinvU, Tm));
+  // Both O(M^2 n) products of the nlZ path run on the int8 tensor cores (error-free fp64 split, ozaki.cu) when there
+  // are enough inducing points for it to pay; GPK_OZAKI_FITC=0 keeps them on DMMA.
+  const bool fitc_oz = env_int("GPK_OZAKI", 1) && env_int("GPK_OZAKI_FITC", 1) && Tm >= 16;
+  if (fitc_oz) GPK_TRY(sweep_forward_oz(h, st, h->fVt, np, Tn, h->fKuu, Mp, h->fDinvU, Tm));
+  else GPK_TRY(sweep_forward(h, st, h->fVt, np, Tn, h->fKuu, Mp, h->fDinvU, Tm));
   // 4. g_sn2 = diagK + sn2 - colsum(V*V) ; r = (y-m)/sqrt(g)                      :415,418
   fitc_g_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(h->fVt, np, np, Mp, n, sf2 + sn2, h->dR, g, rs, r);
   // 5. Vs = diag(g^-1/2) V  (Mp x np)
@@ -338,7 +342,17 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
   const bool sharded = (h->world > 1 && h->nccl_comm);
   if (!sharded || h->rank == 0) GPK_TRY(launch_set_identity(h, st, h->fA2, Mp, Mp, Mp));
   else GPK_CK(h, cudaMemsetAsync(h->fA2, 0, (size_t)Mp * Mp * sizeof(double), st));
-  {
+  if (fitc_oz) {
+    // SYRK over the data points in chunks of 16384 (int32 accumulators: 7 * 16384 * 2^14 < 2^31); every chunk is
+    // sliced with its own row scales and added to A2 by the update kernel's epilogue
+    const int64_t KC = 16384;
+    GPK_TRY(oz_ensure(h, 0, Mp, (int)(np < KC ? np : KC)));
+    for (int64_t c0 = 0; c0 < np; c0 += KC) {
+      const int kw = (int)((np - c0 < KC) ? np - c0 : KC);
+      GPK_TRY(launch_oz_slice(h, 0, st, h->fVs + c0 * Mp, Mp, (int)Mp, kw));
+      GPK_TRY(launch_oz_ex(h, 0, st, h->fA2, Mp, (int)Mp, kw, 0, Tm, 0, 0, 0, /*C +=*/ 2));
+    }
+  } else {
     GemmArgs a{};
     a.A = h->fVs; a.B = h->fVs; a.C = h->fA2; a.lda = Mp; a.ldb = Mp; a.ldc = Mp; a.K = (int)np; a.tri = 1;
     GPK_TRY(launch_gemm_nt(h, st, 2, a, Tm, Tm));

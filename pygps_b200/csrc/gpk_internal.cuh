@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -24,6 +25,10 @@ constexpr int DIAG_LDT = DIAG_IB + 4;
 constexpr size_t DIAG_SMEM = (size_t(NB) * DIAG_LDS + 4 * DIAG_IB * DIAG_LDT + NB) * sizeof(double);
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+inline int env_int(const char* name, int dflt) {   // GPK_* switches for A/B measurements; read at every call
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 // ---- argument blocks ------------------------------------------------------
 // C(tile ti,tj) (+)= A(rows ti) * B(rows tj)^T ; all column-major, all tile-aligned.
@@ -184,7 +189,7 @@ int oz_ensure(Handle* h, int which, int64_t n, int kw);
 int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw, int row0 = 0,
                     int ntot = 0);
 int launch_oz_ex(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
-                 int skip00, int ti_min, int trap, int set);
+                 int skip00, int ti_min, int trap, int cmode /*0: C -= PP', 1: C = PP', 2: C += PP'*/);
 int launch_oz_gemm_stacked(Handle* h, int which, cudaStream_t st, double* Cab, int64_t ldc, int nb, int na, int kw);
 int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
                    int skip00 = 0);
@@ -196,6 +201,9 @@ int check_handle(gpk_handle hh, Handle** out);
 int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A, int64_t lda,
                   const double* Dinv, int T);
 int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv);
+int inverse_factor_T_oz(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv);
+int sweep_forward_oz(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A, int64_t lda,
+                     const double* Dinv, int T);
 int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info,
                  double* b_fwd /*nullable: fused forward solve in/out*/, double* z_out,
                  const CovArgs* lazy_cov = nullptr /*generate the matrix inside, overlapped with the first panels*/);

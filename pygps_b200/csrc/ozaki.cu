@@ -64,11 +64,36 @@ __device__ __forceinline__ unsigned long long oz_digits(double x) {
   }
 }
 
-// One CTA = 32 panel rows x the whole contraction length.  Pass 1: row exponent; pass 2: digits, written in the
-// tensor core's canonical order so that the CTA's output per k-step (4 row groups x S x 256 B) is contiguous.
+// Row maxima for the split-k slicing: grid (rows/32, ksplit), every CTA reduces its k-range and merges with an atomic
+// max on the bit pattern (non-negative doubles order like unsigned integers).  mx must be zero on entry.
+__global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict__ P, int64_t lda, int kw,
+                                                         unsigned long long* __restrict__ mx) {
+  __shared__ double red[8][32];
+  const int r0 = blockIdx.x * 32;
+  const int r = threadIdx.x & 31, kq = threadIdx.x >> 5;
+  const int per = ((kw / 32 + gridDim.y - 1) / gridDim.y) * 32;
+  const int kb = blockIdx.y * per, ke = min(kb + per, kw);
+  const double* prow = P + r0 + r;
+  double m = 0.0;
+#pragma unroll 4
+  for (int k = kb + kq; k < ke; k += 8) m = fmax(m, fabs(prow[(int64_t)k * lda]));
+  red[kq][r] = m;
+  __syncthreads();
+  if (kq == 0) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) m = fmax(m, red[q][r]);
+    if (!(m >= 0.0)) m = 0.0;                                // NaN rows keep the scale 1 (they stay NaN in the product)
+    atomicMax(mx + r0 + r, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+// One CTA = 32 panel rows x (a k-range of) the contraction length.  Pass 1: row exponent (from the CTA's own
+// reduction, or from mx when the k-range is split over gridDim.y CTAs); pass 2: digits, written in the tensor core's
+// canonical order so that the CTA's output per k-step (4 row groups x S x 256 B) is contiguous.
 template <int S, int RB>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t lda, int n, int kw,
-                                                        double* __restrict__ sc, int8_t* __restrict__ sl, int row0) {
+                                                        double* __restrict__ sc, int8_t* __restrict__ sl, int row0,
+                                                        const unsigned long long* __restrict__ mx) {
   // n: rows of the whole slice buffer (k-step stride); this launch fills rows [row0, row0 + 32*gridDim.x) from P
   __shared__ __align__(16) int8_t out[4][S][2][8][16];
   __shared__ double red[8][32];
@@ -77,13 +102,19 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   const int r = threadIdx.x & 31, kq = threadIdx.x >> 5;
   const double* prow = P + r0 + r;
   double m = 0.0;
+  if (mx == nullptr) {
 #pragma unroll 4
-  for (int k = kq; k < kw; k += 8) m = fmax(m, fabs(prow[(int64_t)k * lda]));
-  red[kq][r] = m;
-  __syncthreads();
+    for (int k = kq; k < kw; k += 8) m = fmax(m, fabs(prow[(int64_t)k * lda]));
+    red[kq][r] = m;
+    __syncthreads();
+  }
   if (kq == 0) {
+    if (mx == nullptr) {
 #pragma unroll
-    for (int q = 1; q < 8; ++q) m = fmax(m, red[q][r]);
+      for (int q = 1; q < 8; ++q) m = fmax(m, red[q][r]);
+    } else {
+      m = __longlong_as_double((long long)mx[r0 + r]);
+    }
     // |x| < 2^(ilogb+1)  ->  |x| * 2^-(ilogb+2) < 0.5 ; exponents clamped so that 2^(e-RB) stays a normal double
     int e = 0;
     if (m > 0.0 && m < 1.0e150) {
@@ -92,7 +123,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     }
     if (e < -500) e = -500;
     sh_e[r] = e;
-    sc[row0 + r0 + r] = scalbn(1.0, e - RB);
+    if (blockIdx.y == 0) sc[row0 + r0 + r] = scalbn(1.0, e - RB);
   }
   __syncthreads();
   const int e = sh_e[r];
@@ -102,7 +133,9 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   uint32_t* out32 = reinterpret_cast<uint32_t*>(&out[0][0][0][0][0]);
   // this thread: row r, the four k positions 4*kq .. 4*kq+3 of every k-step -> one 32-bit word per slice
   const int wbase = ((r >> 3) * S * 256 + ((4 * kq) >> 4) * 128 + (r & 7) * 16 + ((4 * kq) & 15)) >> 2;
-  for (int ks = 0; ks < kw / 32; ++ks) {
+  const int nsteps = kw / 32, per = (nsteps + gridDim.y - 1) / gridDim.y;
+  const int ks_b = blockIdx.y * per, ks_e = min(ks_b + per, nsteps);
+  for (int ks = ks_b; ks < ks_e; ++ks) {
     unsigned long long qq[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -132,7 +165,7 @@ struct OzArgs {
   int skip00;         // leave the first diagonal tile (rows/cols 0..127) alone: the panel stream updates it itself
   int ti_min;         // only row tiles >= ti_min (rectangular products: operand rows stacked [B; A], see launch_oz_gemm)
   int trap;           // contraction of row tile ti starts at k = 128*ti (U U' of an upper-triangular U)
-  int set;            // 1: C = +P P' (C is not read) instead of C -= P P'   (pipelined epilogue only)
+  int cmode;          // 0: C -= P P' ; 1: C = +P P' (C is not read) ; 2: C += P P'   (1, 2: pipelined epilogue only)
   long long* dbg;     // optional per-CTA clock stamps [5] (debug timing), else nullptr
 };
 
@@ -372,8 +405,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
         // load of the first column scale of every round)
         if (tid < OZ_BN) sjs[tid] = a.sc[tj * OZ_BN + tid];
         asm volatile("bar.sync 1, %0;\n" ::"n"(OZ_EPI_WARPS * 32) : "memory");
-        const bool rd = (a.set == 0);                    // C is read (update) or only written (set)
-        const double sg = rd ? 1.0 : -1.0;
+        const bool rd = (a.cmode != 1);                  // C is read (update) or only written (set)
+        const double sg = (a.cmode == 0) ? 1.0 : -1.0;
         if (rd) {
 #pragma unroll
           for (int q = 0; q < OZ_BN / 2; ++q)
@@ -449,7 +482,7 @@ int oz_ensure(Handle* h, int which, int64_t n, int kw) {
   if (h->ozScCap[which] < (size_t)n) {
     if (h->ozSc[which]) cudaFree(h->ozSc[which]);
     h->ozSc[which] = nullptr; h->ozScCap[which] = 0;
-    GPK_CK(h, cudaMalloc((void**)&h->ozSc[which], (size_t)n * sizeof(double)));
+    GPK_CK(h, cudaMalloc((void**)&h->ozSc[which], 2 * (size_t)n * sizeof(double)));   // scales, then row-max scratch
     h->ozScCap[which] = (size_t)n;
   }
   return 0;
@@ -458,12 +491,24 @@ int oz_ensure(Handle* h, int which, int64_t n, int kw) {
 template <int S, int RB>
 static int oz_slice_t(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw, int row0,
                       int ntot) {
-  oz_slice_kernel<S, RB><<<n / 32, 256, 0, st>>>(P, lda, ntot, kw, h->ozSc[which], h->ozSl[which], row0);
+  // Few rows and a long contraction (the FITC SYRK: 4096 x 16384; the Cholesky panels: ~15000 x 1152) would leave most
+  // SMs idle with one CTA per 32 rows: split the k-range over gridDim.y CTAs, with the row maxima from a pre-pass.
+  const int ctas = n / 32, nsteps = kw / 32;
+  int ksplit = (ctas >= 1184) ? 1 : (1184 + ctas - 1) / ctas;
+  if (ksplit > nsteps / 4) ksplit = nsteps / 4 > 0 ? nsteps / 4 : 1;
+  if (env_int("GPK_OZAKI_KSPLIT", 1) == 0) ksplit = 1;
+  if (ksplit <= 1) {
+    oz_slice_kernel<S, RB><<<ctas, 256, 0, st>>>(P, lda, ntot, kw, h->ozSc[which], h->ozSl[which], row0, nullptr);
+  } else {
+    unsigned long long* mx = reinterpret_cast<unsigned long long*>(h->ozSc[which] + h->ozScCap[which]);   // second half
+    GPK_CK(h, cudaMemsetAsync(mx, 0, (size_t)n * sizeof(unsigned long long), st));
+    oz_rowmax_kernel<<<dim3(ctas, ksplit), 256, 0, st>>>(P, lda, kw, mx);
+    oz_slice_kernel<S, RB><<<dim3(ctas, ksplit), 256, 0, st>>>(P, lda, ntot, kw, h->ozSc[which], h->ozSl[which], row0, mx);
+  }
   GPK_CK(h, cudaGetLastError());
   return 0;
 }
 
-// slice the panel P (n rows x kw columns, column-major, lda) into h->ozSl / h->ozSc
 // rows [row0, row0+n) of a slice buffer of ntot rows (0: n) <- P (n rows x kw columns, column-major, lda)
 int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw, int row0,
                     int ntot) {
@@ -497,20 +542,20 @@ static int oz_syrk_t(Handle* h, cudaStream_t st, const OzArgs& a) {
 
 // C(lower triangle, 128-column blocks [jb0, jb1)) -= P·P' from the current slices
 // General form: tiles {jb0 <= jb < jb1, ti >= max(jb, ti_min)} of C(stacked row, stacked column) (-)= P P' from the current
-// slices (n rows).  trap: the contraction of row tile ti starts at k = 128 ti.  set: C = +P P' instead of C -= P P'.
+// slices (n rows).  trap: the contraction of row tile ti starts at k = 128 ti.  cmode 1 / 2: C = / += P P'.
 int launch_oz_ex(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
-                 int skip00, int ti_min, int trap, int set) {
+                 int skip00, int ti_min, int trap, int cmode) {
   const OzCfg c = oz_cfg();
   const int nt = n / 128;
   if (jb0 < 0 || jb1 > nt || jb0 >= jb1 || ti_min < 0 || ti_min >= nt) return GPK_ERR_ARG;
   if (skip00 && (c.tpc != 1 || jb0 != 0 || ti_min != 0)) return GPK_ERR_ARG;
   if (trap && (kw != n || jb0 != 0 || ti_min != 0)) return GPK_ERR_ARG;
-  if (set && !c.epi) return GPK_ERR_ARG;                                 // only the pipelined epilogue knows "set"
+  if (cmode && !c.epi) return GPK_ERR_ARG;                               // only the pipelined epilogue knows set / add
   if ((size_t)kw * 7 * 16384 >= 2147483648ull) return GPK_ERR_ARG;      // int32 accumulators: 7 kw 2^14 < 2^31
   long long nt64 = 0;
   for (int jb = jb0; jb < jb1; ++jb) nt64 += 2 * (nt - (jb > ti_min ? jb : ti_min));
   const int ntiles = (int)nt64;
-  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, skip00, ti_min, trap, set, h->ozDbg};
+  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, skip00, ti_min, trap, cmode, h->ozDbg};
   if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
   return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
 }

@@ -495,12 +495,10 @@ __global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_bwd_persistent_kernel(
 
 int launch_trsv_bwd_all(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* z,
                         double* x, int T) {
-  static int persist = -1, sms = 0;
-  if (persist < 0) {
-    const char* e = getenv("GPK_TRSV_PERSIST");
-    persist = e ? atoi(e) : 1;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  }
+  static int sms = 0;
+  if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const char* e = getenv("GPK_TRSV_PERSIST");            // 0: one launch per block step (A/B runs, tests)
+  const int persist = e ? atoi(e) : 1;
   if (!persist || T > sms || T < 2) {
     for (int k = T - 1; k >= 0; --k) GPK_TRY(launch_trsv_bwd(h, st, A, lda, Dinv, z, x, k, T));
     return 0;

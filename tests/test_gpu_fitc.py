@@ -85,3 +85,26 @@ def test_fitc_shape_contract_of_the_reference():
     assert type(nlZ) is np.float64 and all(type(v) is np.float64 for v in dnlZ.cov + dnlZ.lik)
     with pytest.raises(Exception):
         pg.inf.FITC_Exact().evaluate(pg.mean.Zero(), pg.cov.RBF(), pg.lik.Gauss(), x, y, nargout=2)
+
+
+def test_int8_and_dmma_fitc_products_agree(monkeypatch):
+    """The two O(M^2 n) products of the FITC nlZ path (V = Luu^-1 Ku as a blocked sweep through the stacked-operand
+    sliced GEMM; A2 = I + V G^-1 V' as a chunked sliced SYRK) on the int8 tensor cores (default for M >= 2048) against
+    the fp64 DMMA path (GPK_OZAKI_FITC=0): nlZ, alpha, post.L, dnlZ."""
+    import math
+    from pygps_b200 import _lib
+    rng = np.random.default_rng(21)
+    N, M, D = 20000, 2100, 6                       # Mp = 2176 = 17 panels (ragged blocks of 8), two SYRK chunks
+    X = rng.standard_normal((N, D))
+    y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    U = rng.standard_normal((M, D))
+    eng = _lib.Engine(0)
+    eng.set_data(X)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GPK_OZAKI_FITC", mode)
+        res[mode] = eng.fitc_eval(_lib.COV_RBF, 3, [math.log(1.8), 0.1], math.log(0.2), U, y, True)
+    a, b = res["1"], res["0"]
+    assert abs(a[0] - b[0]) <= 1e-10 * abs(b[0]), (a[0], b[0])
+    assert rel(a[1], b[1]) < 1e-6 and rel(a[2], b[2]) < 1e-6
+    assert rel(a[3], b[3]) < 1e-6 and rel(a[4], b[4]) < 1e-6

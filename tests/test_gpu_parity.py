@@ -288,3 +288,48 @@ def test_int8_tensor_core_and_dmma_updates_agree(monkeypatch):
         res[oz] = (out[0], np.array(out[1]))
     assert abs(res["1"][0] - res["0"][0]) <= 1e-11 * abs(res["0"][0])
     assert np.max(np.abs(res["1"][1] - res["0"][1])) <= 1e-8 * np.max(np.abs(res["0"][1]))
+
+
+def test_int8_and_dmma_derivative_paths_agree(monkeypatch):
+    """dnlZ with (K/sn2+I)^-1 = U U' on the int8 tensor cores (blocked L^-T through the stacked-operand sliced GEMM,
+    U U' as a trapezoid sliced SYRK; default) and on fp64 DMMA (GPK_OZAKI_DER=0), at a size whose column blocks are
+    ragged (T = 41 panels, blocks of 8), with an ARD kernel (10 hyper-parameters)."""
+    import math
+    from pygps_b200 import _lib
+    rng = np.random.default_rng(12)
+    N, D = 5200, 9
+    X = rng.standard_normal((N, D))
+    y = np.sin(X[:, :3].sum(1)) + 0.1 * rng.standard_normal(N)
+    hyp = [math.log(2.5)] * D + [0.1]
+    eng = _lib.Engine(0)
+    eng.set_data(X)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GPK_OZAKI_DER", mode)
+        out = eng.exact_eval(_lib.COV_RBFARD, 3, hyp, math.log(0.2), y, True)
+        res[mode] = (out[0], np.array(out[2]), np.array(out[3]))
+    assert res["1"][0] == res["0"][0]                       # the factorisation itself is the same code
+    scale = np.max(np.abs(res["0"][1]))
+    assert np.max(np.abs(res["1"][1] - res["0"][1])) <= 1e-10 * scale
+    assert abs(res["1"][2][0] - res["0"][2][0]) <= 1e-10 * abs(res["0"][2][0])
+
+
+@pytest.mark.parametrize("env", [{"GPK_POTRF_SPLIT": "0"}, {"GPK_POTRF_HEADL1": "0"}, {"GPK_LAZY_COV": "0"},
+                                 {"GPK_POTRF_W2B": "6", "GPK_POTRF_W1": "6"}, {"GPK_TRSV_PERSIST": "0"}])
+def test_schedule_variants_give_the_same_evaluation(monkeypatch, env):
+    """The split panel chain, the head of the level-1 hand-over, the overlapped matrix build and the blocking widths only
+    reorder independent work: nlZ and alpha agree with the default schedule to rounding."""
+    import math
+    from pygps_b200 import _lib
+    rng = np.random.default_rng(13)
+    N = 9000                                               # T = 71 panels: level-1 blocks of 9, then the small blocks
+    X = rng.standard_normal((N, 5))
+    y = np.cos(X.sum(1)) + 0.1 * rng.standard_normal(N)
+    eng = _lib.Engine(0)
+    eng.set_data(X)
+    ref = eng.exact_eval(_lib.COV_RBF, 3, [math.log(1.7), 0.2], math.log(0.15), y, False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    out = eng.exact_eval(_lib.COV_RBF, 3, [math.log(1.7), 0.2], math.log(0.15), y, False)
+    assert abs(out[0] - ref[0]) <= 1e-11 * abs(ref[0])
+    assert np.max(np.abs(np.array(out[1]) - np.array(ref[1]))) <= 1e-8 * np.max(np.abs(np.array(ref[1])))
