@@ -451,6 +451,24 @@ int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int
   return 0;
 }
 
+// C (na x nb, column-major ldc) = / += / -= A (na x K) * B (nb x K)' on the int8 tensor cores: both operands are sliced
+// into one buffer as [B rows; A rows] per contraction chunk of <= 16384 (int32 accumulators), see launch_oz_gemm_stacked.
+// cmode as in launch_oz_ex (0: C -= , 1: C = , 2: C +=).
+int oz_gemm_nt(Handle* h, cudaStream_t st, double* C, int64_t ldc, const double* A, int64_t lda, int na, const double* B,
+               int64_t ldb, int nb, int K, int cmode) {
+  const int KC = 16384;
+  if (na % NB || nb % NB || K % NB || na <= 0 || nb <= 0 || K <= 0) return GPK_ERR_ARG;
+  GPK_TRY(oz_ensure(h, 0, (int64_t)na + nb, K < KC ? K : KC));
+  for (int c0 = 0; c0 < K; c0 += KC) {
+    const int kw = (K - c0 < KC) ? K - c0 : KC;
+    GPK_TRY(launch_oz_slice(h, 0, st, B + (int64_t)c0 * ldb, ldb, nb, kw, 0, nb + na));
+    GPK_TRY(launch_oz_slice(h, 0, st, A + (int64_t)c0 * lda, lda, na, kw, nb, nb + na));
+    const int cm = (c0 == 0) ? cmode : (cmode == 0 ? 0 : 2);
+    GPK_TRY(launch_oz_ex(h, 0, st, C - nb, ldc, nb + na, kw, 0, nb / NB, 0, nb / NB, 0, cm));
+  }
+  return 0;
+}
+
 // sweep_forward with the O(M^2 n) part on the int8 tensor cores: column blocks of WB panels are finished with the DMMA
 // sweep restricted to the block, then ALL later columns get one update of contraction length WB*128,
 //   P[:, ke:] -= P[:, kb:ke] * L[ke:, kb:ke]',   operands stacked as [L rows; P rows] (launch_oz_gemm_stacked).

@@ -416,7 +416,8 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
     {
       GemmArgs a{};
       a.A = h->fVt; a.B = h->dU; a.C = Bt; a.lda = np; a.ldb = Mp; a.ldc = np; a.K = (int)Mp; a.tri = 0;
-      GPK_TRY(launch_gemm_nt(h, st, 0, a, Tn, Tm));
+      if (fitc_oz) GPK_TRY(oz_gemm_nt(h, st, Bt, np, h->fVt, np, (int)np, h->dU, Mp, (int)Mp, (int)Mp, 1));
+      else GPK_TRY(launch_gemm_nt(h, st, 0, a, Tn, Tm));
     }
     // w = B al                                                                           :433
     coldot_kernel<<<(unsigned)Mp, 256, 0, st>>>(Bt, np, np, al, nullptr, wv);
@@ -424,7 +425,8 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
     // W = Lu^-1 (V/g)   ->   Wt = diag(1/g) Vt * Lu^-T                                    :434
     rowscale_kernel<<<grid1(np * Mp), 256, 0, st>>>(h->fVt, np, np, Mp, rs, Wt);
     rowscale_kernel<<<grid1(np * Mp), 256, 0, st>>>(Wt, np, np, Mp, rs, Wt);
-    GPK_TRY(sweep_forward(h, st, Wt, np, Tn, h->fA2, Mp, h->fDinv2, Tm));
+    if (fitc_oz) GPK_TRY(sweep_forward_oz(h, st, Wt, np, Tn, h->fA2, Mp, h->fDinv2, Tm));
+    else GPK_TRY(sweep_forward(h, st, Wt, np, Tn, h->fA2, Mp, h->fDinv2, Tm));
     // ww = colsum(W*W) ; bb = colsum(B*B)
     rowdot2_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(Wt, Wt, np, np, Mp, 0, 0.0, ww);
     rowdot2_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(Bt, Bt, np, np, Mp, 0, 0.0, vb);
@@ -434,11 +436,13 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
     {
       GemmArgs a{};
       a.A = Bm; a.B = Wm; a.C = h->dTmp; a.lda = Mp; a.ldb = Mp; a.ldc = Mp; a.K = (int)np; a.tri = 0;
-      GPK_TRY(launch_gemm_nt(h, st, 0, a, Tm, Tm));
+      if (fitc_oz) GPK_TRY(oz_gemm_nt(h, st, h->dTmp, Mp, Bm, Mp, (int)Mp, Wm, Mp, (int)Mp, (int)np, 1));
+      else GPK_TRY(launch_gemm_nt(h, st, 0, a, Tm, Tm));
       GPK_TRY(dist_allreduce_sum(h, h->dTmp, (size_t)Mp * Mp, st));        // Q = B W' summed over all data shards
       GemmArgs q{};
       q.A = Wt; q.B = h->dTmp; q.C = Gt; q.lda = np; q.ldb = Mp; q.ldc = np; q.K = (int)Mp; q.tri = 0;
-      GPK_TRY(launch_gemm_nt(h, st, 0, q, Tn, Tm));
+      if (fitc_oz) GPK_TRY(oz_gemm_nt(h, st, Gt, np, Wt, np, (int)np, h->dTmp, Mp, (int)Mp, (int)Mp, 1));
+      else GPK_TRY(launch_gemm_nt(h, st, 0, q, Tn, Tm));
     }
     // scalars shared by all hyper-parameters: res[8]=sum log g (unused) [9]=al'al [11]=sum ww [12]=sum 1/g
     fitc_reduce_kernel<<<1, 1024, 0, st>>>(g, n, al, n, nullptr, 0, ww, n, nullptr, nullptr, 0, res + 8);
@@ -471,7 +475,8 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
         GemmArgs a{};                                                  // T' = B' dKuu  (dKuu symmetric)
         a.A = Bt; a.B = h->dW; a.C = h->fVt; a.lda = np; a.ldb = Mp; a.ldc = np; a.K = (int)Mp; a.tri = 0;
         // (V' is no longer needed once B', W' and al exist: its storage is scratch from here on)
-        GPK_TRY(launch_gemm_nt(h, st, 0, a, Tn, Tm));
+        if (fitc_oz) GPK_TRY(oz_gemm_nt(h, st, h->fVt, np, Bt, np, (int)np, h->dW, Mp, (int)Mp, (int)Mp, 1));
+        else GPK_TRY(launch_gemm_nt(h, st, 0, a, Tn, Tm));
       }
       fitc_r_kernel<<<grid1(np * Mp), 256, 0, st>>>(Rt, h->fVt, np * Mp);                         // fVt <- R'
       rowdot2_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(h->fVt, Bt, np, np, Mp, 0, 0.0, vb2);

@@ -202,6 +202,8 @@ int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_ti
                   const double* Dinv, int T);
 int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv);
 int inverse_factor_T_oz(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv);
+int oz_gemm_nt(Handle* h, cudaStream_t st, double* C, int64_t ldc, const double* A, int64_t lda, int na, const double* B,
+               int64_t ldb, int nb, int K, int cmode);
 int sweep_forward_oz(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A, int64_t lda,
                      const double* Dinv, int T);
 int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_parts, int* info,

@@ -101,14 +101,22 @@ __global__ void __launch_bounds__(128) rowdot_kernel(const double* __restrict__ 
   const int sp = blockIdx.y;
   const int64_t per = (cols + nsplit - 1) / nsplit;
   const int64_t r0 = sp * per, r1 = min(cols, r0 + per);
-  double s = 0.0;
   if (c < rows) {
-    if (mode == 0) {
-      for (int64_t r = r0; r < r1; ++r) s = fma(P[c + r * ld], v[r], s);
-    } else {
-      for (int64_t r = r0; r < r1; ++r) { const double x = P[c + r * ld]; s = fma(x, x, s); }
+    // eight independent accumulators: eight loads in flight per thread instead of one dependent FMA chain
+    // (the FITC V r product, 4096 x 262144, took 13.5 ms as a single chain per thread)
+    double a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = 0.0;
+    int64_t r = r0;
+    for (; r + 8 <= r1; r += 8) {
+      double x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = P[c + (r + q) * ld];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = fma(x[q], (mode == 0) ? v[r + q] : x[q], a[q]);
     }
-    part[(int64_t)sp * rows + c] = s;
+    for (; r < r1; ++r) { const double x = P[c + r * ld]; a[0] = fma(x, (mode == 0) ? v[r] : x, a[0]); }
+    part[(int64_t)sp * rows + c] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
 }
 
