@@ -361,6 +361,8 @@ static int free_all(Handle* h) {
   h->dInfo = nullptr;
   if (h->dFlags) cudaFree(h->dFlags);
   h->dFlags = nullptr;
+  if (h->epGraphExec) cudaGraphExecDestroy((cudaGraphExec_t)h->epGraphExec);
+  h->epGraphExec = nullptr;
   for (int w = 0; w < 2; ++w) {
     if (h->ozSl[w]) cudaFree(h->ozSl[w]);
     if (h->ozSc[w]) cudaFree(h->ozSc[w]);

@@ -120,13 +120,21 @@ __global__ void __launch_bounds__(512) ep_site_kernel(const double* __restrict__
 // rounding; the per-sweep rebuild (_epComputeParams) bounds any drift exactly as in the reference.
 // grid = ceil(n/256) CTAs; every CTA recomputes the (deterministic) site scalars, each thread owns one row.
 constexpr int EPB = 128;
-__global__ void __launch_bounds__(256) ep_site_blk_kernel(const double* __restrict__ Sig, int64_t ld, int64_t n, int i,
-                                                          int t, const double* __restrict__ y,
+__global__ void ep_set_int_kernel(int* p, int v) { *p = v; }
+// The site index is i = *i0p + t with t fixed per launch, so the EPB launches of a block are IDENTICAL from block to
+// block and are replayed as one CUDA graph (the per-site cost is launch latency, not work); launches past the last
+// site (ragged last block) return at once.
+__global__ void __launch_bounds__(256) ep_site_blk_kernel(const double* __restrict__ Sig, int64_t ld, int64_t n,
+                                                          const int* __restrict__ i0p, int t,
+                                                          const double* __restrict__ y,
                                                           const double* __restrict__ m, double* __restrict__ ttau,
                                                           double* __restrict__ tnu, double* __restrict__ mu,
                                                           double* __restrict__ S, double* __restrict__ Sc,
-                                                          double* __restrict__ cvec, const double* __restrict__ mu_in,
-                                                          double* __restrict__ mu_out) {
+                                                          double* __restrict__ cvec, double* __restrict__ mun) {
+  const int i = *i0p + t;
+  if (i >= n) return;
+  const double* mu_in = mun + (i & 1);
+  double* mu_out = mun + ((i + 1) & 1);
   __shared__ double w[EPB];
   __shared__ double sh[8];
   __shared__ double s_c, s_coef, s_tt, s_tn;
@@ -165,14 +173,21 @@ __global__ void __launch_bounds__(256) ep_site_blk_kernel(const double* __restri
   const int64_t r = (int64_t)blockIdx.x * 256 + tid;
   if (r < n) {
     double s = (r >= i) ? Sig[r + (int64_t)i * ld] : Sig[i + r * ld];
-    double a0 = 0.0, a1 = 0.0;
+    // eight loads in flight per thread: this loop is pure L2 latency (one launch per site, 32 CTAs at n = 8192)
+    double a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = 0.0;
     int j = 0;
-    for (; j + 1 < t; j += 2) {
-      a0 = fma(S[r + (int64_t)j * ld], w[j], a0);
-      a1 = fma(S[r + (int64_t)(j + 1) * ld], w[j + 1], a1);
+    for (; j + 8 <= t; j += 8) {
+      double x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = S[r + (int64_t)(j + q) * ld];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = fma(x[q], w[j + q], a[q]);
     }
-    if (j < t) a0 = fma(S[r + (int64_t)j * ld], w[j], a0);
-    s -= (a0 + a1);
+    double tail = 0.0;
+    for (; j < t; ++j) tail = fma(S[r + (int64_t)j * ld], w[j], tail);
+    s -= (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) + tail;
     S[r + (int64_t)t * ld] = s;
     Sc[r + (int64_t)t * ld] = c * s;
     const double munew = mu[r] + s * coef;
@@ -322,9 +337,17 @@ static int ep_compute_params(Handle* h, cudaStream_t st, const EpBuf& b, int64_t
   ep_build_b_kernel<<<grid_e(np * np), 256, 0, st>>>(b.K, b.ttau, np, n, np, h->dA);
   GPK_TRY(potrf_device(h, h->dA, np, h->dDinv, b.parts, h->dInfo, nullptr, nullptr));
   ep_colscale_kernel<<<grid_e(np * np), 256, 0, st>>>(b.K, b.ttau, np, n, np, b.P);
-  GPK_TRY(sweep_forward(h, st, b.P, np, T, h->dA, np, h->dDinv, T));               // P <- V'
+  // the two O(n^3) products of the rebuild run on the int8 tensor cores (error-free fp64 split, ozaki.cu) when the
+  // problem is large enough for it to pay and the int32 accumulators cannot overflow; GPK_OZAKI_EP=0: fp64 DMMA
+  const bool ep_oz = env_int("GPK_OZAKI", 1) && env_int("GPK_OZAKI_EP", 1) && T >= 16 && np < 18432;
+  if (ep_oz) GPK_TRY(sweep_forward_oz(h, st, b.P, np, T, h->dA, np, h->dDinv, T)); // P <- V'
+  else GPK_TRY(sweep_forward(h, st, b.P, np, T, h->dA, np, h->dDinv, T));
   GPK_CK(h, cudaMemcpyAsync(b.Sig, b.K, (size_t)np * np * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  {
+  if (ep_oz) {
+    GPK_TRY(oz_ensure(h, 1, np, (int)np));
+    GPK_TRY(launch_oz_slice(h, 1, st, b.P, np, (int)np, (int)np));
+    GPK_TRY(launch_oz_syrk(h, 1, st, b.Sig, np, (int)np, (int)np, 0, T));          // Sigma = K - V'V (lower)
+  } else {
     GemmArgs a{};
     a.A = b.P; a.B = b.P; a.C = b.Sig; a.lda = np; a.ldb = np; a.ldc = np; a.K = (int)np; a.tri = 1;
     GPK_TRY(launch_gemm_nt(h, st, 1, a, T, T));                                      // Sigma = K - V'V (lower)
@@ -444,13 +467,38 @@ int gpk_ep_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nh
       double* Sc = h->dU + np * EPB;
       GPK_CK(h, cudaMemcpyAsync(mun, b.mu, sizeof(double), cudaMemcpyDeviceToDevice, st));   // slot 0 = mu[0]
       const unsigned gsite = (unsigned)((n + 255) / 256);
+      if (!h->dFlags) {
+        GPK_CK(h, cudaMalloc((void**)&h->dFlags, 1024 * sizeof(int)));
+        GPK_CK(h, cudaMemsetAsync(h->dFlags, 0, 1024 * sizeof(int), st));
+        h->flag_epoch = 0;
+      }
+      int* i0p = h->dFlags + 1000;                // (the first T entries are the backward substitution's ready flags)
+      // the EPB site launches of one block as a graph, rebuilt only when a buffer or the size changes
+      const void* sig[8] = {b.Sig, b.y, i0p, b.ttau, b.mu, S, cvec, (const void*)(intptr_t)n};
+      const bool use_graph = env_int("GPK_EP_GRAPH", 1) != 0;
+      if (use_graph && (!h->epGraphExec || std::memcmp(sig, h->epGraphSig, sizeof(sig)) != 0)) {
+        if (h->epGraphExec) { cudaGraphExecDestroy((cudaGraphExec_t)h->epGraphExec); h->epGraphExec = nullptr; }
+        cudaGraph_t g = nullptr;
+        GPK_CK(h, cudaStreamSynchronize(st));
+        GPK_CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        for (int t = 0; t < EPB; ++t)
+          ep_site_blk_kernel<<<gsite, 256, 0, st>>>(b.Sig, np, n, i0p, t, b.y, b.m, b.ttau, b.tnu, b.mu, S, Sc, cvec, mun);
+        GPK_CK(h, cudaStreamEndCapture(st, &g));
+        cudaGraphExec_t ge = nullptr;
+        GPK_CK(h, cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+        h->epGraphExec = ge;
+        std::memcpy(h->epGraphSig, sig, sizeof(sig));
+      }
       for (int i0 = 0; i0 < (int)n; i0 += EPB) {
         const int bl = ((int)n - i0 < EPB) ? (int)n - i0 : EPB;
         GPK_CK(h, cudaMemsetAsync(S, 0, (size_t)(2 * np * EPB) * sizeof(double), st));
-        for (int t = 0; t < bl; ++t) {
-          const int i = i0 + t;
-          ep_site_blk_kernel<<<gsite, 256, 0, st>>>(b.Sig, np, n, i, t, b.y, b.m, b.ttau, b.tnu, b.mu, S, Sc, cvec,
-                                                    mun + (i & 1), mun + ((i + 1) & 1));
+        ep_set_int_kernel<<<1, 1, 0, st>>>(i0p, i0);
+        if (use_graph) {
+          GPK_CK(h, cudaGraphLaunch((cudaGraphExec_t)h->epGraphExec, st));
+        } else {
+          for (int t = 0; t < bl; ++t)
+            ep_site_blk_kernel<<<gsite, 256, 0, st>>>(b.Sig, np, n, i0p, t, b.y, b.m, b.ttau, b.tnu, b.mu, S, Sc, cvec, mun);
         }
         GemmArgs a{};                                 // Sigma0 -= (S diag c) S'  on the lower triangle
         a.A = Sc; a.B = S; a.C = b.Sig; a.lda = np; a.ldb = np; a.ldc = np; a.K = EPB; a.tri = 1;

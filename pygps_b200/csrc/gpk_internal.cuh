@@ -96,6 +96,7 @@ struct Handle {
   double* dR = nullptr;      // (np) y - m
   double* dScal = nullptr;   // scalars: [0..T) logdet parts, then results
   int* dInfo = nullptr;
+  void* epGraphExec = nullptr; const void* epGraphSig[8] = {};   // the EP block's site launches as a CUDA graph (ep.cu)
   int* dFlags = nullptr; int flag_epoch = 0;   // epoch-stamped ready flags of the persistent backward substitution
   double* hPinned = nullptr; // small pinned staging
   // posterior state

@@ -80,3 +80,25 @@ def test_labels_are_checked_and_shapes_follow_the_reference():
     post, nlZ, dnlZ = pg.inf.EP().evaluate(pg.mean.Zero(), pg.cov.RBF(), pg.lik.Erf(), x, y, nargout=3)
     assert post.alpha.shape[0] == 20 and post.L.shape == (20, 20) and post.sW.shape == (20, 1)
     assert type(nlZ) is np.float64 and all(type(v) is np.float64 for v in dnlZ.cov)
+
+
+def test_int8_and_dmma_ep_rebuild_agree(monkeypatch):
+    """EP with the two O(n^3) products of the per-sweep rebuild (V = L^-1 sW K as a blocked sweep, Sigma = K - V'V as a
+    sliced SYRK) on the int8 tensor cores (default for n >= 2048) against fp64 DMMA (GPK_OZAKI_EP=0)."""
+    import math
+    from pygps_b200 import _lib
+    rng = np.random.default_rng(31)
+    n, D = 2300, 4
+    X = rng.standard_normal((n, D))
+    y = np.sign(X[:, 0] + 0.5 * X[:, 1] + 0.3 * rng.standard_normal(n))
+    eng = _lib.Engine(0)
+    eng.set_data(X)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GPK_OZAKI_EP", mode)
+        res[mode] = eng.ep_eval(_lib.COV_RBF, 3, [math.log(2.0), 0.3], np.zeros(n), y, np.zeros(n), np.zeros(n), False, True)
+    a, b = res["1"], res["0"]
+    assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0]), (a[0], b[0])
+    for u, v in zip(a[1:], b[1:]):
+        if isinstance(u, np.ndarray) and u.dtype.kind == "f" and u.size:
+            assert np.max(np.abs(u - v)) <= 1e-6 * max(np.max(np.abs(v)), 1e-300)
