@@ -402,6 +402,9 @@ def run_ours(args):
 
 
 def main():
+    # rank 0 prints ONE JSON line on stdout: keep NCCL's own version / debug lines (printed on stdout when the box
+    # exports NCCL_DEBUG) out of it
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
