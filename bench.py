@@ -36,6 +36,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_JSON_OUT = None   # the original stdout (see main)
 METRIC = "nlZ evals/sec at N=16384 D=8 RBF"
 UNIT = "evals/s"
 N_FULL, D_FULL = 16384, 8
@@ -195,8 +196,14 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
     return 0
+
+
+def _emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -396,15 +403,19 @@ def run_ours(args):
                 "gpu_launches": launches_total, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                 "parity": {"nlZ": nlz_first, "reference_nlZ": ref_nlz, "rel_err": parity}}
         line.update(extra)
-        print(json.dumps(line))
+        _emit(line)
     ctx.close()
     return 0
 
 
 def main():
-    # rank 0 prints ONE JSON line on stdout: keep NCCL's own version / debug lines (printed on stdout when the box
-    # exports NCCL_DEBUG) out of it
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # rank 0 prints ONE JSON line on stdout.  NCCL prints its version / debug lines on the process's stdout (fd 1) when
+    # the box exports NCCL_DEBUG, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private
+    # duplicate of the original stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
