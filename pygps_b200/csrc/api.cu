@@ -826,7 +826,12 @@ int gpk_predict(gpk_handle hh, const double* Xs, int64_t ns, double* ks_alpha, d
     // Ks' alpha  (undo the 1/sn scaling)
     GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, h->dAlpha, 0, ep ? 1.0 : sn, 0.0, dPart, nsplit, dOut, m));
     if (ep) GPK_TRY(launch_colscale_inplace(h, st, h->dP, mp, mp, np, h->eSW));   // sW .* Ks  (Core/gp.py:415)
-    GPK_TRY(sweep_forward(h, st, h->dP, mp, (int)(mp / NB), h->dA, np, h->dDinv, T));
+    // the multi-right-hand-side forward solve (mp x np x np flops): blocked, with the updates on the int8 tensor
+    // cores, when there are enough test points and panels for it to pay (GPK_OZAKI_PREDICT=0: fp64 DMMA sweep)
+    if (env_int("GPK_OZAKI", 1) && env_int("GPK_OZAKI_PREDICT", 1) && T >= 16 && mp >= 1024)
+      GPK_TRY(sweep_forward_oz(h, st, h->dP, mp, (int)(mp / NB), h->dA, np, h->dDinv, T));
+    else
+      GPK_TRY(sweep_forward(h, st, h->dP, mp, (int)(mp / NB), h->dA, np, h->dDinv, T));
     GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, nullptr, 1, 1.0, sf2, dPart, nsplit, dOut + mp, m));
     GPK_CK(h, cudaMemcpyAsync(ks_alpha + lo, dOut, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
     GPK_CK(h, cudaMemcpyAsync(fs2 + lo, dOut + mp, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -415,33 +415,51 @@ __global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_bwd_kernel(const double*
 // GEMVs from shared memory -> publish: a few microseconds, against ~10 us per step for one launch per step.
 // ---------------------------------------------------------------------------
 constexpr int BW_CH = 32;                                  // columns per chunk
-constexpr int BW_RING = 6;                                 // chunks in flight
-constexpr size_t BW_SMEM = size_t(BW_RING) * BW_CH * NB * sizeof(double);   // 192 KB
+constexpr int BW_RING = 4;                                 // L chunks in flight: one whole 128x128 tile
+constexpr int BW_DINV = (128 + 96 + 64 + 32) * BW_CH;      // Dinv_j, lower triangle by 32-column chunks (rows >= 32q)
+constexpr size_t BW_SMEM = (size_t(BW_RING) * BW_CH * NB + BW_DINV) * sizeof(double);   // 128 KB + 80 KB
 
 __global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_bwd_persistent_kernel(
     const double* __restrict__ A, int64_t lda, const double* __restrict__ Dinv, const double* __restrict__ z,
     double* __restrict__ x, int* __restrict__ flags, int epoch, int T) {
-  extern __shared__ __align__(16) double ring[];
+  extern __shared__ __align__(16) double bw_sm[];
+  double* dinv_sm = bw_sm;                                 // resident from the start: nothing to fetch on the chain
+  double* ring = bw_sm + BW_DINV;
   __shared__ double zacc[NB], zfin[NB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = blockIdx.x;
-  const int ntiles = T - 1 - j;                            // tiles of L in this block column, then Dinv_j
-  const int nchunks = 4 * (ntiles + 1);
+  const int ntiles = T - 1 - j;                            // tiles of L in this block column
+  const int nchunks = 4 * ntiles;
   if (tid < NB) zacc[tid] = 0.0;
 
+  // Dinv_j: chunk q = columns 32q..32q+31, rows 32q..127 (the block is lower triangular), pitch 128 - 32q
+  {
+    const double* src = Dinv + (int64_t)j * NB * NB;
+    int off = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rows = NB - 32 * q, pieces = rows / 2;     // 16-byte pieces per column
+      for (int ch = tid; ch < BW_CH * pieces; ch += TRSV_THREADS) {
+        const int c = ch / pieces, r = (ch % pieces) * 2;
+        unsigned sa = (unsigned)__cvta_generic_to_shared(dinv_sm + off + r + c * rows);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + (32 * q + r) + (int64_t)(32 * q + c) * NB) : "memory");
+      }
+      off += rows * BW_CH;
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
   auto issue = [&](int g) {
     if (g < nchunks) {
       const int t = g >> 2, q = g & 3;
-      const double* src; int64_t pitch;
-      if (t < ntiles) { const int k = T - 1 - t; src = A + (int64_t)k * NB + (int64_t)(j * NB + q * BW_CH) * lda; pitch = lda; }
-      else { src = Dinv + (int64_t)j * NB * NB + (int64_t)q * BW_CH * NB; pitch = NB; }
+      const int k = T - 1 - t;
+      const double* src = A + (int64_t)k * NB + (int64_t)(j * NB + q * BW_CH) * lda;
       double* dst = ring + (size_t)(g % BW_RING) * BW_CH * NB;
 #pragma unroll
       for (int i = 0; i < (BW_CH * NB / 2) / TRSV_THREADS; ++i) {
         const int ch = tid + i * TRSV_THREADS;             // 16-byte piece: 64 per column
         const int c = ch >> 6, r = (ch & 63) * 2;
         unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r + c * NB);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + r + (int64_t)c * pitch) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + r + (int64_t)c * lda) : "memory");
       }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -449,41 +467,56 @@ __global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_bwd_persistent_kernel(
 #pragma unroll
   for (int g = 0; g < BW_RING - 1; ++g) issue(g);
 
-  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;           // this lane's entries of the current vector (x_k or z_j)
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;           // this lane's entries of x_k
+  constexpr int CPW = BW_CH / (TRSV_THREADS / 32);         // columns per warp per chunk
   for (int g = 0; g < nchunks; ++g) {
-    const int t = g >> 2, q = g & 3;
-    if (q == 0) {
-      if (t < ntiles) {
-        const int k = T - 1 - t;
-        if (tid == 0) {
-          int f;
-          do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(f) : "l"(flags + k) : "memory"); } while (f != epoch);
-        }
-        __syncthreads();
-        const double* xk = x + (int64_t)k * NB;
-        v0 = __ldcg(xk + lane); v1 = __ldcg(xk + lane + 32); v2 = __ldcg(xk + lane + 64); v3 = __ldcg(xk + lane + 96);
-      } else {
-        __syncthreads();                                   // all updates of z_j are in zacc
-        if (tid < NB) zfin[tid] = z[(int64_t)j * NB + tid] - zacc[tid];
-        __syncthreads();
-        v0 = zfin[lane]; v1 = zfin[lane + 32]; v2 = zfin[lane + 64]; v3 = zfin[lane + 96];
-      }
-    }
+    const int q = g & 3;
     asm volatile("cp.async.wait_group %0;\n" ::"n"(BW_RING - 2) : "memory");
     __syncthreads();                                       // chunk g has landed; chunk g-1's slot is free
-    issue(g + BW_RING - 1);
+    issue(g + BW_RING - 1);                                // requested BEFORE blocking on x_k: the whole tile is in
+    if (q == 0) {                                          // flight (or here) when its x_k is published
+      const int k = T - 1 - (g >> 2);
+      if (tid == 0) {
+        int f;
+        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(f) : "l"(flags + k) : "memory"); } while (f != epoch);
+      }
+      __syncthreads();
+      const double* xk = x + (int64_t)k * NB;
+      v0 = __ldcg(xk + lane); v1 = __ldcg(xk + lane + 32); v2 = __ldcg(xk + lane + 64); v3 = __ldcg(xk + lane + 96);
+    }
     const double* ch = ring + (size_t)(g % BW_RING) * BW_CH * NB;
 #pragma unroll
-    for (int i = 0; i < BW_CH / (TRSV_THREADS / 32); ++i) {
-      const int c = warp * (BW_CH / (TRSV_THREADS / 32)) + i;
+    for (int i = 0; i < CPW; ++i) {
+      const int c = warp * CPW + i;
       const double* col = ch + c * NB;
       double sacc = fma(col[lane], v0, fma(col[lane + 32], v1, fma(col[lane + 64], v2, col[lane + 96] * v3)));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(FULL, sacc, o);
-      if (lane == 0) {
-        if (t < ntiles) zacc[q * BW_CH + c] += sacc;
-        else x[(int64_t)j * NB + q * BW_CH + c] = sacc;
+      if (lane == 0) zacc[q * BW_CH + c] += sacc;
+    }
+  }
+  // x_j = Dinv_j' z_j from the resident copy
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  if (tid < NB) zfin[tid] = z[(int64_t)j * NB + tid] - zacc[tid];
+  __syncthreads();
+  {
+    int off = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rows = NB - 32 * q;
+#pragma unroll
+      for (int i = 0; i < CPW; ++i) {
+        const int c = warp * CPW + i;
+        const double* col = dinv_sm + off + c * rows;      // col[r'] = Dinv[32q + r', 32q + c]
+        double sacc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4 - q; ++b) sacc = fma(col[lane + 32 * b], zfin[32 * q + lane + 32 * b], sacc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(FULL, sacc, o);
+        if (lane == 0) x[(int64_t)j * NB + q * BW_CH + c] = sacc;
       }
+      off += rows * BW_CH;
     }
   }
   __syncthreads();

@@ -333,3 +333,26 @@ def test_schedule_variants_give_the_same_evaluation(monkeypatch, env):
     out = eng.exact_eval(_lib.COV_RBF, 3, [math.log(1.7), 0.2], math.log(0.15), y, False)
     assert abs(out[0] - ref[0]) <= 1e-11 * abs(ref[0])
     assert np.max(np.abs(np.array(out[1]) - np.array(ref[1]))) <= 1e-8 * np.max(np.abs(np.array(ref[1])))
+
+
+def test_int8_and_dmma_predict_solves_agree(monkeypatch):
+    """GP.predict's multi-right-hand-side forward solve as a blocked sweep with int8 tensor-core updates (default for
+    >= 1024 test points and >= 16 panels) against the fp64 DMMA sweep (GPK_OZAKI_PREDICT=0): ym and ys2."""
+    X, y = go.synth_regression(3000, 8)
+    Xs = np.random.default_rng(3).standard_normal((1500, 8))
+    m = pg.GPR()
+    m.setPrior(kernel=pg.cov.RBF(np.log(2.0), 0.0))
+    m.getPosterior(X, y, der=False)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GPK_OZAKI_PREDICT", mode)
+        out[mode] = m.predict(Xs)
+    for a, b in zip(out["1"][:4], out["0"][:4]):
+        assert np.max(np.abs(a - b)) <= 1e-9 * max(np.max(np.abs(b)), 1e-300)
+    # and against the oracle on a subset (the reference's own batch loop, Core/gp.py:402-419)
+    hyp, sn = [np.log(2.0), 0.0], np.log(0.1)
+    rpost = go.exact_evaluate(("zero",), ("rbf", hyp), sn, X, y, 1)
+    if isinstance(rpost, tuple):
+        rpost = rpost[0]
+    rym, rys2 = go.predict(("zero",), ("rbf", hyp), sn, X, rpost, Xs[:200])[:2]
+    assert rel(out["1"][0][:200], rym) < 1e-6 and rel(out["1"][1][:200], rys2) < 1e-6
