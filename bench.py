@@ -65,7 +65,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -76,7 +76,14 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: call at the start and at the end of the timed region."""
+        return len(self.lines)
+
+    def stop(self, lo=0, hi=None):
+        """Summary of the samples [lo, hi) (the timed region).  The sampler is started before the warm-up (nvidia-smi
+        needs a few hundred ms to deliver its first line, the timed region is ~0.25 s); if the region is too short to
+        hold a sample, the closest samples - taken under the same workload during the warm-up - are used and flagged."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -84,9 +91,15 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        hi = len(self.lines) if hi is None else hi
+        window, note = self.lines[lo:hi], None
+        if not window:
+            window = self.lines[max(0, lo - 5):hi + 1]
+            note = "timed region shorter than the sampling interval: samples from the warm-up of the same workload"
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        self._note = note
+        for l in window:
             f = [s.strip() for s in l.split(",")]
             if len(f) < 9:
                 continue
@@ -99,8 +112,11 @@ class ClockSampler(object):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if self._note:
+            out["note"] = self._note
+        return out
 
 
 # ----------------------------------------------------------------------------- CPU legs
@@ -237,6 +253,7 @@ def run_ours(args):
     eng.set_data(X)
     eng.set_profile(True)      # two CUDA events around each step's trailing-update launches (same stream)
     nlz_first = None
+    clocks.start()             # before the warm-up: nvidia-smi's first line takes a few hundred ms
     for k in range(warmup):
         h, sn = replica_hyp(k, ctx.rank)
         out = eng.exact_eval(_lib.COV_RBF, 3, h, sn, ymm, False)
@@ -246,8 +263,8 @@ def run_ours(args):
     parity = None if ref_nlz is None else abs(nlz_first - ref_nlz) / abs(ref_nlz)
     if parity is not None and not parity < 1e-6:
         raise SystemExit("parity gate failed: nlZ %r vs reference %r" % (nlz_first, ref_nlz))
-    clocks.start()
     ctx.barrier()
+    clk_lo = clocks.mark()
     dev_ms = 0.0
     launches = 0
     stage = {"kbuild_ms": 0.0, "potrf_ms": 0.0, "solve_ms": 0.0}
@@ -264,11 +281,12 @@ def run_ours(args):
         syrk_ms += st["syrk_ms"]
         syrk_fl += st["syrk_flops"]
     wall = time.perf_counter() - t0            # every call ends with a stream synchronize
+    clk_hi = clocks.mark()
     ctx.barrier()
     t_rank = max(wall, dev_ms * 1e-3)
     t_max = ctx.max(t_rank)
     value = aggregate_rate(steps, n_gpus, t_max)
-    clk = clocks.stop()
+    clk = clocks.stop(clk_lo, clk_hi)
     launches_total = int(ctx.sum(launches))
 
     # ---- end-to-end arm through the plugin API (host arrays in, host results out) ----------
@@ -350,7 +368,7 @@ def run_ours(args):
                                 "ratio": traffic / float(tj["algorithmic_bytes"]["total"]), "source": tj["source"]}
             except Exception:
                 pass
-            roof = {"bound": "tensor", "kernel": "oz_syrk_kernel<7,8,1> (trailing SYRK update: tcgen05.mma.kind::i8, TMEM accumulators)",
+            roof = {"bound": "tensor", "kernel": "oz_syrk_kernel<7,8,1,0> (trailing SYRK update: tcgen05.mma.kind::i8, TMEM accumulators)",
                     "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_note": traffic_note,
                     "peak_source": src,

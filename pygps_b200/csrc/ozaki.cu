@@ -203,8 +203,12 @@ __device__ __forceinline__ void oz_decode(int idx, int nt, int jb0, int jb1, int
   }
 }
 
-template <int S, int RB, int EPI>
+// GEN = 0: the Cholesky's update (C -= P P', full contraction) with the flags folded away at compile time - the
+// generalised form costs 38 registers and 5 % of the hot kernel; GEN = 1: trap / cmode honoured.
+template <int S, int RB, int EPI, int GEN>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
+  const int a_trap = GEN ? a.trap : 0;
+  const int a_cmode = GEN ? a.cmode : 0;
   constexpr uint32_t A_BYTES = 128 * S * 32, B_BYTES = OZ_BN * S * 32, STAGE = A_BYTES + B_BYTES;
   constexpr uint32_t TCOLS = 512;
   constexpr bool ATMEM = (S * OZ_BN + S * 8 <= 512);   // room for one k-step of the A slices behind the accumulators
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
         oz_decode(tile0, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
         const int8_t* gA = a.sl + (size_t)ti * 128 * S * 32;
         const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
-        const int ks0 = a.trap ? 4 * ti : 0;             // (the last row tile still has nk - ks0 = 4 = OZ_ST k-steps)
+        const int ks0 = a_trap ? 4 * ti : 0;             // (the last row tile still has nk - ks0 = 4 = OZ_ST k-steps)
 #pragma unroll
         for (int ks = 0; ks < OZ_ST; ++ks) {
           mbar_expect_tx(&full[ks], STAGE);
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
         oz_decode(tile, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
         const int8_t* gA = a.sl + (size_t)ti * 128 * S * 32;
         const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
-        for (int ks = a.trap ? 4 * ti : 0; ks < nk; ++ks, ++it) {
+        for (int ks = a_trap ? 4 * ti : 0; ks < nk; ++ks, ++it) {
           const int slot = it % OZ_ST;
           if (it < OZ_ST) continue;                      // requested before the CTA barrier (see above)
           mbar_wait(&empty[slot], ((it / OZ_ST) - 1) & 1);
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
       for (int tile = tile0; tile < tile1; ++tile, ++tcount) {
         if (tcount > 0) { mbar_wait(&tfree, (tcount - 1) & 1); tc_fence_after(); }
         int ks0 = 0;
-        if (a.trap) {
+        if (a_trap) {
           int ti, tj;
           oz_decode(tile, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
           ks0 = 4 * ti;
@@ -405,8 +409,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
         // load of the first column scale of every round)
         if (tid < OZ_BN) sjs[tid] = a.sc[tj * OZ_BN + tid];
         asm volatile("bar.sync 1, %0;\n" ::"n"(OZ_EPI_WARPS * 32) : "memory");
-        const bool rd = (a.cmode != 1);                  // C is read (update) or only written (set)
-        const double sg = (a.cmode == 0) ? 1.0 : -1.0;
+        const bool rd = (a_cmode != 1);                  // C is read (update) or only written (set)
+        const double sg = (a_cmode == 0) ? 1.0 : -1.0;
         if (rd) {
 #pragma unroll
           for (int q = 0; q < OZ_BN / 2; ++q)
@@ -522,17 +526,22 @@ int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int6
   return c.S == 7 ? oz_slice_t<7, 8>(h, which, st, P, lda, n, kw, row0, ntot) : oz_slice_t<6, 8>(h, which, st, P, lda, n, kw, row0, ntot);
 }
 
-template <int S, int RB, int EPI>
-static int oz_syrk_e(Handle* h, cudaStream_t st, const OzArgs& a) {
+template <int S, int RB, int EPI, int GEN>
+static int oz_syrk_g(Handle* h, cudaStream_t st, const OzArgs& a) {
   static bool attr_done = false;
   const size_t smem = (size_t)OZ_ST * (128 + OZ_BN) * S * 32;
   if (!attr_done) {
-    GPK_CK(h, cudaFuncSetAttribute(oz_syrk_kernel<S, RB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPK_CK(h, cudaFuncSetAttribute(oz_syrk_kernel<S, RB, EPI, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  oz_syrk_kernel<S, RB, EPI><<<(a.ntiles + a.tpc - 1) / a.tpc, OZ_THREADS, smem, st>>>(a);
+  oz_syrk_kernel<S, RB, EPI, GEN><<<(a.ntiles + a.tpc - 1) / a.tpc, OZ_THREADS, smem, st>>>(a);
   GPK_CK(h, cudaGetLastError());
   return 0;
+}
+
+template <int S, int RB, int EPI>
+static int oz_syrk_e(Handle* h, cudaStream_t st, const OzArgs& a) {
+  return (a.trap || a.cmode) ? oz_syrk_g<S, RB, EPI, 1>(h, st, a) : oz_syrk_g<S, RB, EPI, 0>(h, st, a);
 }
 
 template <int S, int RB>
