@@ -544,8 +544,16 @@ int launch_trsv_bwd_all(Handle* h, cudaStream_t st, const double* A, int64_t lda
   int epoch = ++h->flag_epoch;
   int* flags = h->dFlags;
   void* args[] = {(void*)&A, (void*)&lda, (void*)&Dinv, (void*)&z, (void*)&x, (void*)&flags, (void*)&epoch, (void*)&T};
-  GPK_CK(h, cudaLaunchCooperativeKernel((const void*)trsv_bwd_persistent_kernel, dim3(T), dim3(TRSV_THREADS), args,
-                                        BW_SMEM, st));
+  // All T CTAs must be co-resident (they wait on each other's flags), which only a cooperative launch guarantees.
+  // If the device cannot grant it (SMs held by another context, MPS limits), fall back to one launch per block step -
+  // the same arithmetic on the same GPU, never a CPU path.
+  const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)trsv_bwd_persistent_kernel, dim3(T),
+                                                     dim3(TRSV_THREADS), args, BW_SMEM, st);
+  if (ce != cudaSuccess) {
+    (void)cudaGetLastError();
+    for (int k = T - 1; k >= 0; --k) GPK_TRY(launch_trsv_bwd(h, st, A, lda, Dinv, z, x, k, T));
+    return 0;
+  }
   h->stats.launches++;
   return 0;
 }
