@@ -172,3 +172,41 @@ def test_poststruct_deepcopy_keeps_lazy_factor_and_dnlz_accumulates():
     d1, d2 = pg.inf.dnlZStruct(m, c, l), pg.inf.dnlZStruct(m, c, l)
     d1.cov, d2.cov = [1., 2.], [3., 4.]
     assert d1.accumulateDnlZ(d2).cov == [4., 6.] and len(d1.mean) == 1 and len(d1.lik) == 1
+
+
+def test_bench_clock_sampler_windows_and_reference_arm_line():
+    """bench.py host logic: the clock summary is taken from the samples of the timed region (falling back, flagged, to the
+    warm-up's when the region holds none), throttle reasons are collected, and `--impl reference` prints ONE JSON line
+    with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+
+    class FakeProc(object):
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    def line(mhz, cap="Not Active"):
+        return "0, %d, 1965, 400.0, 0x0, Not Active, Not Active, Not Active, %s" % (mhz, cap)
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = [line(1200), line(1900), line(1950, "Active"), line(1960), line(1300)]
+    out = s.stop(1, 4)
+    assert out["samples"] == 3 and out["sm_mhz"] == 1950.0 and out["reasons"] == ["sw_power_cap"] and "note" not in out
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = [line(1900), line(1910)]
+    out = s.stop(2, 2)                                   # empty timed window: warm-up samples, flagged
+    assert out["samples"] == 2 and "note" in out
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--problem-n", "512"], capture_output=True, text=True, timeout=300)
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert p.returncode == 0 and len(lines) == 1, (p.returncode, p.stdout[-300:], p.stderr[-300:])
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
