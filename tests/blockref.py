@@ -128,10 +128,11 @@ def trsv_bwd(A, Dinv, z, x, k, T):
         z[j * NB:(j + 1) * NB] -= A[k * NB:(k + 1) * NB, j * NB:(j + 1) * NB].T @ xk
 
 
-def oz_decode(idx, nt, jb0, jb1, band=16):
-    """ozaki.cu oz_decode: CTA index -> (128-row tile, 64-column tile) of the lower-triangular tile set
-    {jb0 <= jb < jb1, ti >= jb}, rasterised in bands of `band` row tiles (L2 reuse of the operand slices)."""
-    r_lo = jb0
+def oz_decode(idx, nt, jb0, jb1, band=16, ti_min=0):
+    """ozaki.cu oz_decode: CTA index -> (128-row tile, 64-column tile) of the tile set
+    {jb0 <= jb < jb1, ti >= max(jb, ti_min)}, rasterised in bands of `band` row tiles (L2 reuse of the operand slices).
+    ti_min = 0: lower triangle (SYRK); ti_min >= jb1: the rectangle of a stacked-operand product."""
+    r_lo = max(jb0, ti_min)
     while True:
         r_hi = min(r_lo + band, nt)
         rows = r_hi - r_lo
@@ -154,9 +155,19 @@ def oz_decode(idx, nt, jb0, jb1, band=16):
         r_lo = r_hi
 
 
-def oz_ntiles(nt, jb0, jb1):
-    """launch_oz_syrk: number of 128x64 tiles (= CTAs) of a launch."""
-    return 2 * nt * (jb1 - jb0) - (jb1 * (jb1 - 1) - jb0 * (jb0 - 1))
+def oz_ntiles(nt, jb0, jb1, ti_min=0):
+    """launch_oz_ex: number of 128x64 tiles (= CTAs) of a launch."""
+    return sum(2 * (nt - max(jb, ti_min)) for jb in range(jb0, jb1))
+
+
+def oz_gemm_stacked(C, A, B, S=7, RB=8):
+    """launch_oz_gemm_stacked: C (rows of A x rows of B) -= A B' through the SYRK machinery on the operands stacked
+    as [B; A]: one split (row scales per stacked row), tiles {ti >= nb/128, jb < nb/128}."""
+    nb = B.shape[0]
+    P = np.vstack([B, A])
+    full = np.zeros((P.shape[0], P.shape[0]))
+    oz_syrk(full, P, S, RB)                       # full -= P P'
+    C += full[nb:, :nb]
 
 
 def oz_split(P, S=7, RB=8):

@@ -181,3 +181,26 @@ def test_split_panel_chain_and_head_update_give_the_same_factor(n, W, W1, W2B):
     Lref = np.linalg.cholesky(A0)
     assert np.max(np.abs(Ls[1] - Lref)) <= 1e-11 * np.max(np.abs(Lref))
     assert np.max(np.abs(Ls[1] - Ls[0])) <= 1e-12 * np.max(np.abs(Lref))
+
+
+@pytest.mark.parametrize("nt,jb0,jb1,ti_min", [(40, 0, 5, 5), (37, 0, 12, 12), (70, 0, 3, 3), (20, 0, 6, 2), (33, 2, 9, 4)])
+def test_rectangular_tile_enumeration_of_the_stacked_product(nt, jb0, jb1, ti_min):
+    """With ti_min the same band rasterisation enumerates {jb0 <= jb < jb1, ti >= max(jb, ti_min)} exactly once -
+    for ti_min >= jb1 that is the nb x na rectangle of launch_oz_gemm_stacked."""
+    n = br.oz_ntiles(nt, jb0, jb1, ti_min)
+    got = [br.oz_decode(i, nt, jb0, jb1, ti_min=ti_min) for i in range(n)]
+    want = {(ti, tj) for jb in range(jb0, jb1) for ti in range(max(jb, ti_min), nt) for tj in (2 * jb, 2 * jb + 1)}
+    assert len(set(got)) == n and set(got) == want
+
+
+def test_stacked_operand_product_matches_fp64():
+    """A B' from ONE split of [B; A] (different row scales per operand row) against the fp64 product."""
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((256, 128)) * np.exp(rng.uniform(-5, 5, size=(256, 1)))
+    B = rng.standard_normal((128, 128)) * np.exp(rng.uniform(-5, 5, size=(128, 1)))
+    C0 = rng.standard_normal((256, 128))
+    C = C0.copy()
+    br.oz_gemm_stacked(C, A, B)
+    ref = C0 - A @ B.T
+    den = np.abs(A) @ np.abs(B).T
+    assert np.max(np.abs(C - ref) / den) < 1e-14
