@@ -41,15 +41,20 @@ static int ensure_prof_events(Handle* h, size_t count) {
 //   level 1: a block of W1 panels; when it is done the whole trailing matrix gets ONE update with contraction
 //            length W1*128.  On the int8 tensor-core path (ozaki.cu) the cost of an update tile's epilogue (TMEM ->
 //            fp64 -> C) is fixed, so long contractions are what makes it efficient: W1 = 9 while the trailing
-//            matrix is large, W1 = W2 once the factorization is bound by the panel chain anyway.
+//            matrix is large; once the factorization is bound by the panel chain the blocks are ONE sub-block of
+//            W2B = 4 panels.
 //   level 2: sub-blocks of W2 panels inside the block; after each, the REST OF THE BLOCK'S columns are updated
 //            (contraction W2*128), on the panel stream.
 //   level 3: single panels of 128 columns: diag -> trsm -> rank-128 update of the remaining columns of the
 //            sub-block (fp64 DMMA).
 // Streams:
-//   s_panel (high priority): everything inside a level-1 block
+//   s_panel (high priority): the dependent chain: diag(p), then the HEAD of panel p (tile (p+1,p) solved, tile
+//                            (p+1,p+1) updated: all diag(p+1) needs), the level-2 updates, and - for the small blocks -
+//                            the level-1 update of the next block's first diagonal tile
+//   s_tail                 : the TAIL of panel p, one panel behind: TRSM of the rows below, rest of the rank-128 update
 //   s_main                 : level-1 update: first the next block's columns (so its panels can start), then
-//                            the rest of the trailing matrix
+//                            the rest of the trailing matrix; with lazy_cov also the generation of the matrix itself
+//                            (first block's columns, then the rest under the first panels)
 //   s_aux                  : single-right-hand-side forward substitution step p, off the critical path
 // Level-1 block j+1 therefore overlaps the bulk of trailing update j (look-ahead 1).
 // ---------------------------------------------------------------------------

@@ -16,9 +16,11 @@
 //   oz_slice_kernel  : row exponents, then the int8 slices written directly in the tensor core's canonical K-major "core matrix" order
 //                      [k-step 32][row group 8][slice t][k chunk 2][row 8][16 B], so that a (rows x 32 k) stage of
 //                      ALL slices of a tile is ONE contiguous block: a single cp.async.bulk (TMA) per operand per stage
-//   oz_syrk_kernel   : 128x64 tiles of C (a few per CTA, lower triangle only); warp 9 = TMA producer, warp 8 = MMA
-//                      issuer, warps 0-7 = epilogue (C prefetch -> TMEM -> fp64 -> C).  S(S+1)/2 MMAs of 128x64x32
-//                      per k-step; the producer runs ahead into the next tile while the epilogue drains TMEM.
+//   oz_syrk_kernel   : 128x64 tiles of C (one per CTA by default, lower triangle only); warp 9 = TMA producer (barriers
+//                      and the first four stages before the CTA barrier), warp 8 = MMA issuer, warps 0-7 = epilogue
+//                      (software-pipelined TMEM -> fp64 -> C).  S(S+1)/2 MMAs of 128x64x32 per k-step.
+//   generalisations  : launch_oz_ex - rectangular products of two operands stacked in one slice buffer (ti_min),
+//                      trapezoid contraction (U U'), C -= / = / += ; used by the derivative, FITC, EP and predict paths.
 // Short CTAs (not one persistent CTA per SM) on purpose: the high-priority panel stream of the look-ahead
 // Cholesky needs SMs to free up every few microseconds.
 #include <cstdint>
