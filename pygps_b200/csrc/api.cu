@@ -357,7 +357,7 @@ int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::
 static int free_all(Handle* h) {
   double** ptrs[] = {&h->dX, &h->dXs, &h->dScale, &h->dA, &h->dDinv, &h->dB, &h->dZ, &h->dAlpha, &h->dR, &h->dScal,
                      &h->dU, &h->dW, &h->dP, &h->dTmp, &h->dUin, &h->dUs, &h->dLpost, &h->dAlphaU,
-                     &h->fKuu, &h->fDinvU, &h->fA2, &h->fDinv2, &h->fVt, &h->fVs, &h->fVec, &h->fWt, &h->dXtmp, &h->gA, &h->gDinv, &h->gPack, &h->gVec, &h->eK, &h->eSig, &h->eVec, &h->eSW};
+                     &h->fKuu, &h->fDinvU, &h->fA2, &h->fDinv2, &h->fVt, &h->fVs, &h->fVec, &h->fWt, &h->dXtmp, &h->gA, &h->gDinv, &h->gPack, &h->gBlk, &h->gVec, &h->eK, &h->eSig, &h->eVec, &h->eSW};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -374,7 +374,7 @@ static int free_all(Handle* h) {
     h->ozSl[w] = nullptr; h->ozSc[w] = nullptr; h->ozCap[w] = h->ozScCap[w] = 0;
   }
   h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = 0;
-  h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->cgA = h->cgDinv = h->cgPack = h->cgVec = h->ceK = h->ceSig = h->ceVec = h->ceSW = h->capUs = h->capLpost = h->capAlphaU = 0;
+  h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->cgA = h->cgDinv = h->cgPack = h->cgBlk = h->cgVec = h->ceK = h->ceSig = h->ceVec = h->ceSW = h->capUs = h->capLpost = h->capAlphaU = 0;
   return 0;
 }
 

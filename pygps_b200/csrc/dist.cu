@@ -275,6 +275,19 @@ int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp
   GPK_CK(h, cudaEventRecord(ev_fork, st));
   GPK_CK(h, cudaStreamWaitEvent(sp, ev_fork, 0));
   GPK_CK(h, cudaStreamWaitEvent(sc, ev_fork, 0));
+  // Blocked variant (GPK_DIST_OZAKI=1; off by default until it has been measured on 8 GPUs): inside a block of WD
+  // panels only the block's own columns get the immediate rank-128 DMMA updates; the broadcast panels are collected
+  // (full height, pitch ld) in a double-buffered block buffer, and after the block every rank slices it once and
+  // applies ONE rank-(WD*128) update on the int8 tensor cores to the columns it owns beyond the block
+  // (launch_oz_cyclic) - the column that becomes the next panel first.
+  const int WD = env_int("GPK_DIST_WD", 8);
+  const bool doz = env_int("GPK_DIST_OZAKI", 0) != 0 && env_int("GPK_OZAKI", 1) != 0 && T >= 4 * WD && WD >= 1 && WD <= 16;
+  double* PB = nullptr;
+  if (doz) {
+    GPK_TRY(ensure(h, &h->gBlk, &h->cgBlk, 2 * ld * (int64_t)WD * NB));
+    PB = h->gBlk;
+    GPK_TRY(oz_ensure(h, 0, ld, WD * NB));
+  }
   for (int k = 0; k < T; ++k) {
     const int o = k % G, lk = k / G;
     const int rem = T - k;                          // tile rows below the diagonal block, incl. the extra row
@@ -301,6 +314,51 @@ int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp
       GPK_CK(h, cudaStreamWaitEvent(st, ev_bcast[k], 0));
     } else {
       GPK_CK(h, cudaStreamWaitEvent(st, ev_packed[k], 0));
+    }
+    if (doz) {
+      const int kb = (k / WD) * WD, ke = (kb + WD < T) ? kb + WD : T;     // the block of panel k: [kb, ke)
+      double* blk = PB + (int64_t)((k / WD) & 1) * ld * WD * NB;
+      // panel k, full height, into its slot of the block buffer (rows (k+1)*NB .. ld)
+      GPK_CK(h, cudaMemcpy2DAsync(blk + (int64_t)(k - kb) * NB * ld + (int64_t)(k + 1) * NB, (size_t)ld * sizeof(double),
+                                  pack, (size_t)prow * sizeof(double), (size_t)prow * sizeof(double), NB,
+                                  cudaMemcpyDeviceToDevice, st));
+      // immediate updates: owned columns j in (k, ke) only
+      const int j0 = k + 1 + (((r - (k + 1)) % G) + G) % G;
+      int jstart = j0;
+      if (j0 == k + 1 && j0 < ke) {
+        GemmArgs u{};
+        u.A = pack; u.B = pack; u.C = h->gA + (int64_t)(k + 1) * NB + (int64_t)(j0 / G) * NB * ld;
+        u.lda = prow; u.ldb = prow; u.ldc = ld; u.K = NB; u.tri = 1; u.ti_off = k + 1; u.tj_off = j0; u.cstride = G;
+        GPK_TRY(launch_gemm_nt(h, st, 1, u, rem, 1));
+        GPK_CK(h, cudaEventRecord(ev_col[k + 1], st));
+        jstart = j0 + G;
+      }
+      if (jstart < ke) {
+        const int ncols = (ke - 1 - jstart) / G + 1;
+        GemmArgs u{};
+        u.A = pack; u.B = pack + (int64_t)(jstart - (k + 1)) * NB;
+        u.C = h->gA + (int64_t)(k + 1) * NB + (int64_t)(jstart / G) * NB * ld;
+        u.lda = prow; u.ldb = prow; u.ldc = ld; u.K = NB; u.tri = 1; u.ti_off = k + 1; u.tj_off = jstart; u.cstride = G;
+        GPK_TRY(launch_gemm_nt(h, st, 1, u, rem, ncols));
+      }
+      if (k == ke - 1 && ke < T) {
+        // the block is complete: one sliced rank-(ke-kb)*NB update of the owned columns >= ke, rows >= ke*NB
+        const int nrows = (T + 1 - ke) * NB, kw = (ke - kb) * NB;
+        GPK_TRY(launch_oz_slice(h, 0, st, blk + (int64_t)ke * NB, ld, nrows, kw));
+        const int jf = ke + (((r - ke) % G) + G) % G;                     // first owned column >= ke
+        if (jf < T) {
+          int ncols = (T - 1 - jf) / G + 1, cfirst = jf - ke;
+          double* C = h->gA + (int64_t)ke * NB + (int64_t)(jf / G) * NB * ld;
+          if (jf == ke) {                                                  // this rank owns the next panel: that column first
+            GPK_TRY(launch_oz_cyclic(h, 0, st, C, ld, nrows, kw, 1, cfirst, G));
+            GPK_CK(h, cudaEventRecord(ev_col[ke], st));
+            C += (int64_t)NB * ld; cfirst += G; --ncols;
+          }
+          GPK_TRY(launch_oz_cyclic(h, 0, st, C, ld, nrows, kw, ncols, cfirst, G));
+        }
+      }
+      GPK_CK(h, cudaEventRecord(ev_upd[k], st));
+      continue;
     }
     // update the owned columns j > k:  C[:, j] -= P[rows >= j] * P[j]^T
     const int j0 = k + 1 + (((r - (k + 1)) % G) + G) % G;

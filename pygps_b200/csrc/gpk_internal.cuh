@@ -119,6 +119,7 @@ struct Handle {
   double* gA = nullptr; int64_t cgA = 0;        // local columns of the (np+128) x np augmented matrix
   double* gDinv = nullptr; int64_t cgDinv = 0;  // inverses of the owned diagonal blocks
   double* gPack = nullptr; int64_t cgPack = 0;  // packed panel being broadcast
+  double* gBlk = nullptr; int64_t cgBlk = 0;    // blocked variant: the panels of the current block, full height (x2)
   double* gVec = nullptr; int64_t cgVec = 0;
   // int8 tensor-core trailing update (ozaki.cu): slices + row exponents of the current panel block
   // (two sets: [0] level-1 updates on s_main, [1] level-2 updates on s_panel, which run concurrently)
@@ -191,6 +192,8 @@ int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int6
                     int ntot = 0);
 int launch_oz_ex(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
                  int skip00, int ti_min, int trap, int cmode /*0: C -= PP', 1: C = PP', 2: C += PP'*/);
+int launch_oz_cyclic(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int ncols, int cfirst,
+                     int cs);
 int launch_oz_gemm_stacked(Handle* h, int which, cudaStream_t st, double* Cab, int64_t ldc, int nb, int na, int kw);
 int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
                    int skip00 = 0);

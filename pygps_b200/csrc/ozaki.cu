@@ -168,6 +168,9 @@ struct OzArgs {
   int ti_min;         // only row tiles >= ti_min (rectangular products: operand rows stacked [B; A], see launch_oz_gemm)
   int trap;           // contraction of row tile ti starts at k = 128*ti (U U' of an upper-triangular U)
   int cmode;          // 0: C -= P P' ; 1: C = +P P' (C is not read) ; 2: C += P P'   (1, 2: pipelined epilogue only)
+  int rect_cols;      // > 0: block-cyclic columns (multi-GPU): the launch covers rect_cols LOCAL 128-column blocks c,
+  int cs, cfirst;     //      global block jb = cfirst + c*cs (relative to the sliced rows); tiles with ti < jb are skipped;
+                      //      C columns are the packed local ones (c*128 + ...), slices / scales / masks use jb
   long long* dbg;     // optional per-CTA clock stamps [5] (debug timing), else nullptr
 };
 
@@ -205,6 +208,34 @@ __device__ __forceinline__ void oz_decode(int idx, int nt, int jb0, int jb1, int
   }
 }
 
+// rectangular enumeration over (row tile, local column block), bands of OZ_BAND row tiles innermost-rows like oz_decode
+__device__ __forceinline__ void oz_decode_rect(int idx, int nt, int ncols, int& ti, int& tjv) {
+  int r_lo = 0;
+  for (;;) {
+    const int rows = min(OZ_BAND, nt - r_lo), cnt = 2 * rows * ncols;
+    if (idx < cnt || r_lo + rows >= nt) { tjv = idx / rows; ti = r_lo + idx % rows; return; }
+    idx -= cnt;
+    r_lo += rows;
+  }
+}
+
+// tile index -> row tile ti, GLOBAL 64-column tile tjg (slices, scales, diagonal mask), LOCAL 64-column tile tjl (C address).
+// Returns false for a tile that is not part of the launch (above the diagonal in block-cyclic mode).
+template <int GEN>
+__device__ __forceinline__ bool oz_tile(const OzArgs& a, int idx, int nt, int& ti, int& tjg, int& tjl) {
+  if (GEN && a.rect_cols > 0) {
+    int tjv;
+    oz_decode_rect(idx, nt, a.rect_cols, ti, tjv);
+    const int jb = a.cfirst + (tjv >> 1) * a.cs;
+    tjg = 2 * jb + (tjv & 1);
+    tjl = tjv;
+    return ti >= jb;
+  }
+  oz_decode(idx, nt, a.jb0, a.jb1, a.ti_min, ti, tjg);
+  tjl = tjg;
+  return true;
+}
+
 // GEN = 0: the Cholesky's update (C -= P P', full contraction) with the flags folded away at compile time - the
 // generalised form costs 38 registers and 5 % of the hot kernel; GEN = 1: trap / cmode honoured.
 template <int S, int RB, int EPI, int GEN>
@@ -230,6 +261,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
     oz_decode(tile0, nt, a.jb0, a.jb1, a.ti_min, ti0, tj0);
     if (ti0 == 0 && tj0 < 2) return;
   }
+  if (GEN && a.rect_cols > 0) {                            // (host guarantees tpc == 1 in block-cyclic mode)
+    int ti0, tg0, tl0;
+    if (!oz_tile<GEN>(a, tile0, nt, ti0, tg0, tl0)) return;
+  }
 
   if (warp == OZ_EPI_WARPS + 1) {
     // the producer initialises the barriers itself and requests the first OZ_ST stages (all of the first tile:
@@ -241,8 +276,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       if (tile0 < tile1) {
-        int ti, tj;
-        oz_decode(tile0, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
+        int ti, tj, tjl;
+        oz_tile<GEN>(a, tile0, nt, ti, tj, tjl);
         const int8_t* gA = a.sl + (size_t)ti * 128 * S * 32;
         const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
         const int ks0 = a_trap ? 4 * ti : 0;             // (the last row tile still has nk - ks0 = 4 = OZ_ST k-steps)
@@ -272,8 +307,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
     if (elect_one()) {
       int it = 0;
       for (int tile = tile0; tile < tile1; ++tile) {
-        int ti, tj;
-        oz_decode(tile, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
+        int ti, tj, tjl;
+        oz_tile<GEN>(a, tile, nt, ti, tj, tjl);
         const int8_t* gA = a.sl + (size_t)ti * 128 * S * 32;
         const int8_t* gB = a.sl + (size_t)tj * OZ_BN * S * 32;
         for (int ks = a_trap ? 4 * ti : 0; ks < nk; ++ks, ++it) {
@@ -297,8 +332,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
         if (tcount > 0) { mbar_wait(&tfree, (tcount - 1) & 1); tc_fence_after(); }
         int ks0 = 0;
         if (a_trap) {
-          int ti, tj;
-          oz_decode(tile, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
+          int ti, tj, tjl;
+          oz_tile<GEN>(a, tile, nt, ti, tj, tjl);
           ks0 = 4 * ti;
         }
         if constexpr (ATMEM) {
@@ -361,11 +396,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
     const uint32_t tw = tbase + ((uint32_t)(q4 * 32) << 16) + chalf;
     int tcount = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++tcount) {
-      int ti, tj;
-      oz_decode(tile, nt, a.jb0, a.jb1, a.ti_min, ti, tj);
-      const int gi = ti * 128 + q4 * 32 + lane, gj0 = tj * OZ_BN + chalf;
+      int ti, tj, tjl;
+      oz_tile<GEN>(a, tile, nt, ti, tj, tjl);
+      const int gi = ti * 128 + q4 * 32 + lane, gj0 = tj * OZ_BN + chalf;      // global (mask, scales)
       const double si = a.sc[gi];
-      double* crow = a.C + gi + (int64_t)gj0 * a.ldc;
+      double* crow = a.C + gi + (int64_t)(tjl * OZ_BN + chalf) * a.ldc;        // local packed column
       if constexpr (EPI == 0) {
         // pull this thread's 32 C entries towards L2 now; they are read after the accumulators are complete
 #pragma unroll
@@ -543,12 +578,26 @@ static int oz_syrk_g(Handle* h, cudaStream_t st, const OzArgs& a) {
 
 template <int S, int RB, int EPI>
 static int oz_syrk_e(Handle* h, cudaStream_t st, const OzArgs& a) {
-  return (a.trap || a.cmode) ? oz_syrk_g<S, RB, EPI, 1>(h, st, a) : oz_syrk_g<S, RB, EPI, 0>(h, st, a);
+  return (a.trap || a.cmode || a.rect_cols) ? oz_syrk_g<S, RB, EPI, 1>(h, st, a) : oz_syrk_g<S, RB, EPI, 0>(h, st, a);
 }
 
 template <int S, int RB>
 static int oz_syrk_t(Handle* h, cudaStream_t st, const OzArgs& a) {
   return oz_cfg().epi ? oz_syrk_e<S, RB, 1>(h, st, a) : oz_syrk_e<S, RB, 0>(h, st, a);
+}
+
+// Block-cyclic columns (sharded factorisation, dist.cu): C holds `ncols` LOCAL 128-column blocks of this rank, local block c
+// being global block cfirst + c*cs of the sliced rows; lower(C) -= P P' on the tiles ti >= global block (the others exit).
+int launch_oz_cyclic(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int ncols, int cfirst,
+                     int cs) {
+  const OzCfg c = oz_cfg();
+  const int nt = n / 128;
+  if (ncols <= 0) return 0;
+  if (c.tpc != 1 || !c.epi || cs < 1 || cfirst < 0 || cfirst + (ncols - 1) * cs >= nt) return GPK_ERR_ARG;
+  if ((size_t)kw * 7 * 16384 >= 2147483648ull) return GPK_ERR_ARG;
+  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, 0, ncols, 2 * nt * ncols, 1, 0, 0, 0, 0, ncols, cs, cfirst, h->ozDbg};
+  if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
+  return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
 }
 
 // C(lower triangle, 128-column blocks [jb0, jb1)) -= P·P' from the current slices
@@ -566,7 +615,7 @@ int launch_oz_ex(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, 
   long long nt64 = 0;
   for (int jb = jb0; jb < jb1; ++jb) nt64 += 2 * (nt - (jb > ti_min ? jb : ti_min));
   const int ntiles = (int)nt64;
-  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, skip00, ti_min, trap, cmode, h->ozDbg};
+  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, skip00, ti_min, trap, cmode, 0, 0, 0, h->ozDbg};
   if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
   return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
 }

@@ -22,7 +22,7 @@ WORKER = textwrap.dedent("""
     eng = _lib.Engine(ctx.local_rank)
     ctx.shard_engine(eng)
     out = {}
-    for N, D in ((300, 3), (2048, 8), (4096, 8)):
+    for N, D in ((300, 3), (2048, 8), (4096, 8), (4500, 5)):
         rng = np.random.default_rng(0)
         X = rng.standard_normal((N, D))
         y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
@@ -55,13 +55,14 @@ def _reference(N, D):
     return float(nlZ), float(np.abs(alpha).sum()), float(alpha[7, 0])
 
 
-def _run(world, tmp_path, port):
+def _run(world, tmp_path, port, extra_env=None):
     script = tmp_path / "w.py"
     script.write_text(WORKER)
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port))
+        env.update(extra_env or {})
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.PIPE, text=True))
     outs = [p.communicate(timeout=600) for p in procs]
@@ -75,14 +76,17 @@ def _run(world, tmp_path, port):
     return res
 
 
+@pytest.mark.parametrize("blocked", [0, 1])
 @pytest.mark.parametrize("world", [1, 2])
-def test_sharded_eval_matches_single_gpu(world, tmp_path, golden):
+def test_sharded_eval_matches_single_gpu(world, blocked, tmp_path, golden):
+    """blocked=1: GPK_DIST_OZAKI=1 - panels collected in blocks of 8, one sliced int8 update of the block-cyclic columns
+    per block (active from 32 panels: the N=4096 and the ragged N=4500 cases)."""
     if _gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    res = _run(world, tmp_path, 29560 + world)
+    res = _run(world, tmp_path, 29560 + world + 10 * blocked, {"GPK_DIST_OZAKI": str(blocked)})
     assert len(res) == world
     g = golden("synthetic")
-    for N, D in ((300, 3), (2048, 8), (4096, 8)):
+    for N, D in ((300, 3), (2048, 8), (4096, 8), (4500, 5)):
         ref = _reference(N, D)
         for rank in range(world):
             got = res[rank][str(N)]
