@@ -76,11 +76,7 @@ def _run(world, tmp_path, port, extra_env=None):
     return res
 
 
-@pytest.mark.parametrize("blocked", [0, 1])
-@pytest.mark.parametrize("world", [1, 2])
-def test_sharded_eval_matches_single_gpu(world, blocked, tmp_path, golden):
-    """blocked=1: GPK_DIST_OZAKI=1 - panels collected in blocks of 8, one sliced int8 update of the block-cyclic columns
-    per block (active from 32 panels: the N=4096 and the ragged N=4500 cases)."""
+def _check_sharded(world, blocked, tmp_path, golden):
     if _gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
     res = _run(world, tmp_path, 29560 + world + 10 * blocked, {"GPK_DIST_OZAKI": str(blocked)})
@@ -93,6 +89,11 @@ def test_sharded_eval_matches_single_gpu(world, blocked, tmp_path, golden):
             assert abs(got[0] - ref[0]) < 1e-10 * abs(ref[0]), (world, rank, N, got, ref)
             assert abs(got[1] - ref[1]) < 1e-8 * abs(ref[1]) and abs(got[2] - ref[2]) < 1e-7 * max(1, abs(ref[2]))
     assert abs(res[0]["2048"][0] - float(g["c2_2048_nlZ"])) < 1e-9 * abs(float(g["c2_2048_nlZ"]))
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_sharded_eval_matches_single_gpu(world, tmp_path, golden):
+    _check_sharded(world, 0, tmp_path, golden)
 
 
 FITC_WORKER = textwrap.dedent("""
