@@ -342,3 +342,90 @@ def pad_spd(Amat):
     P = np.asfortranarray(np.eye(np_))
     P[:n, :n] = Amat
     return P
+
+
+def oz_decode_rect(idx, nt, ncols, band=16):
+    """ozaki.cu oz_decode_rect: CTA index -> (row tile, virtual 64-column tile) over the full nt x ncols rectangle."""
+    r_lo = 0
+    while True:
+        rows = min(band, nt - r_lo)
+        cnt = 2 * rows * ncols
+        if idx < cnt or r_lo + rows >= nt:
+            return r_lo + idx % rows, idx // rows
+        idx -= cnt
+        r_lo += rows
+
+
+def oz_cyclic_tiles(nt, ncols, cfirst, cs):
+    """launch_oz_cyclic / oz_tile: the tiles a block-cyclic launch computes: (row tile, GLOBAL 64-column tile, LOCAL
+    64-column tile) for every CTA whose row tile is not above its global column block."""
+    out = []
+    for idx in range(2 * nt * ncols):
+        ti, tjv = oz_decode_rect(idx, nt, ncols)
+        jb = cfirst + (tjv >> 1) * cs
+        if ti >= jb:
+            out.append((ti, 2 * jb + (tjv & 1), tjv))
+    return out
+
+
+def potrf_dist_blocked(A, G, WD):
+    """dist.cu, blocked variant (GPK_DIST_OZAKI=1), all G ranks simulated in one process: block columns are owned
+    cyclically (column j by rank j % G, packed locally), panels are factored by their owner and "broadcast"; inside a
+    block of WD panels only the block's own columns get the immediate rank-128 updates, after the block every rank applies
+    ONE rank-(WD*128) update to the columns it owns beyond the block, tile by tile as launch_oz_cyclic enumerates them.
+    A: padded (np,np) F-order, lower triangle valid.  Returns the factor (np,np) assembled from the ranks' columns."""
+    np_ = A.shape[0]
+    T = np_ // NB
+    loc = [np.asfortranarray(A[:, [c for j in range(r, T, G) for c in range(j * NB, (j + 1) * NB)]]) for r in range(G)]
+
+    def col(r, j):                                  # rank r's packed storage of global block column j
+        lj = j // G
+        return loc[r][:, lj * NB:(lj + 1) * NB]
+
+    for kb in range(0, T, WD):
+        ke = min(kb + WD, T)
+        blk = np.zeros((np_, (ke - kb) * NB))       # the block buffer (every rank holds the same copy after the broadcasts)
+        for k in range(kb, ke):
+            o = k % G
+            ck = col(o, k)
+            s = slice(k * NB, (k + 1) * NB)
+            L, Li, _, info = diag_block(ck[s, :])
+            assert info == 0
+            ck[s, :] = L
+            ck[(k + 1) * NB:, :] = ck[(k + 1) * NB:, :] @ Li.T
+            pan = ck[(k + 1) * NB:, :].copy()       # the broadcast
+            blk[(k + 1) * NB:, (k - kb) * NB:(k - kb + 1) * NB] = pan
+            for r in range(G):                      # immediate updates: owned columns j in (k, ke)
+                for j in range(k + 1, ke):
+                    if j % G != r:
+                        continue
+                    pj = pan[(j - k - 1) * NB:(j - k) * NB, :]
+                    cj = col(r, j)
+                    upd = pan[(j - k - 1) * NB:, :] @ pj.T
+                    rows = slice(j * NB, np_)
+                    tile = cj[rows, :]
+                    tile[NB:, :] -= upd[NB:, :]
+                    tile[:NB, :] -= np.tril(upd[:NB, :])
+        if ke < T:
+            nt = T - ke                             # (the device has one more row tile: the y - m row of the augmented matrix)
+            P = blk[ke * NB:, :]
+            full = P @ P.T
+            for r in range(G):
+                jf = ke + ((r - ke) % G + G) % G
+                if jf >= T:
+                    continue
+                ncols = (T - 1 - jf) // G + 1
+                C = loc[r][ke * NB:, (jf // G) * NB:]          # rows from the slice origin, local columns from jf's
+                for ti, tjg, tjl in oz_cyclic_tiles(nt, ncols, jf - ke, G):
+                    rs, cg, cl = slice(ti * NB, (ti + 1) * NB), slice(tjg * 64, (tjg + 1) * 64), slice(tjl * 64, (tjl + 1) * 64)
+                    u = full[rs, cg]
+                    if ti * NB < (tjg + 1) * 64:               # tile touches the diagonal: rows >= columns only
+                        gi = np.arange(ti * NB, (ti + 1) * NB)[:, None]
+                        gj = np.arange(tjg * 64, (tjg + 1) * 64)[None, :]
+                        u = np.where(gi >= gj, u, 0.0)
+                    C[rs, cl] -= u
+    out = np.zeros_like(A)
+    for r in range(G):
+        for lj, j in enumerate(range(r, T, G)):
+            out[:, j * NB:(j + 1) * NB] = loc[r][:, lj * NB:(lj + 1) * NB]
+    return np.tril(out)

@@ -204,3 +204,23 @@ def test_stacked_operand_product_matches_fp64():
     ref = C0 - A @ B.T
     den = np.abs(A) @ np.abs(B).T
     assert np.max(np.abs(C - ref) / den) < 1e-14
+
+
+@pytest.mark.parametrize("nt,ncols,cfirst,cs", [(20, 5, 0, 3), (37, 9, 2, 4), (9, 9, 0, 1), (18, 2, 1, 8)])
+def test_block_cyclic_tile_enumeration(nt, ncols, cfirst, cs):
+    """launch_oz_cyclic: every tile {local block c, row tile ti >= cfirst + c*cs} exactly once, with the global column
+    tile for slices / masks and the packed local one for the C address."""
+    got = br.oz_cyclic_tiles(nt, ncols, cfirst, cs)
+    want = {(ti, 2 * (cfirst + c * cs) + hh, 2 * c + hh) for c in range(ncols) for hh in (0, 1)
+            for ti in range(cfirst + c * cs, nt)}
+    assert len(got) == len(set(got)) and set(got) == want
+
+
+@pytest.mark.parametrize("G,WD,n", [(1, 3, 1280), (2, 3, 1536), (3, 4, 1408), (4, 2, 1100)])
+def test_blocked_sharded_factorisation_matches_lapack(G, WD, n):
+    """The blocked variant of the sharded factorisation (immediate rank-128 updates inside a block of WD panels, one
+    delayed rank-(WD*128) update of the block-cyclic columns per block), G ranks simulated in one process."""
+    A0 = _spd(n, seed=4)
+    L = br.potrf_dist_blocked(br.pad_spd(A0), G, WD)
+    Lref = np.linalg.cholesky(A0)
+    assert np.max(np.abs(L[:n, :n] - Lref)) <= 1e-11 * np.max(np.abs(Lref))
