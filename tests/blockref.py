@@ -205,13 +205,51 @@ def oz_syrk(C, P, S=7, RB=8):
     C[L] -= upd[L]
 
 
-def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=None):
+def oz_split_fixed(P, e, S=7, RB=8):
+    """Digits of P with GIVEN row exponents e (|P[i,:]| <= 2^(e_i-1)): the fixed-scale slicing of DESIGN section 8 item 2."""
+    x = np.ldexp(P, -e[:, None])
+    assert np.abs(x).max() <= 0.5
+    q = np.rint(x * 2.0 ** (S * RB)).astype(np.int64)
+    d = np.empty((S,) + P.shape, dtype=np.int8)
+    for t in range(S - 1, -1, -1):
+        lo = q & ((1 << RB) - 1)
+        dd = np.where(lo >= (1 << (RB - 1)), lo - (1 << RB), lo)
+        d[t] = dd
+        q = (q - dd) >> RB
+    assert (q == 0).all()
+    return d
+
+
+def oz_update_from_digits(C, dr, dc, sr, sc_, S=7, RB=8, lower=True):
+    """C (rows x cols) -= (sum of digit products) scaled: dr [S, rows, k], dc [S, cols, k] digits, sr / sc_ row scales."""
+    acc = np.zeros(C.shape)
+    for m in range(S - 1, -1, -1):
+        G = sum(dr[t].astype(np.int64) @ dc[m - t].astype(np.int64).T for t in range(m + 1))
+        assert np.abs(G).max() < 2 ** 31
+        acc = acc * 2.0 ** -RB + G
+    upd = (acc * sr[:, None]) * sc_[None, :]
+    if lower:
+        C -= np.tril(upd)
+    else:
+        C -= upd
+
+
+def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=None, fixed_scale=False):
     """api.cu potrf_device (stream order flattened): three-level blocking - level-1 blocks of W1 panels (W1=0: same as
     the sub-blocks), sub-blocks of W panels, single panels.  oz: trailing updates through oz_syrk.
+    fixed_scale (with oz; NOT on the device yet - the executable specification of DESIGN section 8 item 2): row i is
+    sliced with the scale 2^ceil(log2 sqrt(A_ii)) known before the factorisation (|L_ij| <= sqrt(A_ii)), every sub-block's
+    panels are sliced ONCE when they are finished, and the same digits serve the level-2 update of the block's other
+    columns and the level-1 update of the trailing matrix (no per-update slicing, no row-maximum pass).
     A: padded (np,np) F-order, lower triangle valid; the factor overwrites it.
     Returns Dinv list, logdet parts, info, z."""
     np_ = A.shape[0]
     T = np_ // NB
+    fix_e = None
+    if fixed_scale:
+        _, ex = np.frexp(np.sqrt(np.diag(A).copy()))
+        fix_e = (ex + 1).astype(np.int64)
+    digits = {}                          # (k0, k1) -> digits [S, rows >= k1*NB, (k1-k0)*NB] of a finished sub-block
     Dinv = [None] * T
     parts = np.zeros(T)
     info = 0
@@ -233,7 +271,22 @@ def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=No
         pan = A[rows0 * NB:, k0 * NB:k1 * NB]
         Ct = A[rows0 * NB:, rows0 * NB:]
         ncols = cols_end - rows0
-        if oz:
+        if oz and fixed_scale:
+            # digits of every finished sub-block inside [k0, k1), rows >= rows0*NB (a suffix of what was sliced)
+            parts_ = []
+            for (a0, a1), d in sorted(digits.items()):
+                if a0 >= k0 and a1 <= k1:
+                    parts_.append(d[:, (rows0 - a1) * NB:, :])
+            d = np.concatenate(parts_, axis=2)
+            assert d.shape[2] == (k1 - k0) * NB
+            scl = np.ldexp(1.0, fix_e[rows0 * NB:] - 8)
+            for tj in range(ncols):
+                cs_ = slice(tj * NB, (tj + 1) * NB)
+                rs_ = slice(tj * NB, None)
+                blk = Ct[rs_, cs_]
+                oz_update_from_digits(blk, d[:, rs_, :], d[:, cs_, :], scl[rs_], scl[cs_], lower=False)
+                # the diagonal tile only keeps its lower triangle (the strict upper part of A is never read)
+        elif oz:
             full = Ct.copy()
             oz_syrk(full, pan)
             for tj in range(ncols):
@@ -283,6 +336,8 @@ def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=No
                         gemm_nt(1, A[t0:, t0:], pan, pan, NB, rem - 1, inner - 1, tri=1)
                 if b is not None:
                     trsv_fwd(A, Dinv, b, z, p, T)
+            if oz and fixed_scale and se < T:
+                digits[(sb, se)] = oz_split_fixed(A[se * NB:, sb * NB:se * NB], fix_e[se * NB:])
             if se < pe:
                 update(se, pe, sb, se)          # level-2: the rest of the block's columns
         rem = T - pe
@@ -300,6 +355,7 @@ def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=No
                 A[h, h] = mine                  # (device: oz_syrk skip00 / the split DMMA launches never touch the tile)
             else:
                 update(pe, T, pb, pe)           # level-1: the whole trailing matrix (device: next block's columns first)
+            digits.clear()
     return Dinv, parts, info, z
 
 
