@@ -71,8 +71,10 @@ int gpk_create(int device, gpk_handle* out);
 int gpk_destroy(gpk_handle h);
 const char* gpk_last_error(gpk_handle h);          /* text of the last CUDA error */
 int gpk_last_stats(gpk_handle h, gpk_stats* out);
-/* profile != 0: time every trailing-update launch with events (serialises the
- * look-ahead; for roofline measurement only). */
+/* profile != 0: two timing events are recorded on the trailing-update stream
+ * around each level-1 update (gpk_stats.syrk_ms / syrk_flops).  Nothing is
+ * synchronised and no stream dependency is added, so the look-ahead schedule -
+ * and the evaluation time - are the same with and without it. */
 int gpk_set_profile(gpk_handle h, int profile);
 
 /* ---- cov.*.getCovMatrix / getDerMatrix ---------------------------------- *
@@ -94,9 +96,16 @@ int gpk_cov_matrix(gpk_handle h, int kind, int matern_d,
  * C-order UPPER factor with an exactly zero strict lower triangle, A = R'R.
  * This is jitchol(A).T as the reference uses it (Core/inf.py:362).  The factor
  * stays resident on the handle for gpk_potrs.  logdet_half = sum(log(diag R)).
- * gpk_potrs: X = (R'R)^-1 B for B (n,nrhs) - solve_chol(R,B).               */
+ * gpk_set_factor: make a factor computed elsewhere resident (solve_chol(R,B)
+ * with an R that is not the last gpk_potrf result; post.L of a posterior kept
+ * on the host, Core/gp.py:404-416): R (n,n) C-order upper; info > 0 = first
+ * non-positive diagonal entry.
+ * gpk_potrs: X = (R'R)^-1 B for B (n,nrhs) - solve_chol(R,B) - by two
+ * triangular sweeps over the resident factor.  n must equal the resident
+ * factor's order (GPK_ERR_ARG otherwise): B and X_out are n x nrhs.          */
 int gpk_potrf(gpk_handle h, const double* A, int64_t n, double* R_out, double* logdet_half);
-int gpk_potrs(gpk_handle h, const double* B, int64_t nrhs, double* X_out);
+int gpk_set_factor(gpk_handle h, const double* R, int64_t n, double* logdet_half);
+int gpk_potrs(gpk_handle h, const double* B, int64_t n, int64_t nrhs, double* X_out);
 
 /* ---- inf.Exact.evaluate (Core/inf.py:353-384) --------------------------- *
  * gpk_set_data uploads the training inputs once (GP.setData, Core/gp.py:131). */

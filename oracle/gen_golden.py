@@ -289,8 +289,50 @@ def classification():
     np.savez_compressed(os.path.join(OUT, "classification.npz"), **s)
 
 
+def c4_big():
+    """SURVEY 8(c)/(d)'s larger pins of config 4: (N,M) = (32768,512) -> nlZ 85900.043566, (65536,1024) -> 170971.078457."""
+    s = {}
+    for N, M in ((32768, 512), (65536, 1024)):
+        rng = np.random.default_rng(0)
+        X = rng.standard_normal((N, 8))
+        y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+        U = rng.standard_normal((M, 8))
+        Xs = np.random.default_rng(1).standard_normal((300, 8))
+        m = pyGPs.GPR_FITC()
+        m.setPrior(kernel=pyGPs.cov.RBF(np.log(2.0), 0.0), inducing_points=U)
+        run_model(m, X, y, Xs, "c4_%d_%d" % (N, M), s, keep_L=False)
+        print("c4 big", N, M, repr(s["c4_%d_%d_nlZ" % (N, M)]), flush=True)
+        np.savez_compressed(os.path.join(OUT, "synthetic_c4big.npz"), **s)
+
+
+def c5_big():
+    """SURVEY 8(c)/(d)'s pin of config 5: N=1024, D=16, RBF(log 4, 0), Erf -> nlZ 344.43995473 in 4 sweeps."""
+    s = {}
+    N = 1024
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((N, 16))
+    lab = np.sign(X[:, :1] + 0.5 * X[:, 1:2] + 0.3 * rng.standard_normal((N, 1)))
+    lab[lab == 0] = 1
+    m = pyGPs.GPC()
+    m.setPrior(kernel=pyGPs.cov.RBF(np.log(4.0), 0.0))
+    nlZ, dn, post = m.getPosterior(X, lab)
+    Xs = np.random.default_rng(1).standard_normal((64, 16))
+    out = m.predict(Xs)
+    tag = "c5_%d" % N
+    s[tag + "_nlZ"] = np.float64(nlZ); s[tag + "_dcov"] = np.array(dn.cov); s[tag + "_alpha"] = post.alpha
+    s[tag + "_sW"] = post.sW; s[tag + "_ym"] = out[0]; s[tag + "_ys2"] = out[1]; s[tag + "_fm"] = out[2]
+    s[tag + "_fs2"] = out[3]
+    print(tag, repr(nlZ), flush=True)
+    np.savez_compressed(os.path.join(OUT, "classification_c5big.npz"), **s)
+
+
 if __name__ == "__main__":
-    if "--only-classification" in sys.argv:
+    if "--c4big" in sys.argv or "--c5big" in sys.argv:
+        if "--c5big" in sys.argv:
+            c5_big()
+        if "--c4big" in sys.argv:
+            c4_big()
+    elif "--only-classification" in sys.argv:
         classification()
     else:
         kat_regression()

@@ -54,7 +54,8 @@ PROTOTYPES = [
     ("gpk_set_profile", _I, [_H, _I]),
     ("gpk_cov_matrix", _I, [_H, _I, _I, c_double_p, _I, c_double_p, _L, c_double_p, _L, _I, _I, _I, c_double_p]),
     ("gpk_potrf", _I, [_H, c_double_p, _L, c_double_p, c_double_p]),
-    ("gpk_potrs", _I, [_H, c_double_p, _L, c_double_p]),
+    ("gpk_set_factor", _I, [_H, c_double_p, _L, c_double_p]),
+    ("gpk_potrs", _I, [_H, c_double_p, _L, _L, c_double_p]),
     ("gpk_set_data", _I, [_H, c_double_p, _L, _I]),
     ("gpk_exact_eval", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, _I,
                             c_double_p, c_double_p, c_double_p, c_double_p]),
@@ -116,8 +117,22 @@ def as_f64(a, name="array"):
     return a
 
 
+def _no_engine():
+    return None
+
+
 class Engine(object):
-    """One GPU handle.  Not re-entrant; one in-flight call at a time."""
+    """One GPU handle.  Not re-entrant; one in-flight call at a time.
+
+    A handle cannot be copied or sent to another process: copy.deepcopy / pickle of an object that holds one
+    (a model, its inference method) yields None in its place, and the copy creates its own handle on first use
+    - reference models are plain Python objects and survive deepcopy / joblib / multiprocessing, so must these."""
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_no_engine, ())
 
     def __init__(self, device=None):
         self._lib = load()
@@ -202,10 +217,25 @@ class Engine(object):
         self._check(rc, "gpk_potrf")
         return R, ld.value
 
+    def set_factor(self, R):
+        """Make the upper factor R (A = R'R) the resident one (solve_chol with a factor that is not on the GPU)."""
+        R = as_f64(R, "R")
+        if R.shape[0] != R.shape[1]:
+            raise Exception("factor must be square")
+        self._retire_factor()
+        ld = ctypes.c_double(0.0)
+        rc = self._lib.gpk_set_factor(self._h, _dp(R), R.shape[0], ctypes.byref(ld))
+        if rc > 0:
+            raise np.linalg.LinAlgError("not a Cholesky factor: non-positive diagonal element")
+        self._check(rc, "gpk_set_factor")
+        return ld.value
+
     def potrs(self, B):
         B = as_f64(B, "B")
         X = np.empty_like(B)
-        rc = self._lib.gpk_potrs(self._h, _dp(B), B.shape[1], _dp(X))
+        rc = self._lib.gpk_potrs(self._h, _dp(B), B.shape[0], B.shape[1], _dp(X))
+        if rc == -1:
+            raise Exception("Wrong sizes of matrix arguments in solve_chol.py")
         self._check(rc, "gpk_potrs")
         return X
 

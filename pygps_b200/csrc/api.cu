@@ -357,7 +357,7 @@ int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::
 static int free_all(Handle* h) {
   double** ptrs[] = {&h->dX, &h->dXs, &h->dScale, &h->dA, &h->dDinv, &h->dB, &h->dZ, &h->dAlpha, &h->dR, &h->dScal,
                      &h->dU, &h->dW, &h->dP, &h->dTmp, &h->dUin, &h->dUs, &h->dLpost, &h->dAlphaU,
-                     &h->fKuu, &h->fDinvU, &h->fA2, &h->fDinv2, &h->fVt, &h->fVs, &h->fVec, &h->fWt, &h->dXtmp, &h->gA, &h->gDinv, &h->gPack, &h->gBlk, &h->gVec, &h->eK, &h->eSig, &h->eVec, &h->eSW};
+                     &h->dDinvT, &h->fKuu, &h->fDinvU, &h->fA2, &h->fDinv2, &h->fVt, &h->fVs, &h->fVec, &h->fWt, &h->dXtmp, &h->gA, &h->gDinv, &h->gPack, &h->gBlk, &h->gVec, &h->eK, &h->eSig, &h->eVec, &h->eSW};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -373,7 +373,8 @@ static int free_all(Handle* h) {
     if (h->ozSc[w]) cudaFree(h->ozSc[w]);
     h->ozSl[w] = nullptr; h->ozSc[w] = nullptr; h->ozCap[w] = h->ozScCap[w] = 0;
   }
-  h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = 0;
+  h->capA = h->capU = h->capW = h->capP = h->capTmp = h->capUin = h->capDinvT = 0;
+  h->lt_valid = false;
   h->cKuu = h->cDinvU = h->cA2 = h->cDinv2 = h->cVt = h->cVs = h->cVec = h->cWt = h->capXtmp = h->cgA = h->cgDinv = h->cgPack = h->cgBlk = h->cgVec = h->ceK = h->ceSig = h->ceVec = h->ceSW = h->capUs = h->capLpost = h->capAlphaU = 0;
   return 0;
 }
@@ -406,6 +407,7 @@ static int alloc_problem(Handle* h, int64_t n, int D) {
 
 void stats_begin(Handle* h) {
   std::memset(&h->stats, 0, sizeof(h->stats));
+  h->lt_valid = false;     // every entry point may overwrite the factor or the work buffers gpk_potrs caches things in
 }
 
 int check_handle(gpk_handle hh, Handle** out) {
@@ -432,6 +434,26 @@ int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_ti
       u.C = P + (int64_t)(k + 1) * NB * ldp;
       u.lda = ldp; u.ldb = lda; u.ldc = ldp; u.K = NB; u.tri = 0;
       GPK_TRY(launch_gemm_nt(h, st, 1, u, row_tiles, T - k - 1));
+    }
+  }
+  return 0;
+}
+
+// Backward: P <- P * L^-1 for right-hand sides held transposed (one per ROW of P), block column by block column from the
+// last.  The products need L[k, 0:k] as the B operand of an NT product, i.e. rows of L' : Lt is the explicit transpose
+// of the factor (upper triangular, pitch ldt) and DinvT the transposed block inverses, both made once per factor.
+int sweep_backward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* Lt, int64_t ldt,
+                   const double* DinvT, int T) {
+  for (int k = T - 1; k >= 0; --k) {
+    GemmArgs t{};                                     // X_k = P_k * L_kk^-1 = P_k * (DinvT_k)'
+    t.A = P + (int64_t)k * NB * ldp; t.B = DinvT + (int64_t)k * NB * NB; t.C = P + (int64_t)k * NB * ldp;
+    t.lda = ldp; t.ldb = NB; t.ldc = ldp; t.K = NB; t.tri = 0;
+    GPK_TRY(launch_gemm_nt(h, st, 0, t, row_tiles, 1));
+    if (k > 0) {
+      GemmArgs u{};                                   // P[:, 0:k] -= X_k * L[k, 0:k] ;  B(j, kk) = L[k*NB+kk, j] = Lt[j, k*NB+kk]
+      u.A = P + (int64_t)k * NB * ldp; u.B = Lt + (int64_t)k * NB * ldt; u.C = P;
+      u.lda = ldp; u.ldb = ldt; u.ldc = ldp; u.K = NB; u.tri = 0;
+      GPK_TRY(launch_gemm_nt(h, st, 1, u, row_tiles, k));
     }
   }
   return 0;
@@ -975,39 +997,80 @@ int gpk_potrf(gpk_handle hh, const double* A, int64_t n, double* R_out, double* 
   return 0;
 }
 
-int gpk_potrs(gpk_handle hh, const double* B, int64_t nrhs, double* X_out) {
+// Upload a factor computed elsewhere (post.L of a posterior kept on the host, Core/gp.py:404-416) as the resident factor:
+// R (n,n) C-order upper, A = R'R.  Only the block inverses and the log-determinant are computed (one launch).
+int gpk_set_factor(gpk_handle hh, const double* R, int64_t n, double* logdet_half) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!R || n <= 0) return GPK_ERR_ARG;
+  const int64_t pn = round_up(n, NB);
+  const int T = (int)(pn / NB);
+  cudaStream_t st = h->s_main;
+  stats_begin(h);
+  h->has_post = false; h->has_fitc = false; h->pn = 0;
+  if (pn != h->np || !h->dXs) {
+    h->n = 0;
+    GPK_TRY(alloc_problem(h, n, h->D > 0 ? h->D : 1));
+    h->n = 0;
+  }
+  GPK_TRY(ensure(h, &h->dA, &h->capA, pn * pn));
+  GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, n * n));
+  GPK_CK(h, cudaMemcpyAsync(h->dTmp, R, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  GPK_CK(h, cudaMemsetAsync(h->dInfo, 0, 4 * sizeof(int), st));
+  // the C-order upper factor read as column-major IS the lower factor L = R'; padding rows/columns are the identity
+  GPK_TRY(launch_pad_sym(h, st, h->dTmp, n, h->dA, pn));
+  GPK_TRY(launch_diag_invert(h, st, h->dA, pn, h->dDinv, h->dScal, h->dInfo, T));
+  GPK_TRY(launch_sum_parts(h, st, h->dScal, T, h->dScal + T));
+  GPK_CK(h, cudaMemcpyAsync(h->hPinned, h->dScal + T, sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaMemcpyAsync(h->hPinned + 2048, h->dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaStreamSynchronize(st));
+  h->stats.h2d_bytes = n * n * (int64_t)sizeof(double);
+  const int info = *reinterpret_cast<int*>(h->hPinned + 2048);
+  if (logdet_half) *logdet_half = h->hPinned[0];
+  if (info != 0) return info;          // non-positive diagonal entry: not a Cholesky factor
+  h->pn = n;
+  return 0;
+}
+
+// X = (R'R)^-1 B by two triangular sweeps over the resident factor (never the explicit inverse): with the right-hand
+// sides transposed (one per row), Xt = Bt L^-T L^-1.  The backward sweep reads L' (one bandwidth-bound transpose),
+// which is cached on the handle until the factor changes, so repeated solves cost 2 n^2 nrhs flops each.
+int gpk_potrs(gpk_handle hh, const double* B, int64_t n_rows, int64_t nrhs, double* X_out) {
   Handle* h;
   GPK_TRY(check_handle(hh, &h));
   if (h->pn <= 0) return GPK_ERR_STATE;
   if (!B || !X_out || nrhs <= 0) return GPK_ERR_ARG;
+  if (n_rows != h->pn) return GPK_ERR_ARG;            // B must have exactly as many rows as the resident factor
   const int64_t n = h->pn, pn = round_up(n, NB);
   const int T = (int)(pn / NB);
   cudaStream_t st = h->s_main;
+  const bool cached = h->lt_valid;
   stats_begin(h);
-  // B (n,nrhs) C-order == (nrhs x n) column-major with pitch nrhs: exactly the transposed layout the sweeps use.
-  // X = A^-1 B = B' * (U U') row-wise, with U = L^-T:  Xt = Bt * U * U'.
-  const int64_t rp = round_up(nrhs, NB);
   GPK_TRY(ensure(h, &h->dU, &h->capU, pn * pn));
-  GPK_TRY(ensure(h, &h->dW, &h->capW, pn * pn));
-  GPK_TRY(ensure(h, &h->dP, &h->capP, 2 * rp * pn));
-  double* P0 = h->dP;
-  double* P1 = h->dP + rp * pn;
-  GPK_CK(h, cudaMemsetAsync(P0, 0, (size_t)rp * pn * sizeof(double), st));
-  GPK_CK(h, cudaMemcpy2DAsync(P0, (size_t)rp * sizeof(double), B, (size_t)nrhs * sizeof(double),
-                              (size_t)nrhs * sizeof(double), (size_t)n, cudaMemcpyHostToDevice, st));
-  // Ainv (lower) = U U'
-  GPK_TRY(inverse_factor_T(h, st, h->dU, h->dA, pn, h->dDinv));
-  GemmArgs v{};
-  v.A = h->dU; v.B = h->dU; v.C = h->dW; v.lda = pn; v.ldb = pn; v.ldc = pn; v.K = (int)pn; v.tri = 2;
-  GPK_TRY(launch_gemm_nt(h, st, 0, v, T, T));
-  // symmetrise into dU (full), then Xt = Bt * Ainv' (= Bt * Ainv)
-  GPK_TRY(launch_compact_sym(h, st, h->dW, pn, pn, h->dU));
-  GemmArgs x{};
-  x.A = P0; x.B = h->dU; x.C = P1; x.lda = rp; x.ldb = pn; x.ldc = rp; x.K = (int)pn; x.tri = 0;
-  GPK_TRY(launch_gemm_nt(h, st, 0, x, (int)(rp / NB), T));
-  GPK_CK(h, cudaMemcpy2DAsync(X_out, (size_t)nrhs * sizeof(double), P1, (size_t)rp * sizeof(double),
-                              (size_t)nrhs * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost, st));
+  GPK_TRY(ensure(h, &h->dDinvT, &h->capDinvT, pn * NB));
+  if (!cached) {
+    GPK_TRY(launch_transpose(h, st, h->dA, pn, 0, h->dU, pn, 0, pn, pn, 1));
+    GPK_TRY(launch_transpose(h, st, h->dDinv, NB, (int64_t)NB * NB, h->dDinvT, NB, (int64_t)NB * NB, NB, NB, T));
+  }
+  // B (n,nrhs) C-order == (nrhs x n) column-major with pitch nrhs: exactly the transposed layout the sweeps use
+  const int64_t chunk = 8192;                          // right-hand sides per pass (bounds the work buffer)
+  const int64_t rp_max = round_up(nrhs < chunk ? nrhs : chunk, NB);
+  GPK_TRY(ensure(h, &h->dP, &h->capP, rp_max * pn));
+  for (int64_t lo = 0; lo < nrhs; lo += chunk) {
+    const int64_t m = (nrhs - lo < chunk) ? nrhs - lo : chunk, rp = round_up(m, NB);
+    double* P0 = h->dP;
+    GPK_CK(h, cudaMemsetAsync(P0, 0, (size_t)rp * pn * sizeof(double), st));
+    GPK_CK(h, cudaMemcpy2DAsync(P0, (size_t)rp * sizeof(double), B + lo, (size_t)nrhs * sizeof(double),
+                                (size_t)m * sizeof(double), (size_t)n, cudaMemcpyHostToDevice, st));
+    GPK_TRY(sweep_forward(h, st, P0, rp, (int)(rp / NB), h->dA, pn, h->dDinv, T));
+    GPK_TRY(sweep_backward(h, st, P0, rp, (int)(rp / NB), h->dU, pn, h->dDinvT, T));
+    GPK_CK(h, cudaMemcpy2DAsync(X_out + lo, (size_t)nrhs * sizeof(double), P0, (size_t)rp * sizeof(double),
+                                (size_t)m * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
   GPK_CK(h, cudaStreamSynchronize(st));
+  h->lt_valid = true;
+  h->stats.h2d_bytes = n * nrhs * (int64_t)sizeof(double);
+  h->stats.d2h_bytes = n * nrhs * (int64_t)sizeof(double);
   return 0;
 }
 

@@ -110,6 +110,8 @@ struct Handle {
   double* dXtmp = nullptr; int64_t capXtmp = 0;
   // standalone potrf state
   int64_t pn = 0;
+  bool lt_valid = false;                       // dU holds L' and dDinvT the transposed block inverses of the CURRENT factor
+  double* dDinvT = nullptr; int64_t capDinvT = 0;
   // EP (classification) state; see ep.cu
   bool post_ep = false;
   double *eK = nullptr, *eSig = nullptr, *eVec = nullptr, *eSW = nullptr;
@@ -157,6 +159,8 @@ int launch_prescale(Handle* h, cudaStream_t st, const double* X, int64_t n, int6
                     const double* scale, int divide, double premul, double* out);
 int launch_diag(Handle* h, cudaStream_t st, double* Ablk, int64_t lda, double* Dinv, double* logdet_slot,
                 int* info, int gidx0, long long* dbg_clk = nullptr);
+int launch_diag_invert(Handle* h, cudaStream_t st, double* A, int64_t lda, double* Dinv, double* logdet_parts, int* info,
+                       int T);
 int launch_trsv_fwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* b,
                     double* z, int k, int T);
 int launch_trsv_bwd(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* z,
@@ -181,6 +185,8 @@ int launch_dnlz_sw(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int 
 int launch_colscale_inplace(Handle* h, cudaStream_t st, double* P, int64_t ld, int64_t rows, int64_t cols,
                             const double* s);
 int launch_copy(Handle* h, cudaStream_t st, const double* src, double* dst, int64_t n);
+int launch_transpose(Handle* h, cudaStream_t st, const double* src, int64_t lds, int64_t sstride, double* dst,
+                     int64_t ldd, int64_t dstride, int64_t rows, int64_t cols, int batch);
 int launch_fill_random(Handle* h, cudaStream_t st, double* p, int64_t n, unsigned seed);
 int bench_dmma(Handle* h, int shape, int warps, int iters, double* tflops, double* ms_out);
 int gemm_init(Handle* h);
@@ -204,6 +210,8 @@ void stats_begin(Handle* h);
 int check_handle(gpk_handle hh, Handle** out);
 int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A, int64_t lda,
                   const double* Dinv, int T);
+int sweep_backward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* Lt, int64_t ldt,
+                   const double* DinvT, int T);
 int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv);
 int inverse_factor_T_oz(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv);
 int oz_gemm_nt(Handle* h, cudaStream_t st, double* C, int64_t ldc, const double* A, int64_t lda, int na, const double* B,

@@ -243,6 +243,40 @@ __global__ void __launch_bounds__(1024) dnlz_finish_kernel(const double* __restr
   }
 }
 
+// dst[c + r*ldd] = src[r + c*lds] for `batch` matrices (rows x cols) spaced sstride / dstride apart: 32x32 tiles through
+// shared memory so that both sides are coalesced
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ src, int64_t lds, int64_t sstride,
+                                                        double* __restrict__ dst, int64_t ldd, int64_t dstride,
+                                                        int64_t rows, int64_t cols) {
+  __shared__ double t[32][33];
+  src += (int64_t)blockIdx.z * sstride;
+  dst += (int64_t)blockIdx.z * dstride;
+  const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t r = r0 + tx, c = c0 + ty + 8 * k;
+    t[ty + 8 * k][tx] = (r < rows && c < cols) ? src[r + c * lds] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t c = c0 + tx, r = r0 + ty + 8 * k;
+    if (r < rows && c < cols) dst[c + r * ldd] = t[tx][ty + 8 * k];
+  }
+}
+
+int launch_transpose(Handle* h, cudaStream_t st, const double* src, int64_t lds, int64_t sstride, double* dst,
+                     int64_t ldd, int64_t dstride, int64_t rows, int64_t cols, int batch) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return 0;
+  if ((cols + 31) / 32 > 65535 || batch > 65535) return GPK_ERR_ARG;
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32), (unsigned)batch);
+  transpose_kernel<<<grid, 256, 0, st>>>(src, lds, sstride, dst, ldd, dstride, rows, cols);
+  h->stats.launches++;
+  GPK_CK(h, cudaGetLastError());
+  return 0;
+}
+
 static inline int grid_for(int64_t total) {
   int64_t b = (total + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;

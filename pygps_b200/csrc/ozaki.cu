@@ -66,6 +66,14 @@ __device__ __forceinline__ unsigned long long oz_digits(double x) {
   }
 }
 
+// max(m, |v|) that does NOT lose NaN/Inf (fmax ignores NaN): a non-finite entry turns the row maximum into +Inf, which
+// the slice kernel maps to a NaN row scale, so every product that touches the row comes out NaN - the NaN/Inf of a
+// panel propagate into C like they do in fp64 arithmetic (include/gpk.h: "NaN/Inf propagate into outputs").
+__device__ __forceinline__ double oz_absmax(double m, double v) {
+  const double av = fabs(v);
+  return (av <= 1.0e300) ? fmax(m, av) : __longlong_as_double(0x7ff0000000000000ll);
+}
+
 // Row maxima for the split-k slicing: grid (rows/32, ksplit), every CTA reduces its k-range and merges with an atomic
 // max on the bit pattern (non-negative doubles order like unsigned integers).  mx must be zero on entry.
 __global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict__ P, int64_t lda, int kw,
@@ -78,13 +86,13 @@ __global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict
   const double* prow = P + r0 + r;
   double m = 0.0;
 #pragma unroll 4
-  for (int k = kb + kq; k < ke; k += 8) m = fmax(m, fabs(prow[(int64_t)k * lda]));
+  for (int k = kb + kq; k < ke; k += 8) m = oz_absmax(m, prow[(int64_t)k * lda]);
   red[kq][r] = m;
   __syncthreads();
   if (kq == 0) {
 #pragma unroll
     for (int q = 1; q < 8; ++q) m = fmax(m, red[q][r]);
-    if (!(m >= 0.0)) m = 0.0;                                // NaN rows keep the scale 1 (they stay NaN in the product)
+    // a NaN/Inf entry made m = +Inf (oz_absmax): its bit pattern orders above every finite value
     atomicMax(mx + r0 + r, (unsigned long long)__double_as_longlong(m));
   }
 }
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   double m = 0.0;
   if (mx == nullptr) {
 #pragma unroll 4
-    for (int k = kq; k < kw; k += 8) m = fmax(m, fabs(prow[(int64_t)k * lda]));
+    for (int k = kq; k < kw; k += 8) m = oz_absmax(m, prow[(int64_t)k * lda]);
     red[kq][r] = m;
     __syncthreads();
   }
@@ -119,13 +127,15 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     }
     // |x| < 2^(ilogb+1)  ->  |x| * 2^-(ilogb+2) < 0.5 ; exponents clamped so that 2^(e-RB) stays a normal double
     int e = 0;
-    if (m > 0.0 && m < 1.0e150) {
+    const bool bad = !(m < 1.0e150);          // NaN/Inf in the row (oz_absmax), or a magnitude the digits cannot carry
+    if (m > 0.0 && !bad) {
       e = ilogb(m) + 2;
       if (scalbn(m, -e) > 0.48) ++e;         // head room for the carry into the leading digit
     }
     if (e < -500) e = -500;
     sh_e[r] = e;
-    if (blockIdx.y == 0) sc[row0 + r0 + r] = scalbn(1.0, e - RB);
+    // bad rows: NaN scale -> every entry of C in that row and column becomes NaN in the epilogue
+    if (blockIdx.y == 0) sc[row0 + r0 + r] = bad ? __longlong_as_double(0x7ff8000000000000ll) : scalbn(1.0, e - RB);
   }
   __syncthreads();
   const int e = sh_e[r];

@@ -43,6 +43,16 @@ __device__ __forceinline__ void dmma8(double (&c)[4], const double (&a)[4], doub
 // One warp: acc(32 x 8*NT) += A(32 x K) * Bop(K x 8*NT), operands in shared memory.
 //   A(r,k)   = A[r + k*lda]                       (column-major rows of S)
 //   Bop(k,n) = B[n*sbn + k*sbk]                   (sbn=1,sbk=ld: B^T of a column-major matrix; sbn=ld,sbk=1: B itself)
+// *p = the smallest non-zero info seen (0 = none yet): LAPACK reports the FIRST failing pivot
+__device__ __forceinline__ void info_min(int* p, int v) {
+  int old = atomicCAS(p, 0, v);
+  while (old != 0 && old > v) {
+    const int prev = atomicCAS(p, old, v);
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
 template <int NT>
 __device__ __forceinline__ void warp_mma32(double (&acc)[2][NT][4], const double* A, int lda, const double* B, int sbn,
                                            int sbk, int K, int lane) {
@@ -92,10 +102,20 @@ __device__ __forceinline__ void frag_zero(double (&acc)[2][NT][4]) {
       for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.0;
 }
 
+// INV_ONLY = true: the block already holds a lower Cholesky factor (gpk_set_factor: a factor uploaded by the caller);
+// phase 1 is skipped, only 1/diag, the log-determinant share and the block inverse are produced, one CTA per diagonal
+// block (blockIdx.x) so the whole factor is prepared in ONE launch.
+template <bool INV_ONLY>
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ Dinv,
                   double* __restrict__ logdet_slot, int* __restrict__ info, int gidx0, long long* dbg_clk) {
   extern __shared__ __align__(16) double dsm[];
+  if (INV_ONLY) {
+    Ablk += (int64_t)blockIdx.x * DB * (1 + lda);
+    Dinv += (int64_t)blockIdx.x * DB * DB;
+    logdet_slot += blockIdx.x;
+    gidx0 += blockIdx.x * DB;
+  }
   int dbg_i = 0;
 #define DBG_T() do { if (dbg_clk && threadIdx.x == 0) dbg_clk[dbg_i++] = clock64(); } while (0)
   DBG_T();
@@ -121,8 +141,23 @@ potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ D
   __syncthreads();
   DBG_T();
 
+  if (INV_ONLY) {
+    if (tid < DB) {
+      const double d = S_(tid, tid);
+      rdiag[tid] = 1.0 / d;
+      if (!(d > 0.0)) info_min(&s_info, gidx0 + tid + 1);
+    }
+    if (warp == 0) {
+      double lg = 0.0;
+      for (int i = lane; i < DB; i += 32) lg += log(S_(i, i));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(FULL, lg, o);
+      if (lane == 0) s_logdet = lg;
+    }
+    __syncthreads();
+  }
   // ---------------- phase 1: blocked Cholesky, inner block 32 ----------------
-  for (int jb = 0; jb < DB / IB; ++jb) {
+  for (int jb = 0; jb < (INV_ONLY ? 0 : DB / IB); ++jb) {
     const int j0 = jb * IB;
     if (warp == 0) {
       // 32x32 diagonal block: ONE warp, one matrix row per lane in registers, square-root-free (LDL') elimination.
@@ -259,7 +294,7 @@ potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ D
   }
   if (tid == 0) {
     *logdet_slot = s_logdet;
-    if (s_info != 0) atomicCAS(info, 0, s_info);
+    if (s_info != 0) info_min(info, s_info);
   }
   __syncthreads();
   DBG_T();
@@ -559,7 +594,8 @@ int launch_trsv_bwd_all(Handle* h, cudaStream_t st, const double* A, int64_t lda
 }
 
 int diag_init(Handle* h) {
-  GPK_CK(h, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+  GPK_CK(h, cudaFuncSetAttribute(potrf_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+  GPK_CK(h, cudaFuncSetAttribute(potrf_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
   GPK_CK(h, cudaFuncSetAttribute(trsv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM));
   GPK_CK(h, cudaFuncSetAttribute(trsv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM));
   GPK_CK(h, cudaFuncSetAttribute(trsv_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SMEM));
@@ -568,7 +604,16 @@ int diag_init(Handle* h) {
 
 int launch_diag(Handle* h, cudaStream_t st, double* Ablk, int64_t lda, double* Dinv, double* logdet_slot, int* info,
                 int gidx0, long long* dbg_clk) {
-  potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
+  potrf_diag_kernel<false><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
+  h->stats.launches++;
+  GPK_CK(h, cudaGetLastError());
+  return 0;
+}
+
+// Dinv_k = inv(L_kk), logdet_parts[k] = sum(log diag L_kk) for all T diagonal blocks of a factor that is already there
+int launch_diag_invert(Handle* h, cudaStream_t st, double* A, int64_t lda, double* Dinv, double* logdet_parts, int* info,
+                       int T) {
+  potrf_diag_kernel<true><<<T, DIAG_THREADS, DIAG_SMEM, st>>>(A, lda, Dinv, logdet_parts, info, 0, nullptr);
   h->stats.launches++;
   GPK_CK(h, cudaGetLastError());
   return 0;

@@ -158,6 +158,11 @@ class GP(object):
         spec = getattr(post, '_spec', None)
         if spec is None or spec[0] != kindname or not post._resident():
             return False
+        # the GPU posterior stands in for `post` only if post still IS that evaluation's result for these inputs
+        if post._vsig is None or inf._vec_signature(post) != post._vsig:
+            return False
+        if self.x is None or post._xsig is None or inf._x_signature(self.x) != post._xsig:
+            return False
         dev = self.covfunc._device_spec()
         if dev is None:
             return False
@@ -187,14 +192,20 @@ class GP(object):
         return ymu, ys2, fmu, fs2, (None if ys is None else lp_all), lp_all
 
     def _predict_host_posterior(self, post, xs):
-        """Posterior given as host arrays (predict_with_posterior, composite kernels): the
-        reference's batch loop (Core/gp.py:395-419) with the solves on the GPU."""
+        """Posterior given as host arrays (predict_with_posterior, a caller-edited posterior): the reference's
+        batch loop (Core/gp.py:395-419); the factor is uploaded ONCE (gpk_set_factor) and every batch is two
+        triangular sweeps on the GPU (gpk_potrs)."""
+        from . import _lib
         covfunc, meanfunc, x = self.covfunc, self.meanfunc, self.x
         alpha, L, sW = post.alpha, post.L, post.sW
         if len(L) == 0:
             K = covfunc.getCovMatrix(x=x, mode='train')
             L = jitchol((np.eye(x.shape[0]) + np.dot(sW, sW.T) * K).T).T
         Ltril = np.all(np.tril(L, -1) == 0)
+        eng = None
+        if Ltril:
+            eng = _lib.shared_engine()
+            eng.set_factor(np.asarray(L, dtype=np.float64))
         ns = xs.shape[0]
         fmu = np.zeros((ns, 1))
         fs2 = np.zeros((ns, 1))
@@ -207,7 +218,7 @@ class GP(object):
             if Ltril:
                 # colsum(V*V) with V = L'^-1 (sW*Ks) equals colsum(B * (L'L)^-1 B), B = sW*Ks
                 B = sW * Ks
-                fs2[ids] = kss - (B * solve_chol(L, B)).sum(axis=0).reshape(-1, 1)
+                fs2[ids] = kss - (B * eng.potrs(B)).sum(axis=0).reshape(-1, 1)
             else:
                 fs2[ids] = kss + (Ks * np.dot(L, Ks)).sum(axis=0).reshape(-1, 1)
             fs2[ids] = np.maximum(fs2[ids], 0)

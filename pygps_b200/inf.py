@@ -32,6 +32,18 @@ def _x_signature(x):
     return (x.shape, float(x.flat[0]), float(x.flat[-1]), float(x.sum()))
 
 
+def _vec_signature(post):
+    """Fingerprint of the posterior vectors as the evaluation produced them: a caller-edited alpha / sW no longer
+    matches, and prediction then uses the host arrays the way the reference does (Core/gp.py:402-419)."""
+    a, w = np.asarray(post.alpha), np.asarray(post.sW)
+    return (a.shape, w.shape, float(a.sum()), float(np.abs(a).sum()), float(w.sum()))
+
+
+def _seal(post, x):
+    post._x, post._xsig = x, _x_signature(x)
+    post._vsig = _vec_signature(post)
+
+
 class postStruct(object):
     """Posterior parameters alpha, sW, L (Core/inf.py:59-89).
 
@@ -48,6 +60,7 @@ class postStruct(object):
         self._spec = None        # what the resident factor was built from (for predict / rebuild)
         self._x = None           # training inputs the factor was built from
         self._xsig = None
+        self._vsig = None        # fingerprint of alpha / sW as evaluated (see _vec_signature)
 
     # -- lazy factor ----------------------------------------------------------
     def _resident(self):
@@ -87,8 +100,15 @@ class postStruct(object):
         other.sW = np.array(self.sW, copy=True)
         other._L = None if self._L is None else np.array(self._L, copy=True)
         other._engine, other._epoch, other._n, other._spec = self._engine, self._epoch, self._n, self._spec
-        other._x, other._xsig = self._x, self._xsig
+        other._x, other._xsig, other._vsig = self._x, self._xsig, self._vsig
         return other
+
+    def __getstate__(self):
+        # pickling (joblib, multiprocessing): the factor is materialised, the GPU handle stays behind
+        d = dict(self.__dict__)
+        d["_L"] = self._materialize()
+        d["_engine"], d["_epoch"] = None, -1
+        return d
 
     def __repr__(self):
         return ("posterior: to get the parameters of the posterior distribution use:\n"
@@ -178,7 +198,7 @@ class Exact(Inference):
         post._L = None
         post._engine, post._epoch, post._n = eng, eng.epoch, n
         post._spec = ('exact', kind, md, tuple(hyp), float(likfunc.hyp[0]))
-        post._x, post._xsig = x, _x_signature(x)
+        _seal(post, x)
         if nargout > 1:
             if nargout > 2:
                 dnlZ = dnlZStruct(meanfunc, covfunc, likfunc)
@@ -251,6 +271,7 @@ class EP(Inference):
         post._L = None
         post._engine, post._epoch, post._n = eng, eng.epoch, n
         post._spec = ('ep', kind, md, tuple(hyp), 0.0)
+        _seal(post, x)
         post.L                                    # EP evaluations take seconds: fetch the factor now (no rebuild path)
         if nargout > 1:
             if nargout > 2:
@@ -295,6 +316,7 @@ class FITC_Exact(Inference):
         post.L = Lp
         post._engine, post._epoch, post._n = eng, eng.epoch, xu.shape[0]
         post._spec = ('fitc', kind, md, tuple(hyp), float(likfunc.hyp[0]))
+        _seal(post, x)
         if nargout > 1:
             if nargout > 2:
                 dnlZ = dnlZStruct(meanfunc, covfunc, likfunc)

@@ -8,6 +8,13 @@ import pygps_b200 as pg            # noqa: E402
 from oracle import gp_oracle as go  # noqa: E402
 
 
+from parity_report import check   # noqa: E402
+
+# EP is a fixed-point iteration that the reference stops when nlZ moves by less than 1e-4 between sweeps
+# (Core/inf.py:756,761); both implementations run the same number of sweeps from the same start, so they are compared
+# at rounding level, not at the iteration's own tolerance.
+
+
 def rel(a, b):
     a = np.asarray(a, float); b = np.asarray(b, float)
     return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
@@ -19,22 +26,29 @@ def test_kat5_classification_fixture(golden):
     m = pg.GPC()
     nlZ, dn, post = m.getPosterior(x, y)
     assert type(nlZ) is np.float64
-    assert abs(nlZ - float(g["kat5_nlZ"])) < 1e-6 * abs(float(g["kat5_nlZ"])), (nlZ, g["kat5_nlZ"])
+    check("kat5 nlZ", nlZ, float(g["kat5_nlZ"]), 1e-8)
     assert abs(nlZ - 50.454379530956) < 1e-4
-    assert rel(dn.cov, g["kat5_dcov"]) < 1e-5, (dn.cov, g["kat5_dcov"])
+    check("kat5 dcov", dn.cov, g["kat5_dcov"])
     assert dn.lik == [] and dn.mean == []
     assert post.alpha.shape == (120, 1) and post.sW.shape == (120, 1) and post.L.shape == (120, 120)
-    assert rel(post.alpha, g["kat5_alpha"]) < 1e-5 and rel(post.sW, g["kat5_sW"]) < 1e-5
-    assert np.all(np.tril(post.L, -1) == 0) and rel(post.L, g["kat5_L"]) < 1e-5
-    assert rel(m.inffunc.last_ttau, g["kat5_ttau"]) < 1e-5 and rel(m.inffunc.last_tnu, g["kat5_tnu"]) < 1e-5
+    check("kat5 alpha", post.alpha, g["kat5_alpha"])
+    check("kat5 sW", post.sW, g["kat5_sW"])
+    assert np.all(np.tril(post.L, -1) == 0)
+    check("kat5 post.L", post.L, g["kat5_L"])
+    check("kat5 ttau", m.inffunc.last_ttau, g["kat5_ttau"])
+    check("kat5 tnu", m.inffunc.last_tnu, g["kat5_tnu"])
     out = m.predict(xs, np.ones((xs.shape[0], 1)))
     for name, v in zip(("ym", "ys2", "fm", "fs2", "lp"), out):
-        assert rel(v, g["kat5_" + name]) < 1e-5, (name, rel(v, g["kat5_" + name]))
+        check("kat5 " + name, v, g["kat5_" + name])
 
 
-@pytest.mark.parametrize("N", [200, 512])
+@pytest.mark.parametrize("N", [200, 512, 1024])
 def test_c5_family_synthetic(golden, N):
-    g = golden("classification")
+    """N=1024 is the size of SURVEY 8(c)/(d)'s pin for config 5.  The golden is frozen from the unmodified reference
+    with the recipe in oracle/gen_golden.py:c5_big (nlZ 338.71384325684556); SURVEY's printed value (344.43995473)
+    came from an input variant its text does not record - the N=512 value of the same table (199.32798736) does
+    reproduce with this recipe and is asserted below."""
+    g = golden("classification" if N <= 512 else "classification_c5big")
     rng = np.random.default_rng(0)
     X = rng.standard_normal((N, 16))
     lab = np.sign(X[:, :1] + 0.5 * X[:, 1:2] + 0.3 * rng.standard_normal((N, 1)))
@@ -43,15 +57,20 @@ def test_c5_family_synthetic(golden, N):
     m.setPrior(kernel=pg.cov.RBF(np.log(4.0), 0.0))
     nlZ, dn, post = m.getPosterior(X, lab)
     tag = "c5_%d" % N
-    assert abs(nlZ - float(g[tag + "_nlZ"])) < 1e-6 * abs(float(g[tag + "_nlZ"])), (nlZ, g[tag + "_nlZ"])
-    assert rel(dn.cov, g[tag + "_dcov"]) < 1e-4
-    assert rel(post.alpha, g[tag + "_alpha"]) < 1e-4 and rel(post.sW, g[tag + "_sW"]) < 1e-4
+    check(tag + " nlZ", nlZ, float(g[tag + "_nlZ"]), 1e-8)
+    check(tag + " dcov", dn.cov, g[tag + "_dcov"])
+    check(tag + " alpha", post.alpha, g[tag + "_alpha"])
+    check(tag + " sW", post.sW, g[tag + "_sW"])
     Xs = np.random.default_rng(1).standard_normal((64, 16))
     out = m.predict(Xs)
-    assert rel(out[0], g[tag + "_ym"]) < 1e-4 and rel(out[2], g[tag + "_fm"]) < 1e-4 and rel(out[3], g[tag + "_fs2"]) < 1e-4
+    check(tag + " ym", out[0], g[tag + "_ym"])
+    check(tag + " fm", out[2], g[tag + "_fm"])
+    check(tag + " fs2", out[3], g[tag + "_fs2"])
     assert out[4] is None
     if N == 512:
         assert abs(float(g[tag + "_nlZ"]) - 199.32798736) < 1e-6          # BASELINE.md C5 scaled
+    if N == 1024:
+        assert abs(float(g[tag + "_nlZ"]) - 338.71384325684556) < 1e-9
 
 
 def test_warm_start_and_const_mean_match_the_oracle():
@@ -63,13 +82,14 @@ def test_warm_start_and_const_mean_match_the_oracle():
     nlZ1, dn1, post1 = m.getPosterior(X, lab)
     spec = ("rbfard", [0.3, 0.1, 0.5, 0.2, 0.4])
     rpost, rnlZ, rdn, extra = go.ep_evaluate(("const", 0.2), spec, X, lab, nargout=3)
-    assert abs(nlZ1 - rnlZ) < 1e-6 * abs(rnlZ)
-    assert rel(dn1.cov, rdn["cov"]) < 1e-4 and rel(dn1.mean, rdn["mean"]) < 1e-4
+    check("ep/ard+const nlZ", nlZ1, rnlZ, 1e-8)
+    check("ep/ard+const dcov", dn1.cov, rdn["cov"])
+    check("ep/ard+const dmean", dn1.mean, rdn["mean"])
     m.covfunc.hyp = [0.35, 0.1, 0.5, 0.2, 0.4]                     # second call warm-starts from the first
     nlZ2, dn2, _ = m.getPosterior(X, lab)
     spec2 = ("rbfard", [0.35, 0.1, 0.5, 0.2, 0.4])
     _, rnlZ2, _, _ = go.ep_evaluate(("const", 0.2), spec2, X, lab, nargout=3, last=(extra["ttau"], extra["tnu"]))
-    assert abs(nlZ2 - rnlZ2) < 1e-5 * abs(rnlZ2)
+    check("ep/warm start nlZ", nlZ2, rnlZ2)
 
 
 def test_labels_are_checked_and_shapes_follow_the_reference():

@@ -7,6 +7,8 @@ pytestmark = pytest.mark.gpu
 import pygps_b200 as pg            # noqa: E402
 from oracle import gp_oracle as go  # noqa: E402
 
+from parity_report import check, cond_tol   # noqa: E402
+
 TOL = 1e-6
 
 
@@ -15,23 +17,36 @@ def rel(a, b):
     return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
 
 
-def _check(m, g, tag, x, y, xs, L_tol=1e-5):
+def _fitc_cond(kernel, u, sn2):
+    """Condition number of Kuu + 1e-6 sn2... the matrix every FITC quantity is solved through (Core/inf.py:410:
+    Kuu + snu2*I with snu2 = 1e-6*sn2).  The reference's own LAPACK results carry O(cond * eps) relative error, so
+    agreement between two correct fp64 implementations is only defined to that level."""
+    Kuu = kernel.getCovMatrix(x=u, mode='train')
+    return float(np.linalg.cond(Kuu + 1e-6 * sn2 * np.eye(u.shape[0])))
+
+
+def _check(m, g, tag, x, y, xs):
     nlZ, dn, post = m.getPosterior(x, y)
     ref = float(g[tag + "_nlZ"])
-    assert type(nlZ) is np.float64 and abs(nlZ - ref) < 1e-8 * abs(ref), (tag, nlZ, ref)
+    assert type(nlZ) is np.float64
+    check(tag + " nlZ", nlZ, ref, 1e-8)
     M = m.u.shape[0]
     assert post.alpha.shape == (M, 1) and post.L.shape == (M, M) and post.sW.shape == (x.shape[0], 1)
-    assert rel(post.alpha, g[tag + "_alpha"]) < 1e-5, (tag, "alpha", rel(post.alpha, g[tag + "_alpha"]))
+    sn2 = float(np.exp(2 * m.likfunc.hyp[0]))
+    cond = _fitc_cond(m.covfunc.covfunc, m.u, sn2)
+    tol = cond_tol(cond)
+    why = None if tol <= 1e-6 else "cond(Kuu+snu2 I) = %.1e: 64*cond*eps" % cond
+    check(tag + " alpha", post.alpha, g[tag + "_alpha"], tol, why)
     if tag + "_L" in g.files:
-        assert rel(post.L, g[tag + "_L"]) < L_tol, (tag, "L", rel(post.L, g[tag + "_L"]))
+        check(tag + " post.L", post.L, g[tag + "_L"], tol, why)
     for got, key in ((dn.cov, "_dcov"), (dn.lik, "_dlik"), (dn.mean, "_dmean")):
         r = g[tag + key]
         assert len(got) == len(r)
         if len(r):
-            assert rel(got, r) < 1e-5, (tag, key, got, r)
+            check(tag + " dnlZ" + key, got, r, tol, why)
     out = m.predict(xs)
     for name, v in zip(("ym", "ys2", "fm", "fs2"), out[:4]):
-        assert rel(v, g[tag + "_" + name]) < 1e-5, (tag, name, rel(v, g[tag + "_" + name]))
+        check(tag + " " + name, v, g[tag + "_" + name], tol, why)
 
 
 def test_kat4_reference_fixture(golden):
@@ -46,9 +61,13 @@ def test_kat4_reference_fixture(golden):
     _check(m, g, "kat4b", g["x"], g["y"], g["xs"])
 
 
-@pytest.mark.parametrize("N,M", [(2000, 100), (4096, 256)])
+@pytest.mark.parametrize("N,M", [(2000, 100), (4096, 256), (32768, 512), (65536, 1024)])
 def test_c4_family_synthetic(golden, N, M):
-    g = golden("synthetic")
+    """(32768,512) and (65536,1024) are the sizes of SURVEY 8(c)/(d)'s larger pins.  The goldens are frozen from the
+    unmodified reference with the recipe of oracle/gen_golden.py:c4_big (nlZ 88689.35489999755 and
+    177869.87184098028); SURVEY's printed values (85900.043566, 170971.078457) came from an input variant its text
+    does not record (five obvious variants were tried; none reproduces them)."""
+    g = golden("synthetic" if N <= 4096 else "synthetic_c4big")
     rng = np.random.default_rng(0)
     X = rng.standard_normal((N, 8))
     y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
@@ -56,7 +75,7 @@ def test_c4_family_synthetic(golden, N, M):
     Xs = np.random.default_rng(1).standard_normal((300, 8))
     m = pg.GPR_FITC()
     m.setPrior(kernel=pg.cov.RBF(np.log(2.0), 0.0), inducing_points=U)
-    _check(m, g, "c4_%d_%d" % (N, M), X, y, Xs, L_tol=1e-4)
+    _check(m, g, "c4_%d_%d" % (N, M), X, y, Xs)
 
 
 def test_fitc_other_kernels_against_oracle():
@@ -69,11 +88,17 @@ def test_fitc_other_kernels_against_oracle():
         m.setPrior(kernel=kern, inducing_points=U)
         nlZ, dn, post = m.getPosterior(X, y)
         rpost, rnlZ, rdn = go.fitc_evaluate(("zero",), spec, U, np.log(0.1), X, y, 3)
-        assert abs(nlZ - rnlZ) < 1e-8 * abs(rnlZ)
-        assert rel(dn.cov, rdn["cov"]) < 1e-5 and rel(dn.lik, rdn["lik"]) < 1e-5
+        tag = "fitc/" + spec[0]
+        cond = _fitc_cond(kern, U, 0.01)
+        tol = cond_tol(cond)
+        why = None if tol <= 1e-6 else "cond(Kuu+snu2 I) = %.1e: 64*cond*eps" % cond
+        check(tag + " nlZ", nlZ, rnlZ, 1e-8)
+        check(tag + " dcov", dn.cov, rdn["cov"], tol, why)
+        check(tag + " dlik", dn.lik, rdn["lik"], tol, why)
         out = m.predict(Xs)
         ro = go.predict(("zero",), spec, np.log(0.1), X, rpost, Xs, xu=U)
-        assert rel(out[0], ro[0]) < 1e-5 and rel(out[1], ro[1]) < 1e-5
+        check(tag + " ym", out[0], ro[0], tol, why)
+        check(tag + " ys2", out[1], ro[1], tol, why)
 
 
 def test_fitc_shape_contract_of_the_reference():

@@ -218,3 +218,97 @@ def test_int8_sliced_trailing_update_matches_fp64(eng, n, kw):
     assert np.max(np.abs(out[L] - ref[L]) / den[L]) < 2e-14
     assert np.max(np.abs(out[L] - dm[L]) / den[L]) < 2e-14
     assert np.array_equal(np.triu(out, 1), np.triu(C, 1))
+
+
+def test_int8_update_propagates_nan_and_inf(eng):
+    """include/gpk.h: "NaN/Inf propagate into outputs".  The int8 slicing cannot represent a non-finite entry, so a
+    row that holds one gets a NaN scale: every entry of C in that row and column comes out NaN, exactly the footprint
+    a NaN has in the fp64 product; every other entry still equals the fp64 result."""
+    n, kw = 512, 256
+    rng = np.random.default_rng(77)
+    P = rng.standard_normal((n, kw))
+    P[37, 5] = np.nan
+    P[300, 100] = np.inf
+    P[411, 255] = -np.inf
+    C = rng.standard_normal((n, n)); C = C + C.T
+    out, _ = eng.dbg_oz_syrk(P, C, mode=0)
+    bad = np.zeros(n, bool); bad[[37, 300, 411]] = True
+    hit = bad[:, None] | bad[None, :]
+    lo = np.tril(np.ones((n, n), bool))
+    assert not np.isfinite(out[lo & hit]).any(), "a non-finite panel entry was silently dropped by the slicing"
+    Pz = np.where(np.isfinite(P), P, 0.0)
+    ref = C - Pz @ Pz.T
+    ok = lo & ~hit
+    assert np.isfinite(out[ok]).all()
+    assert np.allclose(out[ok], ref[ok], rtol=1e-12, atol=1e-12)
+
+
+def test_nan_reaches_the_factor_through_the_int8_path_at_n4096(eng):
+    """N=4096: the level-1 trailing updates run on the int8 tensor cores (oz_slice / oz_syrk).  A NaN in an OFF-diagonal
+    entry of A travels L[3000,17] -> (sliced panel row 3000) -> C[3000,3000] -> pivot 3001: info > 0, LinAlgError - what
+    LAPACK's dpotrf reports.  Before the slicing carried NaN the row was sliced as zeros and the factorisation
+    "succeeded" with garbage."""
+    n = 4096
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((n, 8))
+    from pygps_b200 import _lib
+    K = eng.cov_matrix(_lib.COV_RBF, 3, [np.log(2.0), 0.0], X, None, "train")
+    A = K / 0.01 + np.eye(n)
+    R, _ = eng.potrf(A)                                   # sane matrix: factorises
+    assert np.isfinite(R).all()
+    assert eng.stats()["launches"] > 0
+    A[3000, 17] = A[17, 3000] = np.nan
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.potrf(A)
+    A[3000, 17] = A[17, 3000] = np.inf
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.potrf(A)
+    # NaN in a target: the matrix is fine, nlZ and alpha become NaN (no abort, no exception)
+    y = np.sin(X.sum(1)); y[2500] = np.nan
+    eng.set_data(X)
+    nlZ, alpha, _, _ = eng.exact_eval(_lib.COV_RBF, 3, [np.log(2.0), 0.0], np.log(0.1), y, False)
+    assert np.isnan(nlZ) and np.isnan(alpha).any()
+
+
+def test_solve_chol_only_trusts_the_exact_resident_factor(eng):
+    """a slice / copy / edited copy of jitchol's result must not be solved with the resident factor."""
+    import pygps_b200 as pg
+    rng = np.random.default_rng(4)
+    n, k = 300, 170
+    X = rng.standard_normal((n, 3))
+    A = np.exp(-0.5 * ((X[:, None] - X[None]) ** 2).sum(-1)) + 0.1 * np.eye(n)
+    B = rng.standard_normal((n, 4))
+    L = pg.tools.jitchol(A)
+    assert not L.flags.writeable
+    ref = sla.cho_solve((np.asarray(L), True), B)
+    assert np.allclose(pg.tools.solve_chol(L.T, B), ref, rtol=1e-8, atol=1e-10)           # resident
+    # leading principal sub-factor: the factor of A[:k,:k]; must be solved as a k x k system
+    Xk = pg.tools.solve_chol(L[:k, :k].T, B[:k])
+    assert Xk.shape == (k, 4)
+    assert np.allclose(Xk, np.linalg.solve(A[:k, :k], B[:k]), rtol=1e-7, atol=1e-9)
+    # an edited copy is a different matrix
+    L2 = np.array(L) * 2.0
+    assert np.allclose(pg.tools.solve_chol(L2.T, B), ref / 4.0, rtol=1e-8, atol=1e-10)
+    # and the engine itself refuses right-hand sides of the wrong height
+    eng.potrf(A)
+    with pytest.raises(Exception):
+        eng.potrs(B[:k])
+
+
+@pytest.mark.parametrize("n,nrhs", [(130, 1), (700, 300), (1500, 1500)])
+def test_set_factor_and_sweeps_match_lapack(eng, n, nrhs):
+    """gpk_set_factor (upload R, block inverses in one launch) + gpk_potrs as two triangular sweeps."""
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((n, 4))
+    A = np.exp(-0.5 * ((X[:, None] - X[None]) ** 2).sum(-1) / 4.0) / 0.05 + np.eye(n)
+    R = np.linalg.cholesky(A).T
+    ld = eng.set_factor(np.ascontiguousarray(R))
+    assert abs(ld - np.log(np.diag(R)).sum()) < 1e-10 * max(1.0, abs(ld))
+    B = rng.standard_normal((n, nrhs))
+    ref = sla.cho_solve((R, False), B)
+    for _ in range(2):                                   # second call reuses the cached transpose
+        got = eng.potrs(B)
+        assert np.allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max()), _report("potrs", got, ref)
+    Rbad = R.copy(); Rbad[5, 5] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.set_factor(Rbad)

@@ -209,4 +209,8 @@ def test_bench_clock_sampler_windows_and_reference_arm_line():
     assert p.returncode == 0 and len(lines) == 1, (p.returncode, p.stdout[-300:], p.stderr[-300:])
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["value"] > 0 and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+    # the reference arm reports what it actually ran (a measured full-size evaluation, never an extrapolation) and
+    # the SAME config object as the GPU arm
+    assert d["steps"] >= 1 and abs(d["ms_per_step"] * d["value"] - 1e3) < 1e-6
+    assert d["config"] == bench.make_config(512, 8, 1)

@@ -144,6 +144,19 @@ def test_fitc_synthetic(golden):
     close(dn["lik"], g[tag + "_dlik"], rtol=1e-5)
 
 
+def test_fitc_larger_pin_size(golden):
+    """SURVEY 8(c)/(d) larger config-4 size (32768, 512) against the golden frozen from the unmodified reference."""
+    g = golden("synthetic_c4big")
+    N, M = 32768, 512
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((N, 8))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    U = rng.standard_normal((M, 8))
+    post, nlZ = go.fitc_evaluate(("zero",), ("rbf", [np.log(2.0), 0.0]), U, np.log(0.1), X, y, 2)
+    close(nlZ, g["c4_%d_%d_nlZ" % (N, M)], rtol=1e-9)
+    close(post["alpha"], g["c4_%d_%d_alpha" % (N, M)], rtol=1e-5, atol=1e-6 * np.abs(g["c4_%d_%d_alpha" % (N, M)]).max())
+
+
 def test_housing_published_value(golden):
     """doc/source/demoHousing.rst:30 publishes the optimised nlZ 214.46; the frozen run reproduces it."""
     g = golden("housing")
