@@ -65,6 +65,9 @@ typedef struct gpk_stats {
 int         gpk_version(void);
 const char* gpk_strerror(int code);
 int         gpk_device_count(int* count);
+/* free / total bytes of device memory: the host side routes an evaluation whose N x N factor does not fit one GPU to
+ * the sharded path (gpk_exact_eval_dist). */
+int         gpk_device_memory(int device, int64_t* free_bytes, int64_t* total_bytes);
 
 /* One handle = one GPU.  `device` is the CUDA ordinal. */
 int gpk_create(int device, gpk_handle* out);
@@ -170,6 +173,15 @@ int gpk_dist_init(gpk_handle h, const char* nccl_path, int rank, int world, cons
 int gpk_dist_finalize(gpk_handle h);
 int gpk_exact_eval_dist(gpk_handle h, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
                         const double* ymm, double* nlZ, double* alpha);
+/* Sharded GP.predict (Core/gp.py:404-419) and post.L: collective; replicates the distributed factor on every rank
+ * (one packed NCCL broadcast per block column, 4 N^2 bytes in total).  Afterwards gpk_predict / gpk_get_factor work
+ * on every rank WITHOUT further communication - the caller gives every rank its own share of the test points.   */
+int gpk_dist_gather_factor(gpk_handle h);
+/* Sharded inf.Exact.evaluate with derivatives (Core/inf.py:371-382; what optimize() calls): collective; as
+ * gpk_exact_eval_dist, then every rank forms its rows of (K/sn2+I)^-1 by two triangular sweeps against its replica
+ * of the factor and reduces Q o dK over them; one all-reduce of nhyp+1 scalars.  Outputs as gpk_exact_eval.       */
+int gpk_exact_eval_dist_der(gpk_handle h, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
+                            const double* ymm, double* nlZ, double* alpha, double* dcov, double* dlik);
 
 /* ---- measurement helpers (bench.py / tests only) ------------------------ */
 /* fp64 tensor-pipe micro-benchmark: shape 0=m8n8k4 1=m16n8k4 2=m16n8k8

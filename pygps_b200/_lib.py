@@ -47,6 +47,7 @@ PROTOTYPES = [
     ("gpk_version", _I, []),
     ("gpk_strerror", ctypes.c_char_p, [_I]),
     ("gpk_device_count", _I, [c_int_p]),
+    ("gpk_device_memory", _I, [_I, ctypes.POINTER(_L), ctypes.POINTER(_L)]),
     ("gpk_create", _I, [_I, ctypes.POINTER(_H)]),
     ("gpk_destroy", _I, [_H]),
     ("gpk_last_error", ctypes.c_char_p, [_H]),
@@ -70,6 +71,9 @@ PROTOTYPES = [
     ("gpk_dist_init", _I, [_H, ctypes.c_char_p, _I, _I, ctypes.c_char_p]),
     ("gpk_dist_finalize", _I, [_H]),
     ("gpk_exact_eval_dist", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, c_double_p, c_double_p]),
+    ("gpk_dist_gather_factor", _I, [_H]),
+    ("gpk_exact_eval_dist_der", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, c_double_p, c_double_p, c_double_p,
+                                     c_double_p]),
     ("gpk_bench_dmma", _I, [_H, _I, _I, _I, c_double_p, c_double_p]),
     ("gpk_bench_syrk", _I, [_H, _L, _I, _I, c_double_p, c_double_p]),
     ("gpk_bench_copy", _I, [_H, _L, _I, c_double_p]),
@@ -333,6 +337,22 @@ class Engine(object):
         self._check(rc, "gpk_exact_eval_dist")
         return np.float64(nlZ.value), alpha
 
+    def exact_eval_dist_der(self, kind, matern_d, hyp, log_sn, ymm):
+        hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+        ymm = np.ascontiguousarray(ymm, dtype=np.float64).reshape(-1)
+        self._retire_factor()
+        alpha = np.empty((ymm.size, 1))
+        nlZ = ctypes.c_double(0.0)
+        dcov = np.zeros(max(hyp.size, 1))
+        dlik = np.zeros(1)
+        rc = self._lib.gpk_exact_eval_dist_der(self._h, kind, matern_d, _dp(hyp), hyp.size, float(log_sn), _dp(ymm),
+                                               ctypes.byref(nlZ), _dp(alpha), _dp(dcov), _dp(dlik))
+        self._check(rc, "gpk_exact_eval_dist_der")
+        return np.float64(nlZ.value), alpha, dcov[:hyp.size], dlik
+
+    def dist_gather_factor(self):
+        self._check(self._lib.gpk_dist_gather_factor(self._h), "gpk_dist_gather_factor")
+
     # -- FITC -----------------------------------------------------------------
     def fitc_eval(self, kind, matern_d, hyp, log_sn, u, ymm, want_der):
         hyp = np.ascontiguousarray(hyp, dtype=np.float64)
@@ -432,6 +452,112 @@ class Engine(object):
                                     Li.ctypes.data_as(c_double_p), ctypes.byref(ld), ctypes.byref(info))
         self._check(rc, "gpk_dbg_diag")
         return L, Li, ld.value, info.value
+
+
+# ---------------------------------------------------------------------------------------------
+# devices of this process
+_devices = None
+
+
+def device_count():
+    c = ctypes.c_int(0)
+    load().gpk_device_count(ctypes.byref(c))
+    return c.value
+
+
+def set_devices(devices):
+    """Restrict (or order) the GPUs this process uses for multi-GPU work: random restarts of the optimizers and
+    sharded evaluations.  None = every visible device."""
+    global _devices
+    _devices = None if devices is None else [int(d) for d in devices]
+
+
+def visible_devices():
+    """CUDA ordinals this process may use.  Under a one-process-per-GPU launcher (torchrun: WORLD_SIZE > 1) a process
+    owns exactly its LOCAL_RANK device; otherwise every visible device, or the list given to set_devices()."""
+    if _devices is not None:
+        return list(_devices)
+    n = device_count()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "LOCAL_RANK" in os.environ:
+        return [int(os.environ["LOCAL_RANK"]) % max(n, 1)]
+    return list(range(n))
+
+
+def device_memory(device):
+    """(free, total) bytes of HBM on `device`."""
+    f, t = ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = load().gpk_device_memory(int(device), ctypes.byref(f), ctypes.byref(t))
+    if rc != 0:
+        raise GpkError("gpk_device_memory(%d) failed" % device)
+    return f.value, t.value
+
+
+class ShardedEngine(object):
+    """ONE evaluation sharded over several GPUs of this process (BASELINE config 3): one Engine and one thread per
+    GPU, bound together by an NCCL communicator (gpk_dist_init from every thread at once; ctypes releases the GIL, so
+    the ranks really run concurrently).  The factor is distributed by block-cyclic block columns; every rank
+    broadcasts its solved panels over NVLink (csrc/dist.cu)."""
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_no_engine, ())
+
+    def __init__(self, devices):
+        from concurrent.futures import ThreadPoolExecutor
+        self.devices = [int(d) for d in devices]
+        if len(set(self.devices)) != len(self.devices) or not self.devices:
+            raise GpkError("ShardedEngine needs distinct devices")
+        self.world = len(self.devices)
+        self.engines = [Engine(d) for d in self.devices]
+        self._pool = ThreadPoolExecutor(self.world)
+        uid = self.engines[0].dist_unique_id() if self.world > 1 else None
+        self._all(lambda r, e: e.dist_init(r, self.world, uid))
+        self.epoch = 0
+
+    def _all(self, fn):
+        futs = [self._pool.submit(fn, r, e) for r, e in enumerate(self.engines)]
+        return [f.result() for f in futs]
+
+    def set_data(self, x):
+        x = as_f64(x, "x")
+        self._all(lambda r, e: e.set_data(x))
+        self.n, self.D = x.shape
+
+    def exact_eval(self, kind, matern_d, hyp, log_sn, ymm, want_der=False):
+        """nlZ, alpha[, dcov, dlik] - same values on every rank; rank 0's are returned."""
+        self.epoch += 1
+        if want_der:
+            out = self._all(lambda r, e: e.exact_eval_dist_der(kind, matern_d, hyp, log_sn, ymm))
+            return out[0]
+        out = self._all(lambda r, e: e.exact_eval_dist(kind, matern_d, hyp, log_sn, ymm))
+        return out[0][0], out[0][1], np.zeros(len(hyp)), np.zeros(1)
+
+    def get_factor(self, n):
+        self._all(lambda r, e: e.dist_gather_factor())
+        return self.engines[0].get_factor(n)
+
+    def predict(self, xs):
+        """Test points are split over the ranks; every rank solves its share against its replica of the factor
+        (gathered once per posterior, gpk_dist_gather_factor)."""
+        xs = as_f64(xs, "xs")
+        ns = xs.shape[0]
+        cuts = [(ns * r) // self.world for r in range(self.world + 1)]
+
+        def part(r, e):
+            e.dist_gather_factor()
+            if cuts[r + 1] == cuts[r]:
+                return np.empty((0, 1)), np.empty((0, 1))
+            return e.predict(xs[cuts[r]:cuts[r + 1]])
+        out = self._all(part)
+        return np.vstack([o[0] for o in out]), np.vstack([o[1] for o in out])
+
+    def stats(self):
+        return [e.stats() for e in self.engines]
+
+    def close(self):
+        self._pool.shutdown(wait=True)
 
 
 _shared = {}

@@ -422,8 +422,9 @@ int check_handle(gpk_handle hh, Handle** out) {
 // Solve with many right-hand sides held TRANSPOSED: P is (rows x np) column-major with pitch ldp
 // (one right-hand side per ROW).  Forward: P <- P * L^-T, block column by block column.
 int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A,
-                         int64_t lda, const double* Dinv, int T) {
-  for (int k = 0; k < T; ++k) {
+                         int64_t lda, const double* Dinv, int T, int kstart) {
+  // kstart > 0: the first kstart block columns of P are known to be zero (unit right-hand sides e_i, i >= kstart*NB)
+  for (int k = kstart; k < T; ++k) {
     GemmArgs t{};
     t.A = P + (int64_t)k * NB * ldp; t.B = Dinv + (int64_t)k * NB * NB; t.C = P + (int64_t)k * NB * ldp;
     t.lda = ldp; t.ldb = NB; t.ldc = ldp; t.K = NB; t.tri = 0;
@@ -597,6 +598,21 @@ int gpk_device_count(int* count) {
   return 0;
 }
 
+int gpk_device_memory(int device, int64_t* free_bytes, int64_t* total_bytes) {
+  if (!free_bytes || !total_bytes) return GPK_ERR_ARG;
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) return GPK_ERR_ARG;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (cudaSetDevice(device) != cudaSuccess) return GPK_ERR_CUDA;
+  size_t f = 0, t = 0;
+  const cudaError_t e = cudaMemGetInfo(&f, &t);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) return GPK_ERR_CUDA;
+  *free_bytes = (int64_t)f; *total_bytes = (int64_t)t;
+  return 0;
+}
+
 int gpk_create(int device, gpk_handle* out) {
   if (!out) return GPK_ERR_ARG;
   *out = nullptr;
@@ -716,7 +732,7 @@ int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int
     c.nF = n; c.nS = n; c.pF = np; c.pS = np; c.D = D;
     c.kind = kind; c.matern_d = matern_d; c.epi = EPI_COV; c.ard_dim = 0;
     c.sf2 = sf2; c.scale = 1.0 / sn2; c.diag_add = 1.0;
-    c.same_set = 1; c.lower_only = 1; c.pad_identity = 1;
+    c.same_set = 1; c.lower_only = 1; c.pad_identity = 1; c.padded128 = 1;
     lazy = c;
   }
   // right-hand side y - m, zero padded; dB is the forward-solve work copy
@@ -849,6 +865,7 @@ int gpk_predict(gpk_handle hh, const double* Xs, int64_t ns, double* ks_alpha, d
     c.kind = h->kind; c.matern_d = h->matern_d; c.epi = EPI_COV;
     const bool ep = h->post_ep;                   // EP posterior: sW is a vector (sqrt of the site precisions)
     c.sf2 = sf2; c.scale = ep ? 1.0 : 1.0 / sn; c.diag_add = 0.0; c.same_set = 0; c.lower_only = 0; c.pad_identity = 0;
+    c.padded128 = 1;
     GPK_TRY(launch_cov(h, st, c));
     // Ks' alpha  (undo the 1/sn scaling)
     GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, h->dAlpha, 0, ep ? 1.0 : sn, 0.0, dPart, nsplit, dOut, m));
@@ -926,17 +943,19 @@ int gpk_cov_matrix(gpk_handle hh, int kind, int matern_d, const double* hyp, int
     }                                                                      \
   } while (0)
   const int64_t big = (n > mm ? n : mm);
+  // scaled inputs padded (zero rows) to whole 128-point blocks: the tile kernel bulk-copies 128 x D blocks
+  const int64_t n128 = round_up(n, NB), m128 = round_up(train ? n : m, NB);
   CKC(cudaMalloc((void**)&dXr, (size_t)big * D * sizeof(double)));
-  CKC(cudaMalloc((void**)&dXq, (size_t)n * D * sizeof(double)));
-  if (!train) CKC(cudaMalloc((void**)&dZq, (size_t)m * D * sizeof(double)));
+  CKC(cudaMalloc((void**)&dXq, (size_t)n128 * D * sizeof(double)));
+  if (!train) CKC(cudaMalloc((void**)&dZq, (size_t)m128 * D * sizeof(double)));
   CKC(cudaMalloc((void**)&dOut, (size_t)n * mm * sizeof(double)));
   CKC(cudaMalloc((void**)&dSc, (size_t)D * sizeof(double)));
   CKC(cudaMemcpyAsync(dSc, scale.data(), D * sizeof(double), cudaMemcpyHostToDevice, st));
   CKC(cudaMemcpyAsync(dXr, X, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = launch_prescale(h, st, dXr, n, n, D, dSc, divide, premul, dXq);
+  int rc = launch_prescale(h, st, dXr, n, n128, D, dSc, divide, premul, dXq);
   if (rc == 0 && !train) {
     CKC(cudaMemcpyAsync(dXr, Z, (size_t)m * D * sizeof(double), cudaMemcpyHostToDevice, st));
-    rc = launch_prescale(h, st, dXr, m, m, D, dSc, divide, premul, dZq);
+    rc = launch_prescale(h, st, dXr, m, m128, D, dSc, divide, premul, dZq);
   }
   if (rc == 0) {
     CovArgs c{};
@@ -945,6 +964,7 @@ int gpk_cov_matrix(gpk_handle hh, int kind, int matern_d, const double* hyp, int
     c.nF = mm; c.nS = n; c.pF = mm; c.pS = n; c.D = D;
     c.kind = kind; c.matern_d = matern_d; c.epi = epi; c.ard_dim = ard_dim;
     c.sf2 = sf2; c.scale = 1.0; c.diag_add = 0.0; c.same_set = train ? 1 : 0; c.lower_only = 0; c.pad_identity = 0;
+    c.padded128 = 1;
     rc = launch_cov(h, st, c);
   }
   if (rc != 0) { cleanup(); return rc; }

@@ -195,8 +195,8 @@ int gpk_dist_finalize(gpk_handle hh) {
 
 // Sharded counterpart of gpk_exact_eval (no derivatives): every rank calls it with the same arguments after
 // gpk_set_data with the same X; every rank gets the same nlZ and the full alpha.
-int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
-                        const double* ymm, double* nlZ, double* alpha) {
+static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
+                                const double* ymm, double* nlZ, double* alpha) {
   Handle* h;
   GPK_TRY(check_handle(hh, &h));
   if (!h->dX || h->n <= 0) return GPK_ERR_STATE;
@@ -214,7 +214,7 @@ int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp
   if (D > 1900) return GPK_ERR_ARG;
   const double sn2 = std::exp(2.0 * log_sn);
   stats_begin(h);
-  h->has_post = false; h->has_fitc = false; h->pn = 0;
+  h->has_post = false; h->has_fitc = false; h->pn = 0; h->dist_post = false;
   cudaStream_t st = h->s_main;
   GPK_CK(h, cudaFuncSetAttribute(bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_SMEM));
 
@@ -243,7 +243,7 @@ int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp
     c.nF = n; c.nS = n; c.pF = np; c.pS = (int64_t)nloc * NB; c.D = D;
     c.kind = kind; c.matern_d = matern_d; c.epi = EPI_COV;
     c.sf2 = sf2; c.scale = 1.0 / sn2; c.diag_add = 1.0;
-    c.same_set = 1; c.lower_only = 1; c.pad_identity = 1;
+    c.same_set = 1; c.lower_only = 1; c.pad_identity = 1; c.padded128 = 1;
     c.s_bstride = G; c.s_boff = r;
     GPK_TRY(launch_cov(h, st, c));
     fill_aug_kernel<<<148, 256, 0, st>>>(h->gA, ld, np, (int64_t)nloc * NB, G, r, h->dR, n);
@@ -275,13 +275,13 @@ int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp
   GPK_CK(h, cudaEventRecord(ev_fork, st));
   GPK_CK(h, cudaStreamWaitEvent(sp, ev_fork, 0));
   GPK_CK(h, cudaStreamWaitEvent(sc, ev_fork, 0));
-  // Blocked variant (GPK_DIST_OZAKI=1; off by default until it has been measured on 8 GPUs): inside a block of WD
+  // Blocked variant (the default; GPK_DIST_OZAKI=0 selects the rank-128 DMMA updates): inside a block of WD
   // panels only the block's own columns get the immediate rank-128 DMMA updates; the broadcast panels are collected
   // (full height, pitch ld) in a double-buffered block buffer, and after the block every rank slices it once and
   // applies ONE rank-(WD*128) update on the int8 tensor cores to the columns it owns beyond the block
   // (launch_oz_cyclic) - the column that becomes the next panel first.
   const int WD = env_int("GPK_DIST_WD", 8);
-  const bool doz = env_int("GPK_DIST_OZAKI", 0) != 0 && env_int("GPK_OZAKI", 1) != 0 && T >= 4 * WD && WD >= 1 && WD <= 16;
+  const bool doz = env_int("GPK_DIST_OZAKI", 1) != 0 && env_int("GPK_OZAKI", 1) != 0 && T >= 4 * WD && WD >= 1 && WD <= 16;
   double* PB = nullptr;
   if (doz) {
     GPK_TRY(ensure(h, &h->gBlk, &h->cgBlk, 2 * ld * (int64_t)WD * NB));
@@ -424,7 +424,111 @@ int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp
   h->stats.d2h_bytes = (n + 2) * (int64_t)sizeof(double) + 4;
   const int info = *reinterpret_cast<int*>(h->hPinned + 2048);
   *nlZ = h->hPinned[0] / 2.0 + h->hPinned[1] + (double)n * std::log(2.0 * M_PI * sn2) / 2.0;
+  h->kind = kind; h->matern_d = matern_d; h->nhyp = nhyp; h->sn2 = sn2; h->sf2 = sf2;
+  h->hyp.assign(hyp, hyp + nhyp);
+  h->dist_post = (info == 0);            // the distributed factor + alpha describe a posterior (gpk_dist_gather_factor)
   if (info != 0) return info;
+  return 0;
+}
+
+int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
+                        const double* ymm, double* nlZ, double* alpha) {
+  return exact_eval_dist_impl(hh, kind, matern_d, hyp, nhyp, log_sn, ymm, nlZ, alpha);
+}
+
+// Replicate the distributed factor on every rank: L into dA (np x np, lower), the block inverses into dDinv.  One packed
+// trapezoid (rows >= k*128 of block column k) is broadcast per block column by its owner - 4 N^2 bytes in total over
+// NVLink - and the 128x128 block inverses travel as one sum-all-reduce of a buffer in which every block has exactly one
+// non-zero contributor.  Afterwards the handle is in the same state as after gpk_exact_eval: gpk_predict and
+// gpk_get_factor work on every rank (each for its own share of the test points: no further communication).
+int gpk_dist_gather_factor(gpk_handle hh) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (h->has_post && h->dist_post) return 0;          // already gathered for this posterior
+  if (!h->dist_post) return GPK_ERR_STATE;
+  const int G = h->world, r = h->rank;
+  const int64_t np = h->np, ld = np + NB;
+  const int T = (int)(np / NB);
+  cudaStream_t st = h->s_main;
+  GPK_TRY(ensure(h, &h->dA, &h->capA, np * np));
+  GPK_TRY(ensure(h, &h->gPack, &h->cgPack, 2 * ld * NB));
+  GPK_CK(h, cudaMemsetAsync(h->dDinv, 0, (size_t)np * NB * sizeof(double), st));
+  for (int k = 0; k < T; ++k) {
+    const int o = k % G, lk = k / G;
+    const int64_t rows = np - (int64_t)k * NB;        // the lower trapezoid of block column k
+    double* pack = h->gPack + (int64_t)(k & 1) * ld * NB;
+    double* dst = h->dA + (int64_t)k * NB * np + (int64_t)k * NB;
+    if (r == o) {
+      const double* src = h->gA + (int64_t)lk * NB * ld + (int64_t)k * NB;
+      GPK_CK(h, cudaMemcpy2DAsync(dst, (size_t)np * sizeof(double), src, (size_t)ld * sizeof(double),
+                                  (size_t)rows * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+      GPK_CK(h, cudaMemcpyAsync(h->dDinv + (int64_t)k * NB * NB, h->gDinv + (int64_t)lk * NB * NB,
+                                (size_t)NB * NB * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      if (G > 1)
+        GPK_CK(h, cudaMemcpy2DAsync(pack, (size_t)rows * sizeof(double), src, (size_t)ld * sizeof(double),
+                                    (size_t)rows * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+    }
+    if (G > 1) {
+      NCCL_CK(h, g_nccl.bcast(pack, pack, (size_t)rows * NB, NCCL_F64, o, h->nccl_comm, st));
+      if (r != o)
+        GPK_CK(h, cudaMemcpy2DAsync(dst, (size_t)np * sizeof(double), pack, (size_t)rows * sizeof(double),
+                                    (size_t)rows * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (G > 1) NCCL_CK(h, g_nccl.allreduce(h->dDinv, h->dDinv, (size_t)np * NB, NCCL_F64, NCCL_SUM, h->nccl_comm, st));
+  GPK_CK(h, cudaStreamSynchronize(st));
+  h->has_post = true; h->post_ep = false; h->has_fitc = false; h->pn = 0;
+  return 0;
+}
+
+// Sharded counterpart of gpk_exact_eval(want_der = 1).  After the sharded factorisation and the gather, rank r owns the
+// ROWS [i0, i1) of the inverse (a contiguous, tile-aligned share): they are the solutions of A X = E[:, i0:i1], computed
+// as right-hand sides held transposed by the two triangular sweeps (forward from block column i0/128: everything before
+// it is zero), and the fused Q o dK reduction runs over that rectangle (every pair of the full matrix is in exactly one
+// rank's rectangle).  ONE all-reduce of nhyp+1 partial sums.
+int gpk_exact_eval_dist_der(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
+                            const double* ymm, double* nlZ, double* alpha, double* dcov, double* dlik) {
+  if (!dcov || !dlik) return GPK_ERR_ARG;
+  GPK_TRY(exact_eval_dist_impl(hh, kind, matern_d, hyp, nhyp, log_sn, ymm, nlZ, alpha));
+  GPK_TRY(gpk_dist_gather_factor(hh));
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  const int G = h->world, r = h->rank;
+  const int64_t n = h->n, np = h->np;
+  const int D = h->D, T = (int)(np / NB);
+  cudaStream_t st = h->s_main;
+  const int t0 = (int)(((int64_t)T * r) / G), t1 = (int)(((int64_t)T * (r + 1)) / G);
+  const int64_t i0 = (int64_t)t0 * NB, rows = (int64_t)(t1 - t0) * NB;
+  const int64_t g = (n + 63) / 64;
+  const int64_t gi = (rows + 63) / 64 > 0 ? (rows + 63) / 64 : 1;
+  GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, gi * g * 34 + 64));
+  GPK_CK(h, cudaEventRecord(h->t3, st));
+  double* res = h->gVec + np + T;                       // the result slots of the sharded evaluation (16 doubles)
+  double* dres = h->dScal + T + 8;                      // [dcov..., trace]
+  GPK_CK(h, cudaMemsetAsync(dres, 0, (size_t)(nhyp + 1) * sizeof(double), st));
+  (void)res;
+  if (rows > 0) {
+    GPK_TRY(ensure(h, &h->dU, &h->capU, np * np));                 // L' (upper)
+    GPK_TRY(ensure(h, &h->dDinvT, &h->capDinvT, np * NB));
+    GPK_TRY(ensure(h, &h->dW, &h->capW, rows * np));               // this rank's rows of the inverse
+    GPK_TRY(launch_transpose(h, st, h->dA, np, 0, h->dU, np, 0, np, np, 1));
+    GPK_TRY(launch_transpose(h, st, h->dDinv, NB, (int64_t)NB * NB, h->dDinvT, NB, (int64_t)NB * NB, NB, NB, T));
+    GPK_CK(h, cudaMemsetAsync(h->dW, 0, (size_t)rows * np * sizeof(double), st));
+    GPK_TRY(launch_set_identity(h, st, h->dW + i0 * rows, rows, rows, rows));   // P[li, i0 + li] = 1
+    GPK_TRY(sweep_forward(h, st, h->dW, rows, (int)(rows / NB), h->dA, np, h->dDinv, T, t0));
+    GPK_TRY(sweep_backward(h, st, h->dW, rows, (int)(rows / NB), h->dU, np, h->dDinvT, T));
+    GPK_TRY(launch_dnlz_rect(h, st, h->dXs, n, D, h->dW, rows, i0, rows, h->dAlpha, 1.0 / h->sn2, h->sf2, kind,
+                             matern_d, h->dTmp, h->capTmp, dres));
+  }
+  if (G > 1) NCCL_CK(h, g_nccl.allreduce(dres, dres, (size_t)(nhyp + 1), NCCL_F64, NCCL_SUM, h->nccl_comm, st));
+  GPK_CK(h, cudaEventRecord(h->t4, st));
+  GPK_CK(h, cudaMemcpyAsync(h->hPinned + 8, dres, (size_t)(nhyp + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPK_CK(h, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->t3, h->t4); h->stats.deriv_ms = ms;
+  h->stats.total_ms += ms;
+  for (int i = 0; i < nhyp; ++i) dcov[i] = h->hPinned[8 + i] / 2.0;
+  dlik[0] = h->sn2 * h->hPinned[8 + nhyp];
   return 0;
 }
 

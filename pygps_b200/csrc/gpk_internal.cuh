@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <set>
 #include <string>
 #include <vector>
 #include "../../include/gpk.h"
@@ -65,6 +66,8 @@ struct CovArgs {
   int same_set;     // F and S are the same point set (train mode): f==s is the diagonal
   int lower_only;   // skip tiles entirely above the diagonal (f-tile < s-tile); zero strict upper inside diagonal tiles
   int pad_identity; // padded diagonal entries (f==s>=nF) get 1.0 instead of 0.0
+  int padded128;    // F and S are allocated (and zero beyond nF / nS) up to a multiple of 128 points: enables
+                    // cov_tile_kernel (bulk-copied 128-point blocks)
   int s_bstride;    // block-cyclic slow index (multi-GPU): local s maps to the GLOBAL point
   int s_boff;       //   (s/128)*s_bstride*128 + s_boff*128 + s%128 ; 0 = identity.  nS bounds the global index.
 };
@@ -78,6 +81,7 @@ struct Handle {
   cudaError_t last_cuda = cudaSuccess;
   std::string last_msg;
   gpk_stats stats{};
+  std::set<const void*> smem_attr;      // kernels whose dynamic shared-memory limit was raised ON THIS DEVICE
   int profile = 0;
   std::vector<cudaEvent_t> prof_ev;
   int prof_pairs = 0;
@@ -118,6 +122,7 @@ struct Handle {
   int64_t ceK = 0, ceSig = 0, ceVec = 0, ceSW = 0;
   // multi-GPU (block-cyclic columns over NCCL); see dist.cu
   void* nccl_comm = nullptr; int rank = 0, world = 1;
+  bool dist_post = false;                       // the distributed factor (gA) + dAlpha describe the current posterior
   double* gA = nullptr; int64_t cgA = 0;        // local columns of the (np+128) x np augmented matrix
   double* gDinv = nullptr; int64_t cgDinv = 0;  // inverses of the owned diagonal blocks
   double* gPack = nullptr; int64_t cgPack = 0;  // packed panel being broadcast
@@ -144,6 +149,15 @@ struct Handle {
       (h)->last_msg = std::string(#call) + ": " + cudaGetErrorString(e__);     \
       return (e__ == cudaErrorMemoryAllocation) ? GPK_ERR_NOMEM : GPK_ERR_CUDA; \
     }                                                                          \
+  } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember it per handle, not per process
+#define GPK_SMEM_ATTR(h, func, bytes)                                                                          \
+  do {                                                                                                         \
+    if ((h)->smem_attr.find((const void*)(func)) == (h)->smem_attr.end()) {                                    \
+      GPK_CK(h, cudaFuncSetAttribute((func), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      (h)->smem_attr.insert((const void*)(func));                                                              \
+    }                                                                                                          \
   } while (0)
 
 #define GPK_TRY(expr)                 \
@@ -209,7 +223,10 @@ int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::
 void stats_begin(Handle* h);
 int check_handle(gpk_handle hh, Handle** out);
 int sweep_forward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* A, int64_t lda,
-                  const double* Dinv, int T);
+                  const double* Dinv, int T, int kstart = 0);
+int launch_dnlz_rect(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv_rows, int64_t ld,
+                     int64_t i_off, int64_t rows, const double* alpha, double inv_sn2, double sf2, int kind, int matern_d,
+                     double* part, int64_t part_cap, double* res);
 int sweep_backward(Handle* h, cudaStream_t st, double* P, int64_t ldp, int row_tiles, const double* Lt, int64_t ldt,
                    const double* DinvT, int T);
 int inverse_factor_T(Handle* h, cudaStream_t st, double* U, const double* A, int64_t np, const double* Dinv);

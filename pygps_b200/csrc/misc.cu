@@ -151,6 +151,9 @@ struct DnlzArgs {
   int d_begin;      // ARD: first length-scale index handled by this pass
   int nacc;         // accumulators produced by this pass (<= DMAXD+2)
   double* part;     // [ctas][nacc]
+  int rect;         // 1: Ainv holds FULL ROWS [i_off, i_off + rows) of the inverse (rows x n, pitch ld): every pair of the
+  int64_t i_off;    //    rectangle counts once (sharded derivatives: the ranks' rectangles tile the whole matrix)
+  int64_t rows;
 };
 
 __global__ void __launch_bounds__(256) dnlz_kernel(const DnlzArgs a) {
@@ -162,25 +165,28 @@ __global__ void __launch_bounds__(256) dnlz_kernel(const DnlzArgs a) {
 #pragma unroll
   for (int q = 0; q < DMAXD + 2; ++q) acc[q] = 0.0;
 
-  if (bi >= bj) {
+  if (a.rect || bi >= bj) {
     double* Xi = dsh;                 // [64][D]
     double* Xj = dsh + DT_ * a.D;     // [64][D]
-    const int64_t i0 = (int64_t)bi * DT_, j0 = (int64_t)bj * DT_;
+    // i: GLOBAL row index; li: row inside Ainv (rect mode: Ainv row 0 is global row i_off)
+    const int64_t i0 = (int64_t)bi * DT_ + (a.rect ? a.i_off : 0), j0 = (int64_t)bj * DT_;
+    const int64_t ilim = a.rect ? min(a.n, a.i_off + a.rows) : a.n;
     for (int idx = tid; idx < DT_ * a.D; idx += 256) {
       const int p = idx / a.D, d = idx % a.D;
-      Xi[idx] = (i0 + p < a.n) ? a.Xs[(i0 + p) * a.D + d] : 0.0;
+      Xi[idx] = (i0 + p < ilim) ? a.Xs[(i0 + p) * a.D + d] : 0.0;
       Xj[idx] = (j0 + p < a.n) ? a.Xs[(j0 + p) * a.D + d] : 0.0;
     }
     __syncthreads();
     const int ti = tid & 63, tj0 = tid >> 6;  // i fastest across lanes -> coalesced Ainv reads
     const int64_t i = i0 + ti;
-    const double ai = (i < a.n) ? a.alpha[i] : 0.0;
-    const double swi = (a.sw && i < a.n) ? a.sw[i] : 0.0;
+    const int64_t li = i - (a.rect ? a.i_off : 0);
+    const double ai = (i < ilim) ? a.alpha[i] : 0.0;
+    const double swi = (a.sw && i < ilim) ? a.sw[i] : 0.0;
     for (int jj = tj0; jj < DT_; jj += 4) {
       const int64_t j = j0 + jj;
-      if (i >= a.n || j >= a.n || i < j) continue;
-      const double q = a.Ainv[i + j * a.ld] * (a.sw ? swi * a.sw[j] : a.inv_sn2) - ai * a.alpha[j];
-      const double w = (i == j) ? 1.0 : 2.0;
+      if (i >= ilim || j >= a.n || (!a.rect && i < j)) continue;
+      const double q = a.Ainv[li + j * a.ld] * (a.sw ? swi * a.sw[j] : a.inv_sn2) - ai * a.alpha[j];
+      const double w = (a.rect || i == j) ? 1.0 : 2.0;
       double d2 = 0.0;
       for (int d = 0; d < a.D; ++d) { const double df = Xi[ti * a.D + d] - Xj[jj * a.D + d]; d2 = fma(df, df, d2); }
       if (a.kind == GPK_COV_MATERN) {
@@ -337,10 +343,23 @@ static int launch_dnlz_impl(Handle* h, cudaStream_t st, const double* Xs, int64_
                             int64_t ld, const double* alpha, const double* sw, double inv_sn2, double sf2, int kind,
                             int matern_d, double* part, int64_t part_cap, double* res);
 
+static thread_local int64_t t_rect_off = 0, t_rect_rows = 0;
+static thread_local int t_rect = 0;
+
 int launch_dnlz(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
                 const double* alpha, double inv_sn2, double sf2, int kind, int matern_d, double* part,
                 int64_t part_cap, double* res) {
   return launch_dnlz_impl(h, st, Xs, n, D, Ainv, ld, alpha, nullptr, inv_sn2, sf2, kind, matern_d, part, part_cap, res);
+}
+// Ainv = rows [i_off, i_off + rows) of the inverse, full width (rows x n, pitch ld); every pair counts once
+int launch_dnlz_rect(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv_rows, int64_t ld,
+                     int64_t i_off, int64_t rows, const double* alpha, double inv_sn2, double sf2, int kind, int matern_d,
+                     double* part, int64_t part_cap, double* res) {
+  t_rect = 1; t_rect_off = i_off; t_rect_rows = rows;
+  const int rc = launch_dnlz_impl(h, st, Xs, n, D, Ainv_rows, ld, alpha, nullptr, inv_sn2, sf2, kind, matern_d, part,
+                                  part_cap, res);
+  t_rect = 0;
+  return rc;
 }
 int launch_dnlz_sw(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
                    const double* alpha, const double* sw, double sf2, int kind, int matern_d, double* part,
@@ -352,15 +371,17 @@ static int launch_dnlz_impl(Handle* h, cudaStream_t st, const double* Xs, int64_
                             int64_t ld, const double* alpha, const double* sw, double inv_sn2, double sf2, int kind,
                             int matern_d, double* part, int64_t part_cap, double* res) {
   const int64_t g = (n + DT_ - 1) / DT_;
+  const int64_t gi = t_rect ? (t_rect_rows + DT_ - 1) / DT_ : g;     // row tiles (rect mode: the rectangle's rows)
   if (g > 65535) return GPK_ERR_ARG;
-  const int64_t nctas = g * g;
+  const int64_t nctas = gi * g;
   const size_t smem = size_t(2) * DT_ * D * sizeof(double);
   if (smem > 200 * 1024) return GPK_ERR_ARG;
   GPK_CK(h, cudaFuncSetAttribute(dnlz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DnlzArgs a;
   a.Xs = Xs; a.n = n; a.D = D; a.Ainv = Ainv; a.ld = ld; a.alpha = alpha; a.sw = sw; a.inv_sn2 = inv_sn2; a.sf2 = sf2;
   a.kind = kind; a.matern_d = matern_d; a.part = part;
-  dim3 grid((unsigned)g, (unsigned)g);
+  a.rect = t_rect; a.i_off = t_rect_off; a.rows = t_rect_rows;
+  dim3 grid((unsigned)gi, (unsigned)g);
   if (kind != GPK_COV_RBFARD) {
     a.d_begin = 0; a.nacc = 3;
     if (nctas * a.nacc > part_cap) return GPK_ERR_ARG;

@@ -575,12 +575,8 @@ int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int6
 
 template <int S, int RB, int EPI, int GEN>
 static int oz_syrk_g(Handle* h, cudaStream_t st, const OzArgs& a) {
-  static bool attr_done = false;
   const size_t smem = (size_t)OZ_ST * (128 + OZ_BN) * S * 32;
-  if (!attr_done) {
-    GPK_CK(h, cudaFuncSetAttribute(oz_syrk_kernel<S, RB, EPI, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  GPK_SMEM_ATTR(h, (oz_syrk_kernel<S, RB, EPI, GEN>), smem);
   oz_syrk_kernel<S, RB, EPI, GEN><<<(a.ntiles + a.tpc - 1) / a.tpc, OZ_THREADS, smem, st>>>(a);
   GPK_CK(h, cudaGetLastError());
   return 0;

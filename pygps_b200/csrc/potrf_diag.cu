@@ -563,8 +563,8 @@ __global__ void __launch_bounds__(TRSV_THREADS, 1) trsv_bwd_persistent_kernel(
 
 int launch_trsv_bwd_all(Handle* h, cudaStream_t st, const double* A, int64_t lda, const double* Dinv, double* z,
                         double* x, int T) {
-  static int sms = 0;
-  if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   const char* e = getenv("GPK_TRSV_PERSIST");            // 0: one launch per block step (A/B runs, tests)
   const int persist = e ? atoi(e) : 1;
   if (!persist || T > sms || T < 2) {

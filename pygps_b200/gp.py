@@ -47,6 +47,7 @@ class GP(object):
         self.fm = None
         self.fs2 = None
         self.lp = None
+        self.devices = None          # see setDevices
         self.logger = logging.getLogger(__name__)
 
     def __str__(self):
@@ -92,6 +93,17 @@ class GP(object):
     def setOptimizer(self, method, num_restarts=None, min_threshold=None, meanRange=None, covRange=None,
                      likRange=None):
         pass
+
+    def setDevices(self, devices=None, shard=None):
+        """Multi-GPU use of this model (no counterpart in the reference, which has no parallelism at all):
+        `devices` = CUDA ordinals (None: every visible GPU).  The optimizers run their random restarts
+        (Core/opt.py:301-327) concurrently, one per GPU; an exact evaluation whose factor does not fit one GPU - or every
+        evaluation with shard=True - is sharded over all of them (gpk_exact_eval_dist, NCCL panel broadcasts)."""
+        self.devices = None if devices is None else [int(d) for d in devices]
+        if self.inffunc is not None:
+            self.inffunc.devices = self.devices
+            self.inffunc.shard = shard
+            self.inffunc._engine = None
 
     def _take_xy(self, x, y):
         if x is not None and y is not None:
@@ -226,15 +238,17 @@ class GP(object):
 
 
 class GPR(GP):
-    """Gaussian-process regression (Core/gp.py:533-635)."""
+    """Gaussian-process regression (Core/gp.py:533-635).  `devices` / `shard`: see GP.setDevices."""
 
-    def __init__(self):
+    def __init__(self, devices=None, shard=None):
         super(GPR, self).__init__()
         self.meanfunc = mean.Zero()
         self.covfunc = cov.RBF()
         self.likfunc = lik.Gauss()
         self.inffunc = inf.Exact()
         self.optimizer = opt.Minimize(self)
+        if devices is not None or shard is not None:
+            self.setDevices(devices, shard)
 
     def setNoise(self, log_sigma):
         """Replace the default noise (log 0.1) - Core/gp.py:547-553."""

@@ -157,9 +157,16 @@ class Inference(object):
         self.logger = logging.getLogger(__name__)
         self._engine = None
 
+    devices = None        # CUDA ordinals this inference method may use (None: the process default)
+    shard = None          # Exact only - None: shard an evaluation over `devices` when its factor does not fit one GPU;
+                          # True / False: always / never
+
+    def _device_list(self):
+        return list(self.devices) if self.devices else _lib.visible_devices()
+
     def _get_engine(self):
         if getattr(self, '_engine', None) is None:
-            self._engine = _lib.Engine()
+            self._engine = _lib.Engine(self.devices[0] if self.devices else None)
         return self._engine
 
     def evaluate(self, meanfunc, covfunc, likfunc, x, y, nargout=1):
@@ -175,9 +182,34 @@ def _mean_derivs(meanfunc, x, vec, dnlZ):
 class Exact(Inference):
     """Exact inference for a GP with Gaussian likelihood (Core/inf.py:345-384)."""
 
-    def __init__(self):
+    def __init__(self, devices=None, shard=None):
         self.name = "Exact inference"
         self._engine = None
+        self._sharded = None
+        self.devices = devices
+        self.shard = shard
+
+    def _wants_sharding(self, n):
+        """Route the evaluation to the sharded path (gpk_exact_eval_dist) when asked to, or when the N x N factor
+        (plus the int8 slices of one block) does not fit one GPU of the device list."""
+        devs = self._device_list()
+        if self.shard is False or len(devs) < 2:
+            return False
+        if self.shard:
+            return True
+        npad = -(-n // 128) * 128
+        need = 8 * npad * npad + 8 * npad * 1152 + (1 << 30)
+        try:
+            free, total = _lib.device_memory(devs[0])
+        except Exception:
+            return False
+        return need > 0.85 * total
+
+    def _get_sharded(self):
+        devs = self._device_list()
+        if getattr(self, '_sharded', None) is None or self._sharded.devices != devs:
+            self._sharded = _lib.ShardedEngine(devs)
+        return self._sharded
 
     def evaluate(self, meanfunc, covfunc, likfunc, x, y, nargout=1):
         if not isinstance(likfunc, lik.Gauss):
@@ -189,7 +221,7 @@ class Exact(Inference):
         if spec is None:
             return self._evaluate_generic(meanfunc, covfunc, likfunc, x, y, m, sn2, nargout)
         kind, md, hyp = spec
-        eng = self._get_engine()
+        eng = self._get_sharded() if self._wants_sharding(n) else self._get_engine()
         eng.set_data(x)
         nlZ, alpha, dcov, dlik = eng.exact_eval(kind, md, hyp, likfunc.hyp[0], y - m, nargout > 2)
         post = postStruct()

@@ -270,46 +270,149 @@ class Optimizer(object):
     def _run_once(self, hyp, numIters, first):
         raise NotImplementedError
 
+    # -- multi-GPU random restarts ------------------------------------------------------------------------------
+    def _restart_devices(self):
+        """CUDA ordinals the random restarts may run on (model.setDevices, else every GPU this process sees)."""
+        devs = getattr(self.model, 'devices', None)
+        if devs:
+            return list(devs)
+        try:
+            from . import _lib
+            return _lib.visible_devices()
+        except Exception:
+            return [0]
+
+    def _worker_for(self, device):
+        """A private copy of the model (and of this optimizer) whose evaluations run on `device`: the restarts of
+        Core/opt.py:301-327 are independent minimisations, so each GPU gets its own copy and its own libgpk handle."""
+        if not hasattr(self, '_workers'):
+            self._workers = {}
+        w = self._workers.get(device)
+        if w is None:
+            workers, self._workers = self._workers, {}          # do not copy the copies
+            try:
+                m = deepcopy(self.model)
+            finally:
+                self._workers = workers
+            m.devices = [device]
+            m.inffunc.devices = [device]
+            m.inffunc.shard = False
+            m.inffunc._engine = None
+            m.optimizer.searchConfig = None
+            w = self._workers[device] = m
+        return w
+
+    def _run_trials(self, jobs, numIters):
+        """jobs: [(hyp, first)] -> [(hyp, value) | Exception] in the same order.  One GPU: in order on the model itself;
+        several: concurrently, one model copy per GPU (libgpk calls release the GIL), results kept in job order so that
+        the bookkeeping below sees exactly the sequence a serial run would."""
+        devs = self._restart_devices()
+        out = [None] * len(jobs)
+        if len(devs) < 2 or len(jobs) < 2:
+            for i, (hyp, first) in enumerate(jobs):
+                try:
+                    h, v = self._run_once(hyp, numIters, first)
+                    out[i] = (deepcopy(h), v)
+                except Exception as e:                       # a failed trial, as Core/opt.py:317-318
+                    out[i] = e
+            self.devices_used = sorted(set(getattr(self, 'devices_used', [])) | set(devs[:1]))
+            return out
+        import queue
+        import threading
+        todo = queue.Queue()
+        for i, job in enumerate(jobs):
+            todo.put((i, job))
+        used = set()
+
+        copies = {}
+        for d in devs[:len(jobs)]:                           # model copies are made here, on the calling thread
+            try:
+                copies[d] = self._worker_for(d)
+            except Exception as e:
+                copies[d] = e
+
+        def work(dev):
+            m = copies[dev]
+            while True:
+                try:
+                    i, (hyp, first) = todo.get_nowait()
+                except queue.Empty:
+                    return
+                if isinstance(m, Exception):
+                    out[i] = m
+                    continue
+                try:
+                    h, v = m.optimizer._run_once(np.array(hyp, dtype=float), numIters, first)
+                    out[i] = (deepcopy(h), v)
+                    used.add(dev)
+                except Exception as e:
+                    out[i] = e
+        threads = [threading.Thread(target=work, args=(d,)) for d in devs[:len(jobs)]]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        self.devices_used = sorted(set(getattr(self, 'devices_used', [])) | used)
+        return out
+
     def _search(self, hyp0, numIters):
         """First run from the current hyper-parameters, then (with a searchConfig) uniform random
         restarts until num_restarts trials or min_threshold is reached; exceptions inside a trial
-        count as failed trials and more than num_restarts/2 failures abort (Core/opt.py:100-149 etc.)."""
-        optimalHyp = funcValue = None
-        try:
-            optimalHyp, funcValue = self._run_once(hyp0, numIters, True)
-            optimalHyp = deepcopy(optimalHyp)
-        except Exception:
-            self.errorCounter += 1
-            if not self.searchConfig:
-                raise Exception("Can not learn hyperparamters using %s." % self._failtext)
-        self.trailsCounter += 1
+        count as failed trials and more than num_restarts/2 failures abort (Core/opt.py:100-149 etc.).
+        The trials are independent: with several GPUs they run concurrently (one per GPU), drawn and
+        accounted for in the serial order."""
         conf = self.searchConfig
+        optimalHyp = funcValue = None
         if not conf:
-            return optimalHyp, funcValue
+            r = self._run_trials([(hyp0, True)], numIters)[0]
+            self.trailsCounter += 1
+            if isinstance(r, Exception):
+                self.errorCounter += 1
+                raise Exception("Can not learn hyperparamters using %s." % self._failtext)
+            return r
         ranges = conf.meanRange + conf.covRange + conf.likRange
         if not (conf.num_restarts or conf.min_threshold):
             raise Exception('Specify at least one of the stop conditions')
+        ndev = max(1, len(self._restart_devices()))
         hyp = np.array(hyp0, dtype=float)
+        first_pending = True
         while True:
-            self.trailsCounter += 1
-            for i in range(hyp.shape[0]):
-                hyp[i] = np.random.uniform(low=ranges[i][0], high=ranges[i][1])
-            try:
-                h, v = self._run_once(hyp, numIters, False)
-                if funcValue is None or v < funcValue:
-                    funcValue, optimalHyp = v, h
-            except Exception:
-                self.errorCounter += 1
-            if conf.num_restarts and self.errorCounter > conf.num_restarts / 2:
-                self.logger.warning("[%s] %d out of %d trails failed during optimization", self._label,
-                                    self.errorCounter, self.trailsCounter)
-                raise Exception("Over half of the trails failed for %s" % self._failtext)
-            done = (conf.num_restarts and self.trailsCounter > conf.num_restarts - 1) or \
-                   (conf.min_threshold and funcValue is not None and funcValue <= conf.min_threshold)
-            if done:
-                self.logger.warning("[%s] %d out of %d trails failed during optimization", self._label,
-                                    self.errorCounter, self.trailsCounter)
-                return optimalHyp, funcValue
+            # one wave: as many trials as can still be needed (all remaining restarts, or one per GPU when only
+            # min_threshold bounds the search); random starts are drawn in trial order exactly like the serial loop
+            if conf.num_restarts:
+                left = int(conf.num_restarts) - self.trailsCounter
+                wave = max(1, left)
+            else:
+                wave = ndev
+            jobs = []
+            if first_pending:
+                jobs.append((np.array(hyp0, dtype=float), True))
+            while len(jobs) < wave:
+                for i in range(hyp.shape[0]):
+                    hyp[i] = np.random.uniform(low=ranges[i][0], high=ranges[i][1])
+                jobs.append((hyp.copy(), False))
+            results = self._run_trials(jobs, numIters)
+            for (job_hyp, first), r in zip(jobs, results):
+                self.trailsCounter += 1
+                if isinstance(r, Exception):
+                    self.errorCounter += 1
+                else:
+                    h, v = r
+                    if funcValue is None or v < funcValue:
+                        funcValue, optimalHyp = v, h
+                if first:
+                    first_pending = False
+                    continue                                  # the stop conditions are checked after restarts only
+                if conf.num_restarts and self.errorCounter > conf.num_restarts / 2:
+                    self.logger.warning("[%s] %d out of %d trails failed during optimization", self._label,
+                                        self.errorCounter, self.trailsCounter)
+                    raise Exception("Over half of the trails failed for %s" % self._failtext)
+                done = (conf.num_restarts and self.trailsCounter > conf.num_restarts - 1) or \
+                       (conf.min_threshold and funcValue is not None and funcValue <= conf.min_threshold)
+                if done:
+                    self.logger.warning("[%s] %d out of %d trails failed during optimization", self._label,
+                                        self.errorCounter, self.trailsCounter)
+                    return optimalHyp, funcValue
 
 
 class Minimize(Optimizer):

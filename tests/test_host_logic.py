@@ -214,3 +214,81 @@ def test_bench_clock_sampler_windows_and_reference_arm_line():
     # the SAME config object as the GPU arm
     assert d["steps"] >= 1 and abs(d["ms_per_step"] * d["value"] - 1e3) < 1e-6
     assert d["config"] == bench.make_config(512, 8, 1)
+
+
+def test_random_restarts_run_concurrently_with_serial_bookkeeping(monkeypatch):
+    """Core/opt.py:301-327: the random restarts are independent minimisations.  With several devices they run on one
+    model copy per device, concurrently; starts are drawn and results accounted for in the serial order, so the outcome
+    (best hyper-parameters, value, trial / error counters) is identical to a one-device run."""
+    import threading
+    import pygps_b200 as pg
+    from pygps_b200 import opt
+
+    seen = {}
+
+    class Quad(opt.Optimizer):
+        _label, _failtext = 'Quad', 'quad'
+
+        def findMin(self, x, y, numIters=10):
+            return self._search(self._convert_to_array(), numIters)
+
+        def _run_once(self, hyp, numIters, first):
+            seen.setdefault(threading.get_ident(), []).append(tuple(self.model.devices or [None]))
+            import time
+            time.sleep(0.05)                     # an evaluation takes a while: the other devices pick up trials
+            h = np.array(hyp, dtype=float)
+            if abs(h[1]) > 4.0:
+                raise RuntimeError("trial failed")
+            return h * 0.5, float(np.sum((h - 1.0) ** 2))
+
+    def run(devs):
+        np.random.seed(7)
+        m = pg.GPR()
+        m.setDevices(devs)
+        conf = opt.random_init_conf(m.meanfunc, m.covfunc, m.likfunc)
+        conf.num_restarts = 9
+        o = Quad(m, conf)
+        m.optimizer = o
+        monkeypatch.setattr(Quad, "_restart_devices", lambda self: list(devs))
+        res = o.findMin(None, None)
+        return res, o.trailsCounter, o.errorCounter, getattr(o, "devices_used", None)
+
+    seen.clear()
+    (h1, v1), t1, e1, used1 = run([0])
+    n_threads_serial = len(seen)
+    seen.clear()
+    (h3, v3), t3, e3, used3 = run([0, 1, 2])
+    assert np.array_equal(h1, h3) and v1 == v3 and (t1, e1) == (t3, e3) and t1 == 9
+    assert n_threads_serial == 1 and len(seen) == 3 and used3 == [0, 1, 2]
+    assert sorted(set(d for v in seen.values() for d in v)) == [(0,), (1,), (2,)]
+    # min_threshold only: waves of one trial per device until the threshold is met
+    np.random.seed(3)
+    m = pg.GPR()
+    conf = opt.random_init_conf(m.meanfunc, m.covfunc, m.likfunc)
+    conf.min_threshold = 4.0
+    o = Quad(m, conf)
+    m.optimizer = o
+    monkeypatch.setattr(Quad, "_restart_devices", lambda self: [0, 1])
+    h, v = o.findMin(None, None)
+    assert v <= 4.0
+
+
+def test_models_with_engines_survive_deepcopy_and_pickle():
+    """reference models are plain Python objects; ours must stay copyable / picklable after evaluation."""
+    import copy
+    import pickle
+    import pygps_b200 as pg
+    from pygps_b200 import _lib
+
+    class FakeEngine(_lib.Engine):
+        def __init__(self):                     # no GPU here: only the copy protocol is under test
+            self.epoch = 3
+    m = pg.GPR()
+    m.inffunc._engine = FakeEngine()
+    p = pg.inf.postStruct()
+    p.alpha, p.sW, p.L = np.ones((3, 1)), np.ones((3, 1)), np.eye(3)
+    m.posterior = p
+    m2 = copy.deepcopy(m)
+    assert m2.inffunc._engine is None and np.array_equal(m2.posterior.L, np.eye(3))
+    m3 = pickle.loads(pickle.dumps(m))
+    assert m3.inffunc._engine is None and np.array_equal(m3.posterior.L, np.eye(3))
