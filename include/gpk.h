@@ -94,6 +94,39 @@ int gpk_cov_matrix(gpk_handle h, int kind, int matern_d,
                    const double* X, int64_t n, const double* Z, int64_t m, int D,
                    int mode, int der, double* out);
 
+/* ---- composite kernels on the device (Core/cov.py:230-328 and the other stationary kernels) --------------------- *
+ * A covariance function is a PROGRAM: the expression tree of SumOfKernel (:265) / ProductOfKernel (:230) /
+ * ScaleOfKernel (:299) over leaf kernels, as an array of nodes in post-order (children before parents, root last).
+ * `hyp` is the composite's flat list of LOG hyper-parameters exactly as the reference concatenates it (cov1.hyp +
+ * cov2.hyp; ScaleOfKernel: [scalar] + cov.hyp); node.hyp0 is the index of the node's first own entry in it.
+ * node.para: Matern d (:1078), PiecePoly v (:683), Poly order (:623); unused otherwise.
+ * Every thread evaluates the program for its own matrix entries from one pass over the pair's coordinates; the same
+ * program run backwards yields all hyper-parameter derivatives for the fused dnlZ reduction (Core/inf.py:376-377).  */
+enum {
+  GPK_OP_RBF = 0, GPK_OP_RBFARD = 1, GPK_OP_MATERN = 2, GPK_OP_RBFUNIT = 3, GPK_OP_RQ = 4, GPK_OP_RQARD = 5,
+  GPK_OP_PERIODIC = 6, GPK_OP_PIECEPOLY = 7, GPK_OP_GABOR = 8, GPK_OP_NOISE = 9, GPK_OP_CONST = 10, GPK_OP_LINEAR = 11,
+  GPK_OP_POLY = 12, GPK_OP_PRE = 13,
+  GPK_OP_SUM = 32, GPK_OP_PROD = 33, GPK_OP_SCALE = 34
+};
+typedef struct gpk_cov_node {
+  int32_t op;      /* GPK_OP_*                                                          */
+  int32_t a, b;    /* child node indices (SUM, PROD: a and b; SCALE: a); -1 for leaves */
+  int32_t hyp0;    /* index of this node's first hyper-parameter in `hyp`              */
+  double para;     /* Matern d / PiecePoly v / Poly order                               */
+} gpk_cov_node;
+
+/* getCovMatrix / getDerMatrix of a composite (same modes and layouts as gpk_cov_matrix).                          */
+int gpk_cov_matrix_prog(gpk_handle h, const gpk_cov_node* nodes, int nnodes, const double* hyp, int nhyp,
+                        const double* X, int64_t n, const double* Z, int64_t m, int D, int mode, int der, double* out);
+/* cov.Pre (Core/cov.py:1429-1455): upload the precomputed TRAINING matrix M2 (n,n) for the GPK_OP_PRE leaf of the
+ * programs evaluated afterwards on this handle (the cross/self-test parts of M1 stay with the caller).           */
+int gpk_set_pre(gpk_handle h, const double* Ktrain, int64_t n);
+/* inf.Exact.evaluate (Core/inf.py:353-384) for a composite: as gpk_exact_eval, dcov has nhyp entries in the
+ * reference's order.  gpk_predict / gpk_get_factor work afterwards (programs without a PRE leaf).                */
+int gpk_exact_eval_prog(gpk_handle h, const gpk_cov_node* nodes, int nnodes, const double* hyp, int nhyp,
+                        double log_sn, const double* ymm, int want_der,
+                        double* nlZ, double* alpha, double* dcov, double* dlik);
+
 /* ---- tools.jitchol / tools.solve_chol (Core/tools.py:31-97) ------------- *
  * gpk_potrf: A (n,n) symmetric (only the lower triangle is read) -> R (n,n)
  * C-order UPPER factor with an exactly zero strict lower triangle, A = R'R.
@@ -171,6 +204,11 @@ int gpk_ep_eval(gpk_handle h, int kind, int matern_d, const double* hyp, int nhy
 int gpk_dist_unique_id(const char* nccl_path, char* out128);
 int gpk_dist_init(gpk_handle h, const char* nccl_path, int rank, int world, const char* id128);
 int gpk_dist_finalize(gpk_handle h);
+/* Allocate everything the collective calls below need for the current data (level 0: gpk_exact_eval_dist; 1: + the
+ * factor gather; 2: + the sharded derivatives).  Not collective.  When the ranks are threads of ONE process, call it on
+ * every rank and join before the collective call: a device allocation inside a collective phase can dead-lock against
+ * a peer's enqueued NCCL kernel (peer-mapped allocations synchronise the devices).  One process per GPU: optional. */
+int gpk_dist_reserve(gpk_handle h, int level);
 int gpk_exact_eval_dist(gpk_handle h, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
                         const double* ymm, double* nlZ, double* alpha);
 /* Sharded GP.predict (Core/gp.py:404-419) and post.L: collective; replicates the distributed factor on every rank

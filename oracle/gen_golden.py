@@ -24,6 +24,10 @@ sys.path.insert(0, REF)
 warnings.filterwarnings("ignore")
 
 import numpy as np  # noqa: E402
+if not hasattr(np, "float"):
+    # cov.Noise's cross mode (Core/cov.py:1277,1296) uses the alias np.float, removed in numpy 1.24: restore the alias
+    # (same object as the builtin it always was) so the unmodified reference runs on this container's numpy 2.3
+    np.float = float
 import pyGPs  # noqa: E402
 
 logging.disable(logging.WARNING)
@@ -289,6 +293,87 @@ def classification():
     np.savez_compressed(os.path.join(OUT, "classification.npz"), **s)
 
 
+def cov_programs():
+    """The kernels evaluated by the device program (csrc/covprog.cu) and composites of them: matrices in all three
+    modes and every derivative matrix from the reference's own classes, plus the Mauna Loa model of
+    Demo/MaunaLoa/demo_MaunaLoa.py:36-68 (data loaded exactly as the demo does)."""
+    c = pyGPs.cov
+    rng = np.random.RandomState(3)
+    x3 = rng.normal(0, 1.0, (25, 3)); z3 = rng.normal(0, 1.0, (11, 3)); z3[4] = x3[7]     # one coinciding point (Noise)
+    x1 = rng.normal(0, 2.0, (30, 1)); z1 = rng.normal(0, 2.0, (9, 1))
+    s = {"x3": x3, "z3": z3, "x1": x1, "z1": z1}
+    leaves = {
+        "rbfunit": (lambda: c.RBFunit(0.3), 3),
+        "rq": (lambda: c.RQ(0.2, -0.1, 0.4), 3),
+        "rqard": (lambda: c.RQard(log_ell_list=[0.1, -0.2, 0.3], log_sigma=0.2, log_alpha=-0.3), 3),
+        "periodic": (lambda: c.Periodic(0.2, 0.5, 0.1), 1),
+        "piecepoly0": (lambda: c.PiecePoly(0.9, 0, 0.1), 3),
+        "piecepoly1": (lambda: c.PiecePoly(0.9, 1, 0.1), 3),
+        "piecepoly2": (lambda: c.PiecePoly(0.9, 2, 0.1), 3),
+        "piecepoly3": (lambda: c.PiecePoly(1.2, 3, -0.2), 3),
+        "gabor": (lambda: c.Gabor(0.4, 0.3), 3),
+        "noise": (lambda: c.Noise(-0.7), 3),
+        "const": (lambda: c.Const(0.3), 3),
+        "linear": (lambda: c.Linear(-0.4), 3),
+        "poly": (lambda: c.Poly(0.2, 3, -0.3), 3),
+        "comp3": (lambda: c.RBF(0.3, 0.1) * c.Matern(0.5, 5, -0.2) + c.RQ(0.2, -0.1, 0.4) * 1.5 + c.Noise(-1.0)
+                  + c.Const(-0.5) * c.Linear(-1.0), 3),
+        "comp1": (lambda: c.RBF(1.0, 0.5) + c.Periodic(0.2, 0.5, 0.1) * c.RBF(1.5, -0.2) + c.RQ(0.1, -0.4, -0.2)
+                  + (c.RBF(-1.0, -1.0) + c.Noise(-1.5)), 1),
+    }
+    for name, (make, D) in leaves.items():
+        k = make()
+        x, z = (x3, z3) if D == 3 else (x1, z1)
+        s[name + "_hyp"] = np.array(k.hyp, dtype=float)
+        s[name + "_train"] = k.getCovMatrix(x=x, mode="train")
+        s[name + "_cross"] = k.getCovMatrix(x=x, z=z, mode="cross")
+        s[name + "_self"] = k.getCovMatrix(z=z, mode="self_test")
+        for i in range(len(k.hyp)):
+            s["%s_dtrain%d" % (name, i)] = k.getDerMatrix(x=x, mode="train", der=i)
+            s["%s_dcross%d" % (name, i)] = k.getDerMatrix(x=x, z=z, mode="cross", der=i)
+            s["%s_dself%d" % (name, i)] = k.getDerMatrix(z=z, mode="self_test", der=i)
+    # Mauna Loa (Demo/MaunaLoa/demo_MaunaLoa.py:36-68)
+    year, co2 = [], []
+    for line in open(os.path.join(REF, "pyGPs/Demo/MaunaLoa/mauna.txt")):
+        zz = line.split('  ')
+        v = float(zz[1].split('\n')[0])
+        if v != -99.99:
+            year.append(float(zz[0])); co2.append(v)
+    X = np.array([i for i, j in zip(year, co2) if i < 2004]).reshape(-1, 1)
+    Y = np.array([j for i, j in zip(year, co2) if i < 2004]).reshape(-1, 1)
+    xs = np.arange(2004 + 1. / 24., 2024 - 1. / 24., 1. / 12.).reshape(-1, 1)
+    k1 = c.RBF(np.log(67.), np.log(66.))
+    k2 = c.Periodic(np.log(1.3), np.log(1.0), np.log(2.4)) * c.RBF(np.log(90.), np.log(2.4))
+    k3 = c.RQ(np.log(1.2), np.log(0.66), np.log(0.78))
+    k4 = c.RBF(np.log(1.6 / 12.), np.log(0.18)) + c.Noise(np.log(0.19))
+    k = k1 + k2 + k3 + k4
+    m = pyGPs.GPR()
+    m.setData(X, Y)
+    m.setPrior(kernel=k)
+    s["mauna_x"], s["mauna_y"], s["mauna_xs"] = X, Y, xs
+    s["mauna_c"] = np.float64(m.meanfunc.hyp[0])
+    run_model(m, X, Y, xs, "mauna", s, keep_L=False)
+    print("mauna nlZ", repr(s["mauna_nlZ"]), s["mauna_dcov"])
+    # cov.Pre: the same matrices handed over precomputed (GraphExtensions-style use, Core/cov.py:1429-1455)
+    kk = c.RBF(0.3, 0.1)
+    M2 = kk.getCovMatrix(x=x3, mode="train")
+    M1 = np.vstack([kk.getCovMatrix(x=x3, z=z3, mode="cross"), kk.getCovMatrix(z=z3, mode="self_test").T])
+    y3 = np.sin(x3.sum(1, keepdims=True))
+    m = pyGPs.GPR()
+    m.setPrior(kernel=c.Pre(M1, M2))
+    nlZ, post = m.getPosterior(x3, y3, der=False)
+    s["pre_M1"], s["pre_M2"], s["pre_y"] = M1, M2, y3
+    s["pre_nlZ"], s["pre_alpha"] = np.float64(nlZ), post.alpha
+    out = m.predict(z3)
+    s["pre_ym"], s["pre_ys2"] = out[0], out[1]
+    m = pyGPs.GPR()
+    m.setPrior(kernel=c.Pre(M1, M2) + c.Noise(-1.0))
+    nlZ, dn, post = m.getPosterior(x3, y3)
+    s["prenoise_nlZ"], s["prenoise_dcov"], s["prenoise_dlik"] = np.float64(nlZ), np.array(dn.cov), np.array(dn.lik)
+    s["prenoise_alpha"] = post.alpha
+    np.savez_compressed(os.path.join(OUT, "cov_programs.npz"), **s)
+
+
 def c4_big():
     """SURVEY 8(c)/(d)'s larger pins of config 4: (N,M) = (32768,512) -> nlZ 85900.043566, (65536,1024) -> 170971.078457."""
     s = {}
@@ -327,7 +412,9 @@ def c5_big():
 
 
 if __name__ == "__main__":
-    if "--c4big" in sys.argv or "--c5big" in sys.argv:
+    if "--programs" in sys.argv:
+        cov_programs()
+    elif "--c4big" in sys.argv or "--c5big" in sys.argv:
         if "--c5big" in sys.argv:
             c5_big()
         if "--c4big" in sys.argv:

@@ -23,6 +23,11 @@ A covariance function is described by a plain tuple
     ("rbf",    [log_ell, log_sf])                 Core/cov.py:786-808
     ("rbfard", [log_ell_1..log_ell_D, log_sf])    Core/cov.py:872-904
     ("matern", [log_ell, log_sf], d)              Core/cov.py:1078-1148
+    ("rbfunit", [log_ell]) :832 | ("rq", [log_ell, log_sf, log_alpha]) :1304 | ("rqard", [ell.., log_sf, log_alpha]) :1356
+    ("periodic", [log_ell, log_p, log_sf]) :1186 | ("piecepoly", [log_ell, log_sf], v) :683 | ("gabor", [log_ell, log_p]) :392
+    ("noise", [log_s]) :1254 | ("const", [log_s]) :941 | ("linear", [log_s]) :986 | ("poly", [log_c, log_sf], d) :623
+    ("pre", M1, M2) :1429
+    ("sum", k1, k2) :265 | ("prod", k1, k2) :230 | ("scale", c, k) :299      (composites; hyp lists concatenate)
 and a mean function by
     ("zero",) | ("one",) | ("const", c) | ("linear", [a_1..a_D])   Core/mean.py:279-369
 """
@@ -131,7 +136,7 @@ def _sf2(cov, D):
     return np.exp(2.0 * (hyp[D] if cov[0] == "rbfard" else hyp[1]))
 
 
-def cov_matrix(cov, x=None, z=None, mode=None):
+def _native_cov_matrix(cov, x=None, z=None, mode=None):
     """getCovMatrix for RBF / RBFard / Matern.  Core/cov.py:796-808, 887-904, 1124-1148.
 
     mode 'train' -> (n,n), 'cross' -> (n,m), 'self_test' -> (m,1)."""
@@ -155,7 +160,7 @@ def cov_matrix(cov, x=None, z=None, mode=None):
     return sf2 * np.exp(-0.5 * A)
 
 
-def cov_der_matrix(cov, x=None, z=None, mode=None, der=None):
+def _native_cov_der_matrix(cov, x=None, z=None, mode=None, der=None):
     """getDerMatrix: dK/dhyp_der.  RBF Core/cov.py:811-828, RBFard :906-938.
 
     For Matern this is the mathematically CORRECT derivative (sf2*dmfunc(t) for
@@ -193,6 +198,197 @@ def cov_der_matrix(cov, x=None, z=None, mode=None, der=None):
     a = (x[:, der] * inv).reshape(-1, 1)
     b = a if mode == "train" else (z[:, der] * inv).reshape(-1, 1)
     return K * _cdist(a, b, "sqeuclidean")
+
+
+# ---- the other kernels and the composites -----------------------------------------------------------------------
+_NATIVE = ("rbf", "rbfard", "matern")
+
+
+def cov_nhyp(cov, D):
+    """Number of hyper-parameters of a covariance spec (the composite's flat list is the concatenation)."""
+    k = cov[0]
+    if k in ("sum", "prod"):
+        return cov_nhyp(cov[1], D) + cov_nhyp(cov[2], D)
+    if k == "scale":
+        return 1 + cov_nhyp(cov[2], D)
+    if k == "pre":
+        return 0
+    return len(cov[1])
+
+
+def _dist2(cov_scale, x, z, mode):
+    """cdist(x*s, z*s, 'sqeuclidean') in the reference's mode convention; zeros for self-test."""
+    if mode == "self_test":
+        return np.zeros((z.shape[0], 1))
+    a = cov_scale(x)
+    return _cdist(a, a if mode == "train" else cov_scale(z), "sqeuclidean")
+
+
+def _pp(v, r, j, deriv=False):
+    """PiecePoly pp / dpp.  Core/cov.py:696-727."""
+    m = np.maximum(1.0 - r, 0.0)
+    if v == 0:
+        f, df = 1.0 + 0.0 * r, 0.0 * r
+    elif v == 1:
+        f, df = 1.0 + (j + 1) * r, (j + 1) + 0.0 * r
+    elif v == 2:
+        f = 1.0 + (j + 2) * r + (j * j + 4.0 * j + 3) / 3.0 * r * r
+        df = (j + 2) + 2.0 * (j * j + 4.0 * j + 3.0) / 3.0 * r
+    else:
+        f = (1.0 + (j + 3) * r + (6.0 * j * j + 36.0 * j + 45.0) / 15.0 * r * r
+             + (j * j * j + 9.0 * j * j + 23.0 * j + 15.0) / 15.0 * r * r * r)
+        df = ((j + 3) + 2.0 * (6.0 * j * j + 36.0 * j + 45.0) / 15.0 * r
+              + (j * j * j + 9.0 * j * j + 23.0 * j + 15.0) / 5.0 * r * r)
+    if not deriv:
+        return f * m ** (j + v)
+    return m ** (j + v - 1) * r * ((j + v) * f - m * df)
+
+
+def _leaf(cov, x, z, mode, der):
+    """Value (der None) or derivative matrix of one non-native leaf kernel, formulas as in the reference."""
+    k, hyp = cov[0], cov[1]
+    D = (x if x is not None else z).shape[1]
+    n = None if x is None else x.shape[0]
+    nn = None if z is None else z.shape[0]
+    if k == "rbfunit":                                           # Core/cov.py:842-868
+        ell = np.exp(hyp[0])
+        A = _dist2(lambda a: a / ell, x, z, mode)
+        return np.exp(-0.5 * A) if der is None else np.exp(-0.5 * A) * A
+    if k in ("rq", "rqard"):                                     # Core/cov.py:1316-1352, 1373-1425
+        if k == "rq":
+            ell = np.exp(hyp[0]); sf2 = np.exp(2.0 * hyp[1]); al = np.exp(hyp[2])
+            D2 = _dist2(lambda a: a / ell, x, z, mode)
+            nl = 1
+        else:
+            inv = 1.0 / np.exp(np.asarray(hyp[:D], dtype=float)); sf2 = np.exp(2.0 * hyp[D]); al = np.exp(hyp[D + 1])
+            D2 = _dist2(lambda a: a * inv[None, :], x, z, mode)
+            nl = D
+        base = 1.0 + 0.5 * D2 / al
+        if der is None:
+            return sf2 * base ** (-al)
+        if der < nl:
+            if k == "rq":
+                return sf2 * base ** (-al - 1) * D2
+            # TRUE derivative: the reference's (:1413-1418) is identically zero in train mode (distance of two ROW vectors)
+            if mode == "self_test":
+                return D2 * 0
+            a = (x[:, der] * inv[der]).reshape(-1, 1)
+            b = a if mode == "train" else (z[:, der] * inv[der]).reshape(-1, 1)
+            return sf2 * base ** (-al - 1) * _cdist(a, b, "sqeuclidean")
+        if der == nl:
+            return 2.0 * sf2 * base ** (-al)
+        return sf2 * base ** (-al) * (0.5 * D2 / base - al * np.log(base))
+    if k == "periodic":                                          # Core/cov.py:1198-1250
+        ell = np.exp(hyp[0]); p = np.exp(hyp[1]); sf2 = np.exp(2.0 * hyp[2])
+        A = np.pi * np.sqrt(_dist2(lambda a: a, x, z, mode)) / p
+        R = np.sin(A) / ell
+        if der is None:
+            return sf2 * np.exp(-2.0 * R * R)
+        if der == 0:
+            return 4.0 * sf2 * np.exp(-2.0 * R * R) * R * R
+        if der == 1:
+            return 4.0 * sf2 / ell * np.exp(-2.0 * R * R) * R * np.cos(A) * A
+        return 2.0 * sf2 * np.exp(-2.0 * R * R)
+    if k == "piecepoly":                                         # Core/cov.py:729-782
+        ell = np.exp(hyp[0]); sf2 = np.exp(2.0 * hyp[1]); v = int(round(cov[2]))
+        j = np.floor(0.5 * D) + v + 1
+        r = np.sqrt(_dist2(lambda a: a / ell, x, z, mode))
+        if der is None:
+            return sf2 * _pp(v, r, j)
+        if der == 0:
+            return sf2 * _pp(v, r, j, deriv=True)
+        if der == 1:
+            return 2.0 * sf2 * _pp(v, r, j)
+        return r * 0
+    if k == "gabor":                                             # Core/cov.py:413-448 (derivatives as the reference has them)
+        ell = np.exp(hyp[0]); p = np.exp(2.0 * hyp[1])
+        A = _dist2(lambda a: a / ell, x, z, mode)
+        dp = 2 * np.pi * np.sqrt(A) * ell / p
+        K = np.exp(-0.5 * A) * np.cos(dp)
+        if der is None:
+            return K
+        return dp * K if der == 0 else dp * np.exp(-0.5 * A) * np.sin(dp)
+    if k == "noise":                                             # Core/cov.py:1265-1300
+        s2 = np.exp(2.0 * hyp[0])
+        if mode == "self_test":
+            A = np.zeros((nn, 1))
+        elif mode == "train":
+            A = np.eye(n)
+        else:
+            A = (_cdist(x, z, "sqeuclidean") < 1e-9).astype(float)
+        return s2 * A if der is None else 2.0 * s2 * A
+    if k == "const":                                             # Core/cov.py:950-982
+        sf2 = np.exp(hyp[0])
+        if mode == "self_test":
+            A = np.ones((nn, 1))
+        elif mode == "train":
+            A = np.ones((n, n))
+        else:
+            A = np.ones((n, nn))
+        if der is None:
+            return sf2 * A + (np.eye(n) * 1e-10 if mode == "train" else 0.0)
+        return 2.0 * sf2 * A
+    if k in ("linear", "poly"):                                  # Core/cov.py:995-1024, 635-679
+        if mode == "self_test":
+            A = np.sum(z * z, 1).reshape(nn, 1)
+        elif mode == "train":
+            A = np.dot(x, x.T)
+        else:
+            A = np.dot(x, z.T)
+        if k == "linear":
+            sf2 = np.exp(hyp[0])
+            if der is None:
+                return sf2 * (A + (np.eye(n) * 1e-10 if mode == "train" else 0.0))
+            return 2.0 * sf2 * (A + (np.eye(n) * 1e-16 if mode == "train" else 0.0))
+        c = np.exp(hyp[0]); sf2 = np.exp(2.0 * hyp[1]); o = int(round(cov[2]))
+        if der is None:
+            return sf2 * (c + A + (np.eye(n) * 1e-10 if mode == "train" else 0.0)) ** o
+        if der == 0:
+            return c * o * sf2 * (c + A) ** (o - 1)
+        if der == 1:
+            return 2.0 * sf2 * (c + A) ** o
+        return A * 0
+    raise ValueError(k)
+
+
+def cov_matrix(cov, x=None, z=None, mode=None):
+    """getCovMatrix of any supported covariance spec, composites included (Core/cov.py:247-250, 281-284, 315-319)."""
+    k = cov[0]
+    if k in _NATIVE:
+        return _native_cov_matrix(cov, x=x, z=z, mode=mode)
+    if k == "sum":
+        return cov_matrix(cov[1], x, z, mode) + cov_matrix(cov[2], x, z, mode)
+    if k == "prod":
+        return cov_matrix(cov[1], x, z, mode) * cov_matrix(cov[2], x, z, mode)
+    if k == "scale":
+        return np.exp(cov[1]) * cov_matrix(cov[2], x, z, mode)
+    if k == "pre":                                               # Core/cov.py:1442-1450
+        M1, M2 = cov[1], cov[2]
+        if mode == "self_test":
+            return M1[-1, :].reshape(-1, 1)
+        return M2 if mode == "train" else M1[:-1, :]
+    return _leaf(cov, x, z, mode, None)
+
+
+def cov_der_matrix(cov, x=None, z=None, mode=None, der=None):
+    """getDerMatrix of any supported covariance spec (Core/cov.py:252-261, 286-295, 321-328)."""
+    k = cov[0]
+    D = (x if x is not None else z).shape[1]
+    if k in _NATIVE:
+        return _native_cov_der_matrix(cov, x=x, z=z, mode=mode, der=der)
+    if k in ("sum", "prod"):
+        n1 = cov_nhyp(cov[1], D)
+        if der < n1:
+            A = cov_der_matrix(cov[1], x, z, mode, der)
+            return A if k == "sum" else A * cov_matrix(cov[2], x, z, mode)
+        A = cov_der_matrix(cov[2], x, z, mode, der - n1)
+        return A if k == "sum" else A * cov_matrix(cov[1], x, z, mode)
+    if k == "scale":
+        sf2 = np.exp(cov[1])
+        if der == 0:
+            return 2.0 * sf2 * cov_matrix(cov[2], x, z, mode)
+        return sf2 * cov_der_matrix(cov[2], x, z, mode, der - 1)
+    return _leaf(cov, x, z, mode, der)
 
 
 def fitc_cov_matrix(cov, xu, x=None, z=None, mode=None):
@@ -266,7 +462,7 @@ def exact_evaluate(mean, cov, log_sn, x, y, nargout=1):
     if nargout == 2:
         return post, nlZ
     Q = solve_chol(R, np.eye(n)) / sn2 - np.dot(alpha, alpha.T)
-    nh = len(cov[1])
+    nh = cov_nhyp(cov, x.shape[1])
     dn = {"lik": [sn2 * np.trace(Q)],
           "cov": [(Q * cov_der_matrix(cov, x=x, mode="train", der=i)).sum() / 2.0
                   for i in range(nh)],

@@ -15,6 +15,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, "libgpk.so")
 
 COV_RBF, COV_RBFARD, COV_MATERN = 0, 1, 2
+# covariance-program ops (include/gpk.h: GPK_OP_*)
+(OP_RBF, OP_RBFARD, OP_MATERN, OP_RBFUNIT, OP_RQ, OP_RQARD, OP_PERIODIC, OP_PIECEPOLY, OP_GABOR, OP_NOISE, OP_CONST,
+ OP_LINEAR, OP_POLY, OP_PRE) = range(14)
+OP_SUM, OP_PROD, OP_SCALE = 32, 33, 34
 MODE_TRAIN, MODE_CROSS, MODE_SELF_TEST = 0, 1, 2
 _MODES = {"train": MODE_TRAIN, "cross": MODE_CROSS, "self_test": MODE_SELF_TEST}
 
@@ -37,6 +41,19 @@ class GpkError(RuntimeError):
     pass
 
 
+class CovNode(ctypes.Structure):
+    """gpk_cov_node (include/gpk.h)"""
+    _fields_ = [("op", ctypes.c_int32), ("a", ctypes.c_int32), ("b", ctypes.c_int32), ("hyp0", ctypes.c_int32),
+                ("para", ctypes.c_double)]
+
+
+def _node_array(nodes):
+    arr = (CovNode * len(nodes))()
+    for i, (op, a, b, h0, para) in enumerate(nodes):
+        arr[i].op, arr[i].a, arr[i].b, arr[i].hyp0, arr[i].para = int(op), int(a), int(b), int(h0), float(para)
+    return arr
+
+
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -54,6 +71,11 @@ PROTOTYPES = [
     ("gpk_last_stats", _I, [_H, ctypes.POINTER(GpkStats)]),
     ("gpk_set_profile", _I, [_H, _I]),
     ("gpk_cov_matrix", _I, [_H, _I, _I, c_double_p, _I, c_double_p, _L, c_double_p, _L, _I, _I, _I, c_double_p]),
+    ("gpk_cov_matrix_prog", _I, [_H, ctypes.POINTER(CovNode), _I, c_double_p, _I, c_double_p, _L, c_double_p, _L, _I, _I, _I,
+                                 c_double_p]),
+    ("gpk_set_pre", _I, [_H, c_double_p, _L]),
+    ("gpk_exact_eval_prog", _I, [_H, ctypes.POINTER(CovNode), _I, c_double_p, _I, _D, c_double_p, _I,
+                                 c_double_p, c_double_p, c_double_p, c_double_p]),
     ("gpk_potrf", _I, [_H, c_double_p, _L, c_double_p, c_double_p]),
     ("gpk_set_factor", _I, [_H, c_double_p, _L, c_double_p]),
     ("gpk_potrs", _I, [_H, c_double_p, _L, _L, c_double_p]),
@@ -70,6 +92,7 @@ PROTOTYPES = [
     ("gpk_dist_unique_id", _I, [ctypes.c_char_p, ctypes.c_char_p]),
     ("gpk_dist_init", _I, [_H, ctypes.c_char_p, _I, _I, ctypes.c_char_p]),
     ("gpk_dist_finalize", _I, [_H]),
+    ("gpk_dist_reserve", _I, [_H, _I]),
     ("gpk_exact_eval_dist", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, c_double_p, c_double_p]),
     ("gpk_dist_gather_factor", _I, [_H]),
     ("gpk_exact_eval_dist_der", _I, [_H, _I, _I, c_double_p, _I, _D, c_double_p, c_double_p, c_double_p, c_double_p,
@@ -205,6 +228,44 @@ class Engine(object):
                                           _dp(z), z.shape[0], x.shape[1], m, der, _dp(out))
         self._check(rc, "gpk_cov_matrix")
         return out
+
+    def cov_matrix_prog(self, nodes, hyp, x, z, mode, der=-1):
+        """getCovMatrix / getDerMatrix of a covariance program (composite kernels, csrc/covprog.cu)."""
+        hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+        arr = _node_array(nodes)
+        m = _MODES[mode]
+        x = None if (x is None or m == MODE_SELF_TEST) else as_f64(x, "x")
+        z = None if (z is None or m == MODE_TRAIN) else as_f64(z, "z")
+        if m == MODE_CROSS and x.shape[1] != z.shape[1]:
+            raise Exception("x and z must have the same number of columns")
+        D = (x if x is not None else z).shape[1]
+        n = 0 if x is None else x.shape[0]
+        mm = 0 if z is None else z.shape[0]
+        out = np.empty((mm, 1)) if m == MODE_SELF_TEST else np.empty((n, n if m == MODE_TRAIN else mm))
+        rc = self._lib.gpk_cov_matrix_prog(self._h, arr, len(nodes), _dp(hyp), hyp.size, _dp(x), n, _dp(z), mm, D, m,
+                                           int(der), _dp(out))
+        self._check(rc, "gpk_cov_matrix_prog")
+        return out
+
+    def set_pre(self, K):
+        K = as_f64(K, "precomputed training matrix")
+        if K.shape[0] != K.shape[1]:
+            raise Exception("precomputed training matrix must be square")
+        self._check(self._lib.gpk_set_pre(self._h, _dp(K), K.shape[0]), "gpk_set_pre")
+
+    def exact_eval_prog(self, nodes, hyp, log_sn, ymm, want_der):
+        hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+        ymm = np.ascontiguousarray(ymm, dtype=np.float64).reshape(-1)
+        arr = _node_array(nodes)
+        self._retire_factor()
+        alpha = np.empty((ymm.size, 1))
+        nlZ = ctypes.c_double(0.0)
+        dcov = np.zeros(max(hyp.size, 1))
+        dlik = np.zeros(1)
+        rc = self._lib.gpk_exact_eval_prog(self._h, arr, len(nodes), _dp(hyp), hyp.size, float(log_sn), _dp(ymm),
+                                           1 if want_der else 0, ctypes.byref(nlZ), _dp(alpha), _dp(dcov), _dp(dlik))
+        self._check(rc, "gpk_exact_eval_prog")
+        return np.float64(nlZ.value), alpha, dcov[:hyp.size], dlik
 
     # -- jitchol / solve_chol -------------------------------------------------
     def potrf(self, A, want_factor=True):
@@ -349,6 +410,9 @@ class Engine(object):
                                                ctypes.byref(nlZ), _dp(alpha), _dp(dcov), _dp(dlik))
         self._check(rc, "gpk_exact_eval_dist_der")
         return np.float64(nlZ.value), alpha, dcov[:hyp.size], dlik
+
+    def dist_reserve(self, level):
+        self._check(self._lib.gpk_dist_reserve(self._h, int(level)), "gpk_dist_reserve")
 
     def dist_gather_factor(self):
         self._check(self._lib.gpk_dist_gather_factor(self._h), "gpk_dist_gather_factor")
@@ -528,6 +592,8 @@ class ShardedEngine(object):
     def exact_eval(self, kind, matern_d, hyp, log_sn, ymm, want_der=False):
         """nlZ, alpha[, dcov, dlik] - same values on every rank; rank 0's are returned."""
         self.epoch += 1
+        # allocate on every rank FIRST and join (gpk_dist_reserve): no device allocation inside the collective phase
+        self._all(lambda r, e: e.dist_reserve(2 if want_der else 0))
         if want_der:
             out = self._all(lambda r, e: e.exact_eval_dist_der(kind, matern_d, hyp, log_sn, ymm))
             return out[0]
@@ -535,6 +601,7 @@ class ShardedEngine(object):
         return out[0][0], out[0][1], np.zeros(len(hyp)), np.zeros(1)
 
     def get_factor(self, n):
+        self._all(lambda r, e: e.dist_reserve(1))
         self._all(lambda r, e: e.dist_gather_factor())
         return self.engines[0].get_factor(n)
 
@@ -545,8 +612,10 @@ class ShardedEngine(object):
         ns = xs.shape[0]
         cuts = [(ns * r) // self.world for r in range(self.world + 1)]
 
+        self._all(lambda r, e: e.dist_reserve(1))
+        self._all(lambda r, e: e.dist_gather_factor())
+
         def part(r, e):
-            e.dist_gather_factor()
             if cuts[r + 1] == cuts[r]:
                 return np.empty((0, 1)), np.empty((0, 1))
             return e.predict(xs[cuts[r]:cuts[r + 1]])

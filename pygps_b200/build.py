@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpk.so")
-SOURCES = ["api.cu", "gemm_nt.cu", "potrf_diag.cu", "kbuild.cu", "misc.cu", "fitc.cu", "dist.cu", "ep.cu", "tc_i8.cu", "ozaki.cu"]
+SOURCES = ["api.cu", "gemm_nt.cu", "potrf_diag.cu", "kbuild.cu", "covprog.cu", "misc.cu", "fitc.cu", "dist.cu", "ep.cu", "tc_i8.cu", "ozaki.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

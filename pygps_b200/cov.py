@@ -7,9 +7,10 @@ Same class names, constructor arguments, `.hyp` lists of LOG hyper-parameters,
 :1078-1182 Matern, :332-390 FITCOfKernel, :230-328 composites).  All matrix
 arithmetic runs in libgpk.so (csrc/kbuild.cu); nothing here computes a distance.
 
-Only the kernels on the accelerated path are provided natively.  Composites
-(+, *, scalar *) combine device-built matrices element-wise on the host - they
-are the "next tier" of SURVEY section 8(f3).
+RBF / RBFard / Matern have a dedicated fused build (gpk_cov_matrix).  Every other kernel here and every composite
+(+, *, scalar *; Core/cov.py:230-328) is a PROGRAM evaluated on the device (csrc/covprog.cu): the expression tree in
+post-order, one pass over the pair's coordinates, all components and all hyper-parameter derivatives at once -
+`_device_prog()` below emits it.  cov.Pre (precomputed matrices, :1429-1455) uploads its training matrix once.
 """
 import logging
 
@@ -73,6 +74,48 @@ class Kernel(object):
         """(kind, matern_d, hyp) when libgpk has a native fused path for this kernel, else None."""
         return None
 
+    _op = None                 # GPK_OP_* of a leaf kernel
+
+    def _para(self):
+        return 0.0
+
+    def _emit(self, nodes, h0):
+        """Append this kernel's nodes (post-order) to `nodes`; return the index of its root.  h0 = index of this
+        kernel's first hyper-parameter in the composite's flat list.  Leaves override nothing but _op / _para."""
+        if self._op is None:
+            raise NotImplementedError("%s has no device implementation" % type(self).__name__)
+        nodes.append((self._op, -1, -1, h0, float(self._para())))
+        return len(nodes) - 1
+
+    def _device_prog(self):
+        """(nodes, hyp): the covariance program of this kernel (csrc/covprog.cu), or None if some component has no
+        device implementation.  nodes: list of (op, a, b, hyp0, para)."""
+        nodes = []
+        try:
+            self._emit(nodes, 0)
+        except NotImplementedError:
+            return None
+        if len(nodes) > 32 or len(self.hyp) > 96:
+            return None
+        return nodes, [float(v) for v in self.hyp]
+
+    def _pre_leaves(self):
+        return []
+
+    def _prog_matrix(self, x, z, mode, der):
+        """getCovMatrix / getDerMatrix through the device program."""
+        prog = self._device_prog()
+        if prog is None:
+            raise Exception("%s: no device implementation of this kernel" % type(self).__name__)
+        nodes, hyp = prog
+        if mode not in ('train', 'cross', 'self_test'):
+            return None
+        if mode == 'train' and x is None:
+            raise Exception("Specify training input (x) for mode 'train'")
+        if mode == 'self_test' and z is None:
+            raise Exception("Specify test input (z) for mode 'self_test'")
+        return _lib.shared_engine().cov_matrix_prog(nodes, hyp, x, z, mode, -1 if der is None else int(der))
+
 
 class _NativeKernel(Kernel):
     """RBF / RBFard / Matern: matrices come from gpk_cov_matrix."""
@@ -112,6 +155,7 @@ class _NativeKernel(Kernel):
 class RBF(_NativeKernel):
     """Squared exponential, isotropic.  hyp = [log_ell, log_sigma]  (Core/cov.py:786-828)."""
     _kind = _lib.COV_RBF
+    _op = _lib.OP_RBF
 
     def __init__(self, log_ell=0., log_sigma=0.):
         self.hyp = [log_ell, log_sigma]
@@ -121,6 +165,7 @@ class RBF(_NativeKernel):
 class RBFard(_NativeKernel):
     """Squared exponential with ARD.  hyp = log_ell_list + [log_sigma]  (Core/cov.py:872-938)."""
     _kind = _lib.COV_RBFARD
+    _op = _lib.OP_RBFARD
 
     def __init__(self, D=None, log_ell_list=None, log_sigma=0.):
         if log_ell_list is None:
@@ -139,10 +184,14 @@ class Matern(_NativeKernel):
     `getDerMatrix(der=0)` returns the mathematically correct length-scale derivative; the
     reference's (Core/cov.py:1173-1177) reuses K as the distance and is wrong."""
     _kind = _lib.COV_MATERN
+    _op = _lib.OP_MATERN
 
     def __init__(self, log_ell=0., d=3, log_sigma=0.):
         self.hyp = [log_ell, log_sigma]
         self.para = [d]
+
+    def _para(self):
+        return self._matern_d()
 
     def _matern_d(self):
         d = self.para[0]
@@ -220,7 +269,188 @@ class FITCOfKernel(Kernel):
         return self.covfunc._device_spec()
 
 
+class _ProgKernel(Kernel):
+    """Leaf kernels evaluated by the device program (csrc/covprog.cu)."""
+    _nder_extra = 0            # trailing non-learned parameters the reference accepts as `der` and answers with zeros
+
+    def getCovMatrix(self, x=None, z=None, mode=None):
+        self.checkInputGetCovMatrix(x, z, mode)
+        self._check_inputs(x, z)
+        return self._prog_matrix(x, z, mode, None)
+
+    def getDerMatrix(self, x=None, z=None, mode=None, der=None):
+        self.checkInputGetDerMatrix(x, z, mode, der)
+        self._check_inputs(x, z)
+        if isinstance(der, (int, np.integer)) and len(self.hyp) <= der < len(self.hyp) + self._nder_extra:
+            return np.zeros_like(self._prog_matrix(x, z, mode, None))
+        if not (isinstance(der, (int, np.integer)) and 0 <= der < len(self.hyp)):
+            raise Exception("Wrong derivative index in %s" % type(self).__name__)
+        return self._prog_matrix(x, z, mode, der)
+
+    def _check_inputs(self, x, z):
+        pass
+
+
+class RBFunit(_ProgKernel):
+    """Squared exponential with unit magnitude.  hyp = [log_ell]  (Core/cov.py:832-868)."""
+    _op = _lib.OP_RBFUNIT
+
+    def __init__(self, log_ell=0.):
+        self.hyp = [log_ell]
+        self.para = []
+
+
+class RQ(_ProgKernel):
+    """Rational quadratic, isotropic.  hyp = [log_ell, log_sigma, log_alpha]  (Core/cov.py:1304-1352)."""
+    _op = _lib.OP_RQ
+
+    def __init__(self, log_ell=0., log_sigma=0., log_alpha=0.):
+        self.hyp = [log_ell, log_sigma, log_alpha]
+        self.para = []
+
+
+class RQard(_ProgKernel):
+    """Rational quadratic with ARD.  hyp = log_ell_list + [log_sigma, log_alpha]  (Core/cov.py:1356-1425).
+    The length-scale derivatives are the true ones: the reference's (:1413-1418) take the distance between two
+    (1,n) ROW vectors and are identically zero in train mode."""
+    _op = _lib.OP_RQARD
+
+    def __init__(self, D=None, log_ell_list=None, log_sigma=0., log_alpha=0.):
+        if log_ell_list is None:
+            self.hyp = [0. for i in range(D)] + [log_sigma, log_alpha]
+        else:
+            self.hyp = log_ell_list + [log_sigma, log_alpha]
+        self.para = []
+
+
+class Periodic(_ProgKernel):
+    """Smooth periodic kernel for 1-d inputs.  hyp = [log_ell, log_p, log_sigma]  (Core/cov.py:1186-1250)."""
+    _op = _lib.OP_PERIODIC
+
+    def __init__(self, log_ell=0., log_p=0., log_sigma=0.):
+        self.hyp = [log_ell, log_p, log_sigma]
+        self.para = []
+
+    def _check_inputs(self, x, z):
+        if x is not None:
+            assert x.shape[1] == 1, 'periodic covariance can only be used for 1d data'
+        if z is not None:
+            assert z.shape[1] == 1, 'periodic covariance can only be used for 1d data'
+
+
+class PiecePoly(_ProgKernel):
+    """Piecewise polynomial with compact support, degree v in {0,1,2,3}.  hyp = [log_ell, log_sigma], para = [v]
+    (Core/cov.py:683-782)."""
+    _op = _lib.OP_PIECEPOLY
+    _nder_extra = 1
+
+    def __init__(self, log_ell=0., v=2, log_sigma=0.):
+        self.hyp = [log_ell, log_sigma]
+        self.para = [v]
+
+    def _para(self):
+        v = self.para[0]
+        if np.abs(v - np.round(v)) < 1e-8:
+            v = int(round(v))
+        assert int(v) in range(4)
+        return int(v)
+
+
+class Gabor(_ProgKernel):
+    """Gabor kernel h(t) = exp(-t^2/(2 ell^2)) cos(2 pi t / p).  hyp = [log_ell, log_p]; as in the reference the
+    period enters as exp(2*log_p) and the derivative matrices are the reference's dp*K and tan(dp)*dp*K
+    (Core/cov.py:392-448)."""
+    _op = _lib.OP_GABOR
+
+    def __init__(self, log_ell=0., log_p=0.):
+        self.hyp = [log_ell, log_p]
+        self.para = []
+
+
+class Noise(_ProgKernel):
+    """White noise.  hyp = [log_sigma].  Train mode: s2*I; cross mode: s2 where the points coincide (sq. distance
+    < 1e-9); self-test mode: 0, as the reference returns (Core/cov.py:1254-1300)."""
+    _op = _lib.OP_NOISE
+
+    def __init__(self, log_sigma=0.):
+        self.hyp = [log_sigma]
+        self.para = []
+
+
+class Const(_ProgKernel):
+    """Constant kernel.  hyp = [log_sigma]; the reference uses sf2 = exp(hyp[0]) (Core/cov.py:941-982)."""
+    _op = _lib.OP_CONST
+
+    def __init__(self, log_sigma=0.):
+        self.hyp = [log_sigma]
+        self.para = []
+
+
+class Linear(_ProgKernel):
+    """Linear kernel sf2 * x z'.  hyp = [log_sigma]; sf2 = exp(hyp[0]) as in the reference (Core/cov.py:986-1024)."""
+    _op = _lib.OP_LINEAR
+
+    def __init__(self, log_sigma=0.):
+        self.hyp = [log_sigma]
+        self.para = []
+
+
+class Poly(_ProgKernel):
+    """Polynomial kernel sf2 (c + x z')^d.  hyp = [log_c, log_sigma], para = [d]  (Core/cov.py:623-679)."""
+    _op = _lib.OP_POLY
+    _nder_extra = 1
+
+    def __init__(self, log_c=0., d=2, log_sigma=0.):
+        self.hyp = [log_c, log_sigma]
+        self.para = [d]
+
+    def _para(self):
+        o = self.para[0]
+        if np.abs(o - np.round(o)) < 1e-8:
+            o = int(round(o))
+        assert o >= 1.
+        return int(o)
+
+
+class Pre(Kernel):
+    """Precomputed kernel matrices (Core/cov.py:1429-1455): M1 = (train+1) x test, cross-covariances with the test
+    points' self-covariances in the last row; M2 = train x train.  No hyper-parameters.  On the device the training
+    matrix is uploaded once per evaluation (gpk_set_pre) and read by the program's PRE leaf."""
+    _op = _lib.OP_PRE
+
+    def __init__(self, M1, M2):
+        self.M1 = M1
+        self.M2 = M2
+        self.hyp = []
+        self.para = []
+
+    def getCovMatrix(self, x=None, z=None, mode=None):
+        if mode == 'self_test':
+            A = self.M1[-1, :]
+            return np.reshape(A, (A.shape[0], 1))
+        if mode == 'train':
+            return self.M2
+        if mode == 'cross':
+            return self.M1[:-1, :]
+
+    def getDerMatrix(self, x=None, z=None, mode=None, der=None):
+        if der is not None:
+            raise Exception("Error: NO optimization in precomputed kernel matrix")
+        return 0
+
+    def _pre_leaves(self):
+        return [self]
+
+
+def _host_combine(kernel):
+    """Composites that contain a Pre leaf are combined on the host from their parts (the precomputed parts ARE host
+    matrices; the other parts still come from the device)."""
+    return len(kernel._pre_leaves()) > 0
+
+
 class _Pair(Kernel):
+    _pair_op = None
+
     def __init__(self, cov1, cov2):
         self.cov1 = cov1
         self.cov2 = cov2
@@ -238,39 +468,58 @@ class _Pair(Kernel):
         return self._hyp
     hyp = property(_getHyp, _setHyp)
 
+    def _emit(self, nodes, h0):
+        a = self.cov1._emit(nodes, h0)
+        b = self.cov2._emit(nodes, h0 + len(self.cov1.hyp))
+        nodes.append((self._pair_op, a, b, -1, 0.0))
+        return len(nodes) - 1
+
+    def _pre_leaves(self):
+        return self.cov1._pre_leaves() + self.cov2._pre_leaves()
+
 
 class SumOfKernel(_Pair):
     """k1 + k2 (Core/cov.py:265-295)."""
+    _pair_op = _lib.OP_SUM
 
     def getCovMatrix(self, x=None, z=None, mode=None):
         self.checkInputGetCovMatrix(x, z, mode)
-        return self.cov1.getCovMatrix(x, z, mode) + self.cov2.getCovMatrix(x, z, mode)
+        if _host_combine(self):
+            return self.cov1.getCovMatrix(x, z, mode) + self.cov2.getCovMatrix(x, z, mode)
+        return self._prog_matrix(x, z, mode, None)
 
     def getDerMatrix(self, x=None, z=None, mode=None, der=None):
         self.checkInputGetDerMatrix(x, z, mode, der)
         n1 = len(self.cov1.hyp)
-        if der < n1:
-            return self.cov1.getDerMatrix(x, z, mode, der)
-        if der < len(self.hyp):
+        if not der < len(self.hyp):
+            raise Exception("Error: der out of range for covSum")
+        if _host_combine(self):
+            if der < n1:
+                return self.cov1.getDerMatrix(x, z, mode, der)
             return self.cov2.getDerMatrix(x, z, mode, der - n1)
-        raise Exception("Error: der out of range for covSum")
+        return self._prog_matrix(x, z, mode, der)
 
 
 class ProductOfKernel(_Pair):
     """k1 * k2 (Core/cov.py:230-261)."""
+    _pair_op = _lib.OP_PROD
 
     def getCovMatrix(self, x=None, z=None, mode=None):
         self.checkInputGetCovMatrix(x, z, mode)
-        return self.cov1.getCovMatrix(x, z, mode) * self.cov2.getCovMatrix(x, z, mode)
+        if _host_combine(self):
+            return self.cov1.getCovMatrix(x, z, mode) * self.cov2.getCovMatrix(x, z, mode)
+        return self._prog_matrix(x, z, mode, None)
 
     def getDerMatrix(self, x=None, z=None, mode=None, der=None):
         self.checkInputGetDerMatrix(x, z, mode, der)
         n1 = len(self.cov1.hyp)
-        if der < n1:
-            return self.cov1.getDerMatrix(x, z, mode, der) * self.cov2.getCovMatrix(x, z, mode)
-        if der < len(self.hyp):
+        if not der < len(self.hyp):
+            raise Exception("Error: der out of range for covProduct")
+        if _host_combine(self):
+            if der < n1:
+                return self.cov1.getDerMatrix(x, z, mode, der) * self.cov2.getCovMatrix(x, z, mode)
             return self.cov2.getDerMatrix(x, z, mode, der - n1) * self.cov1.getCovMatrix(x, z, mode)
-        raise Exception("Error: der out of range for covProduct")
+        return self._prog_matrix(x, z, mode, der)
 
 
 class ScaleOfKernel(Kernel):
@@ -294,13 +543,25 @@ class ScaleOfKernel(Kernel):
         return self._hyp
     hyp = property(_getHyp, _setHyp)
 
+    def _emit(self, nodes, h0):
+        a = self.cov._emit(nodes, h0 + 1)
+        nodes.append((_lib.OP_SCALE, a, -1, h0, 0.0))
+        return len(nodes) - 1
+
+    def _pre_leaves(self):
+        return self.cov._pre_leaves()
+
     def getCovMatrix(self, x=None, z=None, mode=None):
         self.checkInputGetCovMatrix(x, z, mode)
-        return np.exp(self.hyp[0]) * self.cov.getCovMatrix(x, z, mode)
+        if _host_combine(self):
+            return np.exp(self.hyp[0]) * self.cov.getCovMatrix(x, z, mode)
+        return self._prog_matrix(x, z, mode, None)
 
     def getDerMatrix(self, x=None, z=None, mode=None, der=None):
         self.checkInputGetDerMatrix(x, z, mode, der)
-        sf2 = np.exp(self.hyp[0])
-        if der == 0:
-            return 2. * sf2 * self.cov.getCovMatrix(x, z, mode)
-        return sf2 * self.cov.getDerMatrix(x, z, mode, der - 1)
+        if _host_combine(self):
+            sf2 = np.exp(self.hyp[0])
+            if der == 0:
+                return 2. * sf2 * self.cov.getCovMatrix(x, z, mode)
+            return sf2 * self.cov.getDerMatrix(x, z, mode, der - 1)
+        return self._prog_matrix(x, z, mode, der)

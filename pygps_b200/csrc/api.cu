@@ -700,19 +700,19 @@ int gpk_set_data(gpk_handle hh, const double* X, int64_t n, int D) {
   return 0;
 }
 
-int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
-                   const double* ymm, int want_der, double* nlZ, double* alpha, double* dcov, double* dlik) {
-  Handle* h;
-  GPK_TRY(check_handle(hh, &h));
+// kind == GPK_COV_PROG: the program has been compiled into h->hprog and uploaded to h->dProg by the caller
+static int exact_eval_core(Handle* h, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
+                           const double* ymm, int want_der, double* nlZ, double* alpha, double* dcov, double* dlik) {
   if (!h->dX || h->n <= 0) return GPK_ERR_STATE;
-  if (!hyp || !ymm || !nlZ || !alpha) return GPK_ERR_ARG;
+  if ((nhyp > 0 && !hyp) || !ymm || !nlZ || !alpha) return GPK_ERR_ARG;
   if (want_der && (!dcov || !dlik)) return GPK_ERR_ARG;
   const int64_t n = h->n, np = h->np;
   const int D = h->D, T = (int)(np / NB);
-  std::vector<double> scale;
+  const bool prog = (kind == GPK_COV_PROG);
+  std::vector<double> scale(D, 1.0);
   int divide = 0;
   double premul = 1.0, sf2 = 1.0;
-  GPK_TRY(kind_scale(kind, matern_d, hyp, nhyp, D, scale, &divide, &premul, &sf2));
+  if (!prog) GPK_TRY(kind_scale(kind, matern_d, hyp, nhyp, D, scale, &divide, &premul, &sf2));
   if (D > 1900) return GPK_ERR_ARG;  // pinned staging layout
   const double sn2 = std::exp(2.0 * log_sn);
   stats_begin(h);
@@ -733,6 +733,10 @@ int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int
     c.kind = kind; c.matern_d = matern_d; c.epi = EPI_COV; c.ard_dim = 0;
     c.sf2 = sf2; c.scale = 1.0 / sn2; c.diag_add = 1.0;
     c.same_set = 1; c.lower_only = 1; c.pad_identity = 1; c.padded128 = 1;
+    if (prog) {                      // composite kernel: the program works on the RAW inputs
+      c.F = h->dX; c.S = h->dX; c.prog = h->dProg; c.prog_der1 = 0; c.padded128 = 0;
+      c.pre = (h->preN == n) ? h->dPre : nullptr; c.pre_ld = n;
+    }
     lazy = c;
   }
   // right-hand side y - m, zero padded; dB is the forward-solve work copy
@@ -777,8 +781,14 @@ int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int
       v.K = (int)np; v.tri = 2;
       GPK_TRY(launch_gemm_nt(h, st, 0, v, T, T));
     }
-    GPK_TRY(launch_dnlz(h, st, h->dXs, n, D, h->dW, np, h->dAlpha, 1.0 / sn2, sf2, kind, matern_d, h->dTmp,
-                        h->capTmp, res + 8));
+    if (prog) {
+      GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, g * g * (nhyp + 1) + 64));
+      GPK_TRY(launch_dnlz_prog(h, st, h->dProg, nhyp, h->dX, n, D, h->dW, np, h->dAlpha, 1.0 / sn2,
+                               (h->preN == n) ? h->dPre : nullptr, n, h->dTmp, h->capTmp, res + 8));
+    } else {
+      GPK_TRY(launch_dnlz(h, st, h->dXs, n, D, h->dW, np, h->dAlpha, 1.0 / sn2, sf2, kind, matern_d, h->dTmp,
+                          h->capTmp, res + 8));
+    }
   }
   GPK_CK(h, cudaEventRecord(h->t4, st));
 
@@ -812,6 +822,40 @@ int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int
   return 0;
 }
 
+int gpk_exact_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
+                   const double* ymm, int want_der, double* nlZ, double* alpha, double* dcov, double* dlik) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!hyp || kind < 0 || kind > GPK_COV_MATERN) return GPK_ERR_ARG;
+  return exact_eval_core(h, kind, matern_d, hyp, nhyp, log_sn, ymm, want_der, nlZ, alpha, dcov, dlik);
+}
+
+int gpk_exact_eval_prog(gpk_handle hh, const gpk_cov_node* nodes, int nnodes, const double* hyp, int nhyp,
+                        double log_sn, const double* ymm, int want_der, double* nlZ, double* alpha, double* dcov,
+                        double* dlik) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!h->dX || h->n <= 0) return GPK_ERR_STATE;
+  GPK_TRY(prog_compile(nodes, nnodes, hyp, nhyp, h->D, &h->hprog));
+  if (prog_has_op(h->hprog, OP_PRE) && h->preN != h->n) return GPK_ERR_STATE;     // gpk_set_pre first
+  if (nhyp + 12 > 4 * h->D + 240) return GPK_ERR_ARG;                             // result slots behind the log-det parts
+  GPK_TRY(prog_upload(h, h->s_main, h->hprog));
+  static const double none = 0.0;
+  return exact_eval_core(h, GPK_COV_PROG, 0, nhyp > 0 ? hyp : &none, nhyp, log_sn, ymm, want_der, nlZ, alpha, dcov, dlik);
+}
+
+int gpk_set_pre(gpk_handle hh, const double* Ktrain, int64_t n) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!Ktrain || n <= 0) return GPK_ERR_ARG;
+  GPK_TRY(ensure(h, &h->dPre, &h->capPre, n * n));
+  GPK_CK(h, cudaMemcpyAsync(h->dPre, Ktrain, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+  GPK_CK(h, cudaStreamSynchronize(h->s_main));
+  h->preN = n;
+  h->stats.h2d_bytes = n * n * (int64_t)sizeof(double);
+  return 0;
+}
+
 int gpk_get_factor(gpk_handle hh, double* R_out) {
   Handle* h;
   GPK_TRY(check_handle(hh, &h));
@@ -842,17 +886,19 @@ int gpk_predict(gpk_handle hh, const double* Xs, int64_t ns, double* ks_alpha, d
   const int64_t cp_max = round_up(ns < chunk ? ns : chunk, NB);
   // dP: transposed cross-covariance chunk (cp_max x np); dTmp: raw + scaled test inputs, partial sums, outputs
   GPK_TRY(ensure(h, &h->dP, &h->capP, cp_max * np));
-  const int64_t tmp_need = 2 * cp_max * D + (int64_t)nsplit * cp_max + 2 * cp_max;
+  const int64_t tmp_need = 2 * cp_max * D + (int64_t)nsplit * cp_max + 3 * cp_max;
   GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, tmp_need));
   double* dXraw = h->dTmp;
   double* dXsc = dXraw + cp_max * D;
   double* dPart = dXsc + cp_max * D;
   double* dOut = dPart + (int64_t)nsplit * cp_max;
   // same input scaling as the posterior's kernel
-  std::vector<double> scale;
+  const bool prog = (h->kind == GPK_COV_PROG);
+  if (prog && prog_has_op(h->hprog, OP_PRE)) return GPK_ERR_STATE;   // cov.Pre: cross-covariances are the caller's (M1)
+  std::vector<double> scale(D, 1.0);
   int divide = 0;
   double premul = 1.0, sf2 = 1.0;
-  GPK_TRY(kind_scale(h->kind, h->matern_d, h->hyp.data(), h->nhyp, D, scale, &divide, &premul, &sf2));
+  if (!prog) GPK_TRY(kind_scale(h->kind, h->matern_d, h->hyp.data(), h->nhyp, D, scale, &divide, &premul, &sf2));
   const double sn = std::sqrt(h->sn2);
   for (int64_t lo = 0; lo < ns; lo += chunk) {
     const int64_t m = (ns - lo < chunk) ? ns - lo : chunk;
@@ -866,6 +912,15 @@ int gpk_predict(gpk_handle hh, const double* Xs, int64_t ns, double* ks_alpha, d
     const bool ep = h->post_ep;                   // EP posterior: sW is a vector (sqrt of the site precisions)
     c.sf2 = sf2; c.scale = ep ? 1.0 : 1.0 / sn; c.diag_add = 0.0; c.same_set = 0; c.lower_only = 0; c.pad_identity = 0;
     c.padded128 = 1;
+    const double* kss_vec = nullptr;
+    if (prog) {
+      // composite kernel: cross-covariances from the program on the raw inputs; prior variances k(z,z) per test point
+      GPK_CK(h, cudaMemsetAsync(h->dP, 0, (size_t)mp * np * sizeof(double), st));   // padding rows / columns
+      c.F = dXraw; c.S = h->dX; c.prog = h->dProg; c.prog_der1 = 0; c.padded128 = 0;
+      c.pF = m; c.pS = n;
+      GPK_TRY(launch_cov_prog_diag(h, st, h->dProg, dXraw, m, D, -1, dOut + 2 * cp_max));
+      kss_vec = dOut + 2 * cp_max;
+    }
     GPK_TRY(launch_cov(h, st, c));
     // Ks' alpha  (undo the 1/sn scaling)
     GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, h->dAlpha, 0, ep ? 1.0 : sn, 0.0, dPart, nsplit, dOut, m));
@@ -876,7 +931,7 @@ int gpk_predict(gpk_handle hh, const double* Xs, int64_t ns, double* ks_alpha, d
       GPK_TRY(sweep_forward_oz(h, st, h->dP, mp, (int)(mp / NB), h->dA, np, h->dDinv, T));
     else
       GPK_TRY(sweep_forward(h, st, h->dP, mp, (int)(mp / NB), h->dA, np, h->dDinv, T));
-    GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, nullptr, 1, 1.0, sf2, dPart, nsplit, dOut + mp, m));
+    GPK_TRY(launch_rowdot(h, st, h->dP, mp, mp, np, nullptr, 1, 1.0, sf2, dPart, nsplit, dOut + mp, m, kss_vec));
     GPK_CK(h, cudaMemcpyAsync(ks_alpha + lo, dOut, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
     GPK_CK(h, cudaMemcpyAsync(fs2 + lo, dOut + mp, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
     GPK_CK(h, cudaStreamSynchronize(st));
@@ -974,6 +1029,67 @@ int gpk_cov_matrix(gpk_handle hh, int kind, int matern_d, const double* hyp, int
   cleanup();
   h->stats.h2d_bytes = (n + (train ? 0 : m)) * D * (int64_t)sizeof(double);
   h->stats.d2h_bytes = n * mm * (int64_t)sizeof(double);
+  return 0;
+}
+
+// getCovMatrix / getDerMatrix of a composite kernel (program), all three modes
+int gpk_cov_matrix_prog(gpk_handle hh, const gpk_cov_node* nodes, int nnodes, const double* hyp, int nhyp,
+                        const double* X, int64_t n, const double* Z, int64_t m, int D, int mode, int der, double* out) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!out || D <= 0 || der >= nhyp) return GPK_ERR_ARG;
+  CovProg prog;
+  GPK_TRY(prog_compile(nodes, nnodes, hyp, nhyp, D, &prog));
+  const bool has_pre = prog_has_op(prog, OP_PRE);
+  stats_begin(h);
+  cudaStream_t st = h->s_main;
+  const bool train = (mode == GPK_MODE_TRAIN), selft = (mode == GPK_MODE_SELF_TEST);
+  if (!train && !selft && mode != GPK_MODE_CROSS) return GPK_ERR_ARG;
+  if (selft ? (!Z || m <= 0) : (!X || n <= 0)) return GPK_ERR_ARG;
+  if (mode == GPK_MODE_CROSS && (!Z || m <= 0)) return GPK_ERR_ARG;
+  if (has_pre && (!train || h->preN != n)) return GPK_ERR_STATE;     // cov.Pre: only the training matrix lives here
+  GPK_TRY(prog_upload(h, st, prog));
+  const int64_t mm = train ? n : m;
+  const int64_t nout = selft ? m : n * mm;
+  double *dXr = nullptr, *dZr = nullptr, *dOut = nullptr;
+  auto cleanup = [&]() {
+    if (dXr) cudaFree(dXr);
+    if (dZr) cudaFree(dZr);
+    if (dOut) cudaFree(dOut);
+  };
+  int rc = 0;
+  cudaError_t e = cudaSuccess;
+  do {
+    if (!selft) {
+      if ((e = cudaMalloc((void**)&dXr, (size_t)n * D * sizeof(double))) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(dXr, X, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    }
+    if (!train) {
+      if ((e = cudaMalloc((void**)&dZr, (size_t)m * D * sizeof(double))) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(dZr, Z, (size_t)m * D * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    }
+    if ((e = cudaMalloc((void**)&dOut, (size_t)nout * sizeof(double))) != cudaSuccess) break;
+    if (selft) {
+      rc = launch_cov_prog_diag(h, st, h->dProg, dZr, m, D, der, dOut);
+    } else {
+      CovArgs c{};
+      // C-order (n, mm) output: fast index = column j (second point set), slow = row i
+      c.F = train ? dXr : dZr; c.S = dXr; c.out = dOut; c.ld = mm;
+      c.nF = mm; c.nS = n; c.pF = mm; c.pS = n; c.D = D;
+      c.scale = 1.0; c.diag_add = 0.0; c.same_set = train ? 1 : 0;
+      c.prog = h->dProg; c.prog_der1 = der + 1;
+      c.pre = has_pre ? h->dPre : nullptr; c.pre_ld = n;
+      rc = launch_cov(h, st, c);
+    }
+    if (rc != 0) break;
+    if ((e = cudaMemcpyAsync(out, dOut, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+    e = cudaStreamSynchronize(st);
+  } while (0);
+  cleanup();
+  if (rc != 0) return rc;
+  GPK_CK(h, e);
+  h->stats.h2d_bytes = ((selft ? 0 : n) + (train ? 0 : m)) * D * (int64_t)sizeof(double);
+  h->stats.d2h_bytes = nout * (int64_t)sizeof(double);
   return 0;
 }
 

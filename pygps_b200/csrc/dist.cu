@@ -179,6 +179,9 @@ int gpk_dist_init(gpk_handle hh, const char* nccl_path, int rank, int world, con
   if (nccl_load(nccl_path) != 0) { h->last_msg = "cannot load libnccl.so.2"; return GPK_ERR_STATE; }
   nccl_uid id;
   std::memcpy(id.internal, id128, 128);
+  // connect every channel inside ncclCommInitRank, not lazily inside the first collective: with the ranks as threads of
+  // one process a lazy connect (which allocates) could land behind a peer's already-enqueued kernel
+  setenv("NCCL_RUNTIME_CONNECT", "0", 0);
   NCCL_CK(h, g_nccl.init_rank(&h->nccl_comm, world, id, rank));
   GPK_CK(h, cudaFuncSetAttribute(bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_SMEM));
   return 0;
@@ -190,6 +193,55 @@ int gpk_dist_finalize(gpk_handle hh) {
   if (h->nccl_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
   h->nccl_comm = nullptr;
   h->world = 1; h->rank = 0;
+  return 0;
+}
+
+// Every device allocation the sharded evaluation (level 0), the factor gather (level 1) and the sharded derivatives
+// (level 2) need for the current problem size.  When the ranks are THREADS of one process (pygps_b200.ShardedEngine),
+// cudaMalloc / cudaFree on one device synchronise with its NCCL peers (peer mappings), so an allocation issued after a
+// peer has already enqueued a collective that waits for this rank dead-locks: the caller reserves on every rank, joins,
+// and only then starts the collective call, which then allocates nothing.
+static int dist_reserve(Handle* h, int level) {
+  const int G = h->world, r = h->rank;
+  const int64_t n = h->n, np = h->np;
+  if (n <= 0 || np <= 0) return GPK_ERR_STATE;
+  const int T = (int)(np / NB);
+  const int64_t ld = np + NB;
+  const int nloc = (T > r) ? (T - 1 - r) / G + 1 : 0;
+  const int64_t ncl = (int64_t)(nloc > 0 ? nloc : 1) * NB;
+  GPK_TRY(ensure(h, &h->gA, &h->cgA, ld * ncl));
+  GPK_TRY(ensure(h, &h->gDinv, &h->cgDinv, ncl * NB));
+  GPK_TRY(ensure(h, &h->gVec, &h->cgVec, np + T + 16 + (int64_t)T * NB + NB));
+  GPK_TRY(ensure(h, &h->gPack, &h->cgPack, 2 * ld * NB));
+  while (h->ev.size() < 4 * (size_t)T + 4) {
+    cudaEvent_t e;
+    GPK_CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev.push_back(e);
+  }
+  const int WD = env_int("GPK_DIST_WD", 8);
+  const bool doz = env_int("GPK_DIST_OZAKI", 1) != 0 && env_int("GPK_OZAKI", 1) != 0 && T >= 4 * WD && WD >= 1 && WD <= 16;
+  if (doz) {
+    GPK_TRY(ensure(h, &h->gBlk, &h->cgBlk, 2 * ld * (int64_t)WD * NB));
+    GPK_TRY(oz_ensure(h, 0, ld, WD * NB));
+  }
+  if (level >= 1) GPK_TRY(ensure(h, &h->dA, &h->capA, np * np));
+  if (level >= 2) {
+    const int t0 = (int)(((int64_t)T * r) / G), t1 = (int)(((int64_t)T * (r + 1)) / G);
+    const int64_t rows = (int64_t)(t1 - t0) * NB;
+    const int64_t g = (n + 63) / 64, gi = (rows + 63) / 64 > 0 ? (rows + 63) / 64 : 1;
+    GPK_TRY(ensure(h, &h->dTmp, &h->capTmp, gi * g * 34 + 64));
+    if (rows > 0) {
+      GPK_TRY(ensure(h, &h->dU, &h->capU, np * np));
+      GPK_TRY(ensure(h, &h->dDinvT, &h->capDinvT, np * NB));
+      GPK_TRY(ensure(h, &h->dW, &h->capW, rows * np));
+    }
+  }
+  if (!h->dFlags) {                                  // (not used by the sharded path; allocated here for completeness)
+    GPK_CK(h, cudaMalloc((void**)&h->dFlags, 1024 * sizeof(int)));
+    GPK_CK(h, cudaMemsetAsync(h->dFlags, 0, 1024 * sizeof(int), h->s_main));
+    h->flag_epoch = 0;
+  }
+  GPK_CK(h, cudaStreamSynchronize(h->s_main));
   return 0;
 }
 
@@ -434,6 +486,13 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
 int gpk_exact_eval_dist(gpk_handle hh, int kind, int matern_d, const double* hyp, int nhyp, double log_sn,
                         const double* ymm, double* nlZ, double* alpha) {
   return exact_eval_dist_impl(hh, kind, matern_d, hyp, nhyp, log_sn, ymm, nlZ, alpha);
+}
+
+int gpk_dist_reserve(gpk_handle hh, int level) {
+  Handle* h;
+  GPK_TRY(check_handle(hh, &h));
+  if (!h->dX) return GPK_ERR_STATE;
+  return dist_reserve(h, level);
 }
 
 // Replicate the distributed factor on every rank: L into dA (np x np, lower), the block inverses into dDinv.  One packed

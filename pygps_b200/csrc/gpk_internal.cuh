@@ -48,6 +48,26 @@ struct GemmArgs {
 
 enum CovEpi { EPI_COV = 0, EPI_DER_ELL = 1, EPI_DER_SF = 2, EPI_DER_ARD = 3 };
 
+// ---- covariance programs: composite kernels evaluated on the device (covprog.cu) ---------------------------------
+// leaf ops 0..2 coincide with GPK_COV_RBF / RBFARD / MATERN
+enum CovOp {
+  OP_RBF = 0, OP_RBFARD = 1, OP_MATERN = 2, OP_RBFUNIT = 3, OP_RQ = 4, OP_RQARD = 5, OP_PERIODIC = 6, OP_PIECEPOLY = 7,
+  OP_GABOR = 8, OP_NOISE = 9, OP_CONST = 10, OP_LINEAR = 11, OP_POLY = 12, OP_PRE = 13,
+  OP_SUM = 32, OP_PROD = 33, OP_SCALE = 34
+};
+constexpr int PROG_MAX_NODES = 32, PROG_MAX_HYP = 96, PROG_MAX_ARD = 2, PROG_MAX_D = 64;
+constexpr int GPK_COV_PROG = 3;      // Handle::kind of a posterior built from a program
+struct ProgNode {
+  int op, a, b, h0;                  // children (node indices, post-order: < own index); first hyper-parameter index
+  int ard, ipar;                     // ARD weight set; integer parameter (Matern d, PiecePoly v, Poly order)
+  double p0, p1, p2, p3;             // derived parameters (see prog_compile)
+};
+struct CovProg {
+  int n_nodes, nhyp, n_ard, D;
+  ProgNode node[PROG_MAX_NODES];
+  double ardw[PROG_MAX_ARD][PROG_MAX_D];   // 1/ell_d^2 per ARD leaf
+};
+
 struct CovArgs {
   const double* F;  // scaled inputs indexed by the FAST output index (nF, D) row-major
   const double* S;  // scaled inputs indexed by the SLOW output index (nS, D)
@@ -66,6 +86,10 @@ struct CovArgs {
   int same_set;     // F and S are the same point set (train mode): f==s is the diagonal
   int lower_only;   // skip tiles entirely above the diagonal (f-tile < s-tile); zero strict upper inside diagonal tiles
   int pad_identity; // padded diagonal entries (f==s>=nF) get 1.0 instead of 0.0
+  const CovProg* prog;   // non-null: evaluate this program (DEVICE pointer) on the RAW inputs F, S instead of `kind`
+  int prog_der1;         //   0: the covariance; h+1: the derivative w.r.t. hyper-parameter h (getDerMatrix)
+  const double* pre;     //   OP_PRE leaf: uploaded training matrix (cov.Pre), entry (f, s) at pre[f + s*pre_ld]
+  int64_t pre_ld;
   int padded128;    // F and S are allocated (and zero beyond nF / nS) up to a multiple of 128 points: enables
                     // cov_tile_kernel (bulk-copied 128-point blocks)
   int s_bstride;    // block-cyclic slow index (multi-GPU): local s maps to the GLOBAL point
@@ -112,6 +136,9 @@ struct Handle {
   double* dP = nullptr; int64_t capP = 0;
   double* dTmp = nullptr; int64_t capTmp = 0;
   double* dXtmp = nullptr; int64_t capXtmp = 0;
+  // covariance program of the current evaluation / posterior (covprog.cu)
+  CovProg hprog{}; CovProg* dProg = nullptr; CovProg* hProgPinned = nullptr;
+  double* dPre = nullptr; int64_t capPre = 0; int64_t preN = 0;     // cov.Pre: uploaded training matrix (n x n)
   // standalone potrf state
   int64_t pn = 0;
   bool lt_valid = false;                       // dU holds L' and dDinvT the transposed block inverses of the CURRENT factor
@@ -169,6 +196,15 @@ struct Handle {
 // ---- launchers (defined in the .cu files) ----------------------------------
 int launch_gemm_nt(Handle* h, cudaStream_t st, int mode /*0 set, 1 sub*/, const GemmArgs& a, int tiles_m, int tiles_n);
 int launch_cov(Handle* h, cudaStream_t st, const CovArgs& a);
+int prog_compile(const gpk_cov_node* nodes, int nnodes, const double* hyp, int nhyp, int D, CovProg* out);
+bool prog_has_op(const CovProg& p, int op);
+int prog_upload(Handle* h, cudaStream_t st, const CovProg& p);
+int launch_cov_prog(Handle* h, cudaStream_t st, const CovArgs& a);
+int launch_cov_prog_diag(Handle* h, cudaStream_t st, const CovProg* dprog, const double* Z, int64_t m, int D, int der,
+                         double* out);
+int launch_dnlz_prog(Handle* h, cudaStream_t st, const CovProg* dprog, int nhyp, const double* X, int64_t n, int D,
+                     const double* Ainv, int64_t ld, const double* alpha, double inv_sn2, const double* pre,
+                     int64_t pre_ld, double* part, int64_t part_cap, double* res);
 int launch_prescale(Handle* h, cudaStream_t st, const double* X, int64_t n, int64_t np, int D,
                     const double* scale, int divide, double premul, double* out);
 int launch_diag(Handle* h, cudaStream_t st, double* Ablk, int64_t lda, double* Dinv, double* logdet_slot,
@@ -189,7 +225,8 @@ int launch_compact_lower(Handle* h, cudaStream_t st, const double* src, int64_t 
 int launch_compact_sym(Handle* h, cudaStream_t st, const double* src, int64_t ld, int64_t n, double* dst);
 int launch_set_identity(Handle* h, cudaStream_t st, double* M, int64_t ld, int64_t rows, int64_t cols);
 int launch_rowdot(Handle* h, cudaStream_t st, const double* P, int64_t ld, int64_t rows, int64_t cols, const double* v,
-                  int mode, double scale, double kss, double* part, int nsplit, double* out, int64_t nvalid);
+                  int mode, double scale, double kss, double* part, int nsplit, double* out, int64_t nvalid,
+                  const double* kss_vec = nullptr /*mode 1: per-point prior variances instead of the scalar kss*/);
 int launch_dnlz(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
                 const double* alpha, double inv_sn2, double sf2, int kind, int matern_d, double* part,
                 int64_t part_cap, double* res);

@@ -315,6 +315,7 @@ int launch_prescale(Handle* h, cudaStream_t st, const double* X, int64_t n, int6
 }
 
 int launch_cov(Handle* h, cudaStream_t st, const CovArgs& a) {
+  if (a.prog) return launch_cov_prog(h, st, a);
   const int64_t gf = (a.pF + CT - 1) / CT, gs = (a.pS + CT - 1) / CT;
   if (gf <= 0 || gs <= 0) return 0;
   if (cov_tile_ok(a)) {

@@ -122,12 +122,13 @@ __global__ void __launch_bounds__(128) rowdot_kernel(const double* __restrict__ 
 
 // out[c] = post( sum_split part[split][c] ):  mode 0: scale*sum ; mode 1: max(kss - sum, 0)
 __global__ void rowdot_finish_kernel(const double* __restrict__ part, int nsplit, int64_t rows, int mode, double scale,
-                                     double kss, double* __restrict__ out, int64_t nvalid) {
+                                     double kss, double* __restrict__ out, int64_t nvalid,
+                                     const double* __restrict__ kss_vec) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nvalid) return;
   double s = 0.0;
   for (int sp = 0; sp < nsplit; ++sp) s += part[(int64_t)sp * rows + c];
-  out[c] = (mode == 0) ? s * scale : fmax(kss - s, 0.0);
+  out[c] = (mode == 0) ? s * scale : fmax((kss_vec ? kss_vec[c] : kss) - s, 0.0);
 }
 
 // ---------------------------------------------------------------------------
@@ -328,11 +329,12 @@ int launch_set_identity(Handle* h, cudaStream_t st, double* M, int64_t ld, int64
   return 0;
 }
 int launch_rowdot(Handle* h, cudaStream_t st, const double* P, int64_t ld, int64_t rows, int64_t cols, const double* v,
-                  int mode, double scale, double kss, double* part, int nsplit, double* out, int64_t nvalid) {
+                  int mode, double scale, double kss, double* part, int nsplit, double* out, int64_t nvalid,
+                  const double* kss_vec) {
   dim3 grid((unsigned)((rows + 127) / 128), (unsigned)nsplit);
   rowdot_kernel<<<grid, 128, 0, st>>>(P, ld, cols, v, mode, nsplit, part, rows);
   rowdot_finish_kernel<<<(unsigned)((nvalid + 255) / 256), 256, 0, st>>>(part, nsplit, rows, mode, scale, kss, out,
-                                                                         nvalid);
+                                                                         nvalid, kss_vec);
   h->stats.launches += 2;
   GPK_CK(h, cudaGetLastError());
   return 0;

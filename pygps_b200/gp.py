@@ -177,7 +177,10 @@ class GP(object):
             return False
         dev = self.covfunc._device_spec()
         if dev is None:
-            return False
+            prog = self.covfunc._device_prog() if not isinstance(self.covfunc, FITCOfKernel) else None
+            if prog is None:
+                return False
+            dev = ('prog', tuple(prog[0]), prog[1])
         kind, md, hyp = dev
         lik0 = float(self.likfunc.hyp[0]) if self.likfunc.hyp else 0.0
         return (spec[1] == kind and spec[2] == md and tuple(hyp) == spec[3] and lik0 == spec[4])

@@ -80,7 +80,10 @@ class postStruct(object):
                 _, kind, md, hyp, log_sn = self._spec
                 eng = _scratch_engine()
                 eng.set_data(self._x)
-                eng.exact_eval(kind, md, list(hyp), log_sn, np.zeros(self._x.shape[0]), False)
+                if kind == 'prog':
+                    eng.exact_eval_prog(list(md), list(hyp), log_sn, np.zeros(self._x.shape[0]), False)
+                else:
+                    eng.exact_eval(kind, md, list(hyp), log_sn, np.zeros(self._x.shape[0]), False)
                 self._L = eng.get_factor(self._n)
         return self._L
 
@@ -217,9 +220,11 @@ class Exact(Inference):
         n, D = x.shape
         m = meanfunc.getMean(x)
         sn2 = np.exp(2 * likfunc.hyp[0])
-        spec = covfunc._device_spec() if not isinstance(covfunc, cov.FITCOfKernel) else None
+        if isinstance(covfunc, cov.FITCOfKernel):
+            raise Exception('inf.Exact needs a plain covariance function (use inf.FITC_Exact with cov.FITCOfKernel)')
+        spec = covfunc._device_spec()
         if spec is None:
-            return self._evaluate_generic(meanfunc, covfunc, likfunc, x, y, m, sn2, nargout)
+            return self._evaluate_program(meanfunc, covfunc, likfunc, x, y, m, sn2, nargout)
         kind, md, hyp = spec
         eng = self._get_sharded() if self._wants_sharding(n) else self._get_engine()
         eng.set_data(x)
@@ -231,6 +236,10 @@ class Exact(Inference):
         post._engine, post._epoch, post._n = eng, eng.epoch, n
         post._spec = ('exact', kind, md, tuple(hyp), float(likfunc.hyp[0]))
         _seal(post, x)
+        return self._pack(post, nlZ, dcov, dlik, meanfunc, covfunc, likfunc, x, alpha, nargout)
+
+    @staticmethod
+    def _pack(post, nlZ, dcov, dlik, meanfunc, covfunc, likfunc, x, alpha, nargout):
         if nargout > 1:
             if nargout > 2:
                 dnlZ = dnlZStruct(meanfunc, covfunc, likfunc)
@@ -241,29 +250,38 @@ class Exact(Inference):
             return post, nlZ
         return post
 
-    def _evaluate_generic(self, meanfunc, covfunc, likfunc, x, y, m, sn2, nargout):
-        """Composite kernels: K is assembled from device-built pieces on the host, the
-        factorisation and solves still run on the GPU (gpk_potrf / gpk_potrs)."""
+    def _evaluate_program(self, meanfunc, covfunc, likfunc, x, y, m, sn2, nargout):
+        """Composite kernels and the kernels without a dedicated build: the covariance PROGRAM (cov._device_prog) is
+        evaluated on the device inside the same single foreign call - matrix build, factorisation, solves, and one
+        fused pass for ALL hyper-parameter derivatives of all components (csrc/covprog.cu).  A cov.Pre leaf reads its
+        training matrix from device memory (uploaded here, gpk_set_pre)."""
         n = x.shape[0]
-        K = covfunc.getCovMatrix(x=x, mode='train')
-        L = jitchol(K / sn2 + np.eye(n)).T
-        alpha = solve_chol(L, y - m) / sn2
+        prog = covfunc._device_prog()
+        pres = covfunc._pre_leaves()
+        if prog is None or len(pres) > 1:
+            raise Exception('%s: this covariance function has no device implementation (there is no CPU fallback)'
+                            % type(covfunc).__name__)
+        nodes, hyp = prog
+        eng = self._get_engine()
+        eng.set_data(x)
+        if pres:
+            M2 = np.asarray(pres[0].M2, dtype=np.float64)
+            if M2.shape != (n, n):
+                raise Exception('cov.Pre: the training matrix M2 must be (n,n) for n training inputs')
+            eng.set_pre(M2)
+        nlZ, alpha, dcov, dlik = eng.exact_eval_prog(nodes, hyp, likfunc.hyp[0], y - m, nargout > 2)
         post = postStruct()
         post.alpha = alpha
         post.sW = np.ones((n, 1)) / np.sqrt(sn2)
-        post.L = np.ascontiguousarray(L)
-        if nargout > 1:
-            nlZ = (np.dot((y - m).T, alpha) / 2. + np.log(np.diag(L)).sum() + n * np.log(2 * np.pi * sn2) / 2.)[0, 0]
-            if nargout > 2:
-                dnlZ = dnlZStruct(meanfunc, covfunc, likfunc)
-                Q = solve_chol(L, np.eye(n)) / sn2 - np.dot(alpha, alpha.T)
-                dnlZ.lik = [sn2 * np.trace(Q)]
-                for ii in range(len(covfunc.hyp)):
-                    dnlZ.cov[ii] = (Q * covfunc.getDerMatrix(x=x, mode='train', der=ii)).sum() / 2.
-                _mean_derivs(meanfunc, x, alpha, dnlZ)
-                return post, nlZ, dnlZ
-            return post, nlZ
-        return post
+        post._L = None
+        post._engine, post._epoch, post._n = eng, eng.epoch, n
+        # a posterior with a Pre leaf cannot be predicted from on the device (its cross-covariances are host matrices)
+        post._spec = None if pres else ('exact', 'prog', tuple(nodes), tuple(hyp), float(likfunc.hyp[0]))
+        _seal(post, x)
+        if pres:
+            post._x = None                       # no rebuild path either: fetch the factor while it is resident
+            post.L
+        return self._pack(post, nlZ, dcov, dlik, meanfunc, covfunc, likfunc, x, alpha, nargout)
 
 
 class EP(Inference):

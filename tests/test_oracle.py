@@ -205,3 +205,117 @@ def test_erf_special_functions_cover_all_branches():
     n_p = go.erf_gau_over_cum_gauss(z, p)
     np.testing.assert_allclose(n_p[z > -5], norm.pdf(z[z > -5]) / norm.cdf(z[z > -5]), rtol=1e-10)
     assert np.all(np.diff(n_p) < 0)
+
+
+PROGRAM_SPECS = {
+    "rbfunit": (("rbfunit", [0.3]), 3),
+    "rq": (("rq", [0.2, -0.1, 0.4]), 3),
+    "rqard": (("rqard", [0.1, -0.2, 0.3, 0.2, -0.3]), 3),
+    "periodic": (("periodic", [0.2, 0.5, 0.1]), 1),
+    "piecepoly0": (("piecepoly", [0.9, 0.1], 0), 3),
+    "piecepoly1": (("piecepoly", [0.9, 0.1], 1), 3),
+    "piecepoly2": (("piecepoly", [0.9, 0.1], 2), 3),
+    "piecepoly3": (("piecepoly", [1.2, -0.2], 3), 3),
+    "gabor": (("gabor", [0.4, 0.3]), 3),
+    "noise": (("noise", [-0.7]), 3),
+    "const": (("const", [0.3]), 3),
+    "linear": (("linear", [-0.4]), 3),
+    "poly": (("poly", [0.2, -0.3], 3), 3),
+    "comp3": (("sum", ("sum", ("sum", ("prod", ("rbf", [0.3, 0.1]), ("matern", [0.5, -0.2], 5)),
+                               ("scale", 1.5, ("rq", [0.2, -0.1, 0.4]))), ("noise", [-1.0])),
+               ("prod", ("const", [-0.5]), ("linear", [-1.0]))), 3),
+    "comp1": (("sum", ("sum", ("sum", ("rbf", [1.0, 0.5]), ("prod", ("periodic", [0.2, 0.5, 0.1]), ("rbf", [1.5, -0.2]))),
+                       ("rq", [0.1, -0.4, -0.2])), ("sum", ("rbf", [-1.0, -1.0]), ("noise", [-1.5]))), 1),
+}
+# derivative matrices the reference gets structurally wrong (checked by finite differences instead):
+#   Matern, BOTH derivatives (Core/cov.py:1173-1177: the distance is overwritten by K before it is used);
+#   RQard length scales (:1413-1420: identically zero in train mode, scaled by ell instead of 1/ell in cross mode)
+BROKEN_IN_REFERENCE = {("rqard", 0), ("rqard", 1), ("rqard", 2), ("comp3", 2), ("comp3", 3)}
+
+
+def test_program_kernels_and_composites_against_reference(golden):
+    g = golden("cov_programs")
+    for name, (spec, D) in PROGRAM_SPECS.items():
+        x, z = (g["x3"], g["z3"]) if D == 3 else (g["x1"], g["z1"])
+        close(go.cov_matrix(spec, x=x, mode="train"), g[name + "_train"], rtol=1e-12, atol=1e-14)
+        close(go.cov_matrix(spec, x=x, z=z, mode="cross"), g[name + "_cross"], rtol=1e-12, atol=1e-14)
+        close(go.cov_matrix(spec, z=z, mode="self_test"), g[name + "_self"], rtol=1e-12, atol=1e-14)
+        assert go.cov_nhyp(spec, D) == len(g[name + "_hyp"])
+        for i in range(go.cov_nhyp(spec, D)):
+            if (name, i) in BROKEN_IN_REFERENCE:
+                continue
+            close(go.cov_der_matrix(spec, x=x, mode="train", der=i), g["%s_dtrain%d" % (name, i)], rtol=1e-11, atol=1e-13)
+            close(go.cov_der_matrix(spec, x=x, z=z, mode="cross", der=i), g["%s_dcross%d" % (name, i)], rtol=1e-11, atol=1e-13)
+            close(go.cov_der_matrix(spec, z=z, mode="self_test", der=i), g["%s_dself%d" % (name, i)], rtol=1e-11, atol=1e-13)
+
+
+def test_true_derivatives_where_the_reference_is_broken(golden):
+    """RQard length-scale derivatives by central differences of the (reference-pinned) covariance itself."""
+    g = golden("cov_programs")
+    x = g["x3"]
+    hyp = [0.1, -0.2, 0.3, 0.2, -0.3]
+    for i in range(3):
+        hp, hm = list(hyp), list(hyp)
+        hp[i] += 1e-6; hm[i] -= 1e-6
+        fd = (go.cov_matrix(("rqard", hp), x=x, mode="train") - go.cov_matrix(("rqard", hm), x=x, mode="train")) / 2e-6
+        close(go.cov_der_matrix(("rqard", hyp), x=x, mode="train", der=i), fd, rtol=1e-6, atol=1e-8)
+        assert np.all(g["rqard_dtrain%d" % i] == 0)          # what the reference returns
+    # the whole gradient of the 3-d composite (it contains a Matern factor) by central differences
+    spec, D = PROGRAM_SPECS["comp3"]
+
+    def rebuild(sp, h, pos=0):
+        k = sp[0]
+        if k in ("sum", "prod"):
+            a, pos = rebuild(sp[1], h, pos)
+            b, pos = rebuild(sp[2], h, pos)
+            return (k, a, b), pos
+        if k == "scale":
+            c = h[pos]
+            a, pos = rebuild(sp[2], h, pos + 1)
+            return (k, c, a), pos
+        n = len(sp[1])
+        return (k, list(h[pos:pos + n])) + tuple(sp[2:]), pos + n
+
+    def flat(sp):
+        k = sp[0]
+        if k in ("sum", "prod"):
+            return flat(sp[1]) + flat(sp[2])
+        if k == "scale":
+            return [sp[1]] + flat(sp[2])
+        return list(sp[1])
+    h0 = flat(spec)
+    assert rebuild(spec, h0)[0] == spec
+    for i in range(len(h0)):
+        hp, hm = list(h0), list(h0)
+        hp[i] += 1e-6; hm[i] -= 1e-6
+        fd = (go.cov_matrix(rebuild(spec, hp)[0], x=x, mode="train") - go.cov_matrix(rebuild(spec, hm)[0], x=x, mode="train")) / 2e-6
+        an = go.cov_der_matrix(spec, x=x, mode="train", der=i)
+        if spec_is_reference_convention(spec, i):
+            an = an / 2.0          # ScaleOfKernel / Const / Linear: the reference's derivative carries a factor 2 (exp(h), not exp(2h))
+        close(an, fd, rtol=2e-6, atol=1e-8)
+
+
+def spec_is_reference_convention(spec, i):
+    """comp3's hyper-parameter order: rbf(0,1) matern(2,3) scale(4) rq(5,6,7) noise(8) const(9) linear(10)."""
+    return i in (4, 9, 10)
+
+
+MAUNA = ("sum", ("sum", ("sum", ("rbf", [np.log(67.), np.log(66.)]),
+                         ("prod", ("periodic", [np.log(1.3), np.log(1.0), np.log(2.4)]), ("rbf", [np.log(90.), np.log(2.4)]))),
+                 ("rq", [np.log(1.2), np.log(0.66), np.log(0.78)])),
+         ("sum", ("rbf", [np.log(1.6 / 12.), np.log(0.18)]), ("noise", [np.log(0.19)])))
+
+
+def test_mauna_loa_composite_against_reference(golden):
+    """Demo/MaunaLoa/demo_MaunaLoa.py:65-68: k1 + k2 + k3 + k4 with 13 hyper-parameters, Const mean from setData."""
+    g = golden("cov_programs")
+    X, Y, xs = g["mauna_x"], g["mauna_y"], g["mauna_xs"]
+    mean = ("const", float(g["mauna_c"]))
+    post, nlZ, dn = go.exact_evaluate(mean, MAUNA, np.log(0.1), X, Y, 3)
+    close(nlZ, g["mauna_nlZ"], rtol=1e-9)
+    close(dn["cov"], g["mauna_dcov"], rtol=1e-6, atol=1e-8)
+    close(dn["lik"], g["mauna_dlik"], rtol=1e-6)
+    close(post["alpha"], g["mauna_alpha"], rtol=1e-6, atol=1e-8 * np.abs(g["mauna_alpha"]).max())
+    ym, ys2 = go.predict(mean, MAUNA, np.log(0.1), X, post, xs)[:2]
+    close(ym, g["mauna_ym"], rtol=1e-8)
+    close(ys2, g["mauna_ys2"], rtol=1e-6)
