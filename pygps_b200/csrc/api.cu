@@ -1,5 +1,6 @@
 // api.cu - the extern "C" surface of libgpk.so (include/gpk.h) and the host-side
 // orchestration of the blocked right-looking Cholesky with one-panel look-ahead.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <new>
@@ -101,16 +102,43 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   }
   bstart.push_back(T);
   const int nblk = (int)bstart.size() - 1;
-  if (need0) {
-    kw0 = (int)((need0 + rows0 - 1) / rows0);             // capacity rows0 x kw0 covers every block's slices
-    GPK_TRY(oz_ensure(h, 0, rows0, kw0));
+  // Fixed row scales (GPK_OZ_FIXED, default on): |L_ij| <= sqrt(A_ii), so ONE scale per matrix row is valid for every
+  // panel.  Each sub-block is then sliced once, right when it is complete, on the panel stream, into a buffer indexed by
+  // GLOBAL row and by the k-position inside the level-1 block; the level-2 update of the block's other columns and the
+  // level-1 update of the trailing matrix read the same digits.  This removes the row-maximum passes, the second read of
+  // every panel and - the point - the slicing of the whole block from the critical stream of the level-1 hand-over.
+  // Two buffers alternate between consecutive blocks (block j+1's sub-blocks are sliced while update j still runs).
+  const bool fixed = oz && (need0 || need1) && env_int("GPK_OZ_FIXED", 1) != 0;
+  if (fixed) {
+    int wmax = 0;
+    for (size_t b = 0; b + 1 < bstart.size(); ++b) wmax = std::max(wmax, bstart[b + 1] - bstart[b]);
+    GPK_TRY(oz_ensure(h, 0, np, wmax * NB));
+    GPK_TRY(oz_ensure(h, 1, np, wmax * NB));
+    if (h->ozFixCap < (size_t)np) {
+      if (h->ozFix) cudaFree(h->ozFix);
+      h->ozFix = nullptr; h->ozFixCap = 0;
+      GPK_CK(h, cudaMalloc((void**)&h->ozFix, (size_t)np * sizeof(double)));
+      h->ozFixCap = (size_t)np;
+    }
+  } else {
+    if (need0) {
+      kw0 = (int)((need0 + rows0 - 1) / rows0);             // capacity rows0 x kw0 covers every block's slices
+      GPK_TRY(oz_ensure(h, 0, rows0, kw0));
+    }
+    if (need1) GPK_TRY(oz_ensure(h, 1, rows1, W2 * NB));
   }
-  if (need1) GPK_TRY(oz_ensure(h, 1, rows1, W2 * NB));
-  GPK_TRY(ensure_events(h, 5 * (size_t)T + 4));
+  const size_t rowbytes = (size_t)oz_slices() * 32;        // bytes per buffer row per k-step
+  auto fx_sl = [&](int j, int row_tile, int kstep0) {        // slice-buffer address of (row tile, k-step) of block j
+    return h->ozSl[j & 1] + ((size_t)kstep0 * np + (size_t)row_tile * NB) * rowbytes;
+  };
+  GPK_TRY(ensure_events(h, 5 * (size_t)T + 5));
   if (h->profile) GPK_TRY(ensure_prof_events(h, 2 * (size_t)T + 2));
   cudaEvent_t* ev_panel = h->ev.data();      // [T]   panel p factored and solved
   cudaEvent_t* ev_col = h->ev.data() + T;    // [T]   columns of level-1 block j up to date
-  cudaEvent_t ev_fork = h->ev[2 * T], ev_join = h->ev[2 * T + 1], ev_aux = h->ev[2 * T + 2];
+  cudaEvent_t ev_fork = h->ev[2 * T], ev_join = h->ev[2 * T + 1], ev_aux = h->ev[2 * T + 2], ev_fix = h->ev[2 * T + 3];
+  bool fix_pending = false;                   // the panel stream still has to wait for the fixed scales (ev_fix)
+  cudaEvent_t ev_built = h->ev[5 * T + 4];    // lazy_cov: the WHOLE matrix exists (the columns behind the first block too)
+  bool built_pending = false;
   cudaEvent_t* ev_diag = h->ev.data() + 2 * T + 4;   // [T] diagonal block p factored and inverted   (split chain)
   cudaEvent_t* ev_head = ev_diag + T;                // [T] head of panel p: tile (p+1,p) solved, tile (p+1,p+1) updated
   cudaEvent_t* ev_tail = ev_head + T;                // [T] tail of panel p: rows p+2.. solved, rest of the sub-block updated
@@ -130,6 +158,11 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
     const int64_t c1 = (int64_t)bstart[1] * NB;
     CovArgs c = *lazy_cov;
     c.pS = c1;
+    // stationary kernels: A_ii = sf2*scale + diag_add for every i - the fixed scales need no look at the matrix
+    const bool const_diag = fixed && !lazy_cov->prog;
+    if (const_diag)
+      GPK_TRY(launch_oz_fixed_scales(h, h->s_main, nullptr, 0, (int)np, lazy_cov->sf2 * lazy_cov->scale + lazy_cov->diag_add,
+                                     h->ozFix));
     GPK_TRY(launch_cov(h, h->s_main, c));
     GPK_CK(h, cudaEventRecord(ev_fork, h->s_main));
     if (c1 < np) {
@@ -140,7 +173,20 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
       GPK_TRY(launch_cov(h, h->s_main, r));
     }
     GPK_CK(h, cudaEventRecord(h->t1, h->s_main));
+    if (c1 < np) {
+      // The panel stream works inside the first block's columns until the block is done; the first thing it touches
+      // outside them is the head update of the next diagonal tile at the hand-over - it must not run before the builder
+      // has written that tile (a slow builder - a long composite program - used to lose this race).
+      GPK_CK(h, cudaEventRecord(ev_built, h->s_main));
+      built_pending = true;
+    }
+    if (fixed && !const_diag) {                 // composite kernels: the diagonal is read once the whole matrix exists
+      GPK_TRY(launch_oz_fixed_scales(h, h->s_main, A, lda, (int)np, 0.0, h->ozFix));
+      GPK_CK(h, cudaEventRecord(ev_fix, h->s_main));
+      fix_pending = true;
+    }
   } else {
+    if (fixed) GPK_TRY(launch_oz_fixed_scales(h, h->s_main, A, lda, (int)np, 0.0, h->ozFix));
     GPK_CK(h, cudaEventRecord(ev_fork, h->s_main));
   }
   GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_fork, 0));
@@ -228,12 +274,22 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
       }
       // the sub-block is complete when its last panel's tail is (the panel stream runs the level-2 / level-1 hand-over)
       if (split && se - 1 >= sb) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_tail[se - 1], 0));
+      // fixed scales: this sub-block's digits, once, for the level-2 update below AND the level-1 update of the block
+      const bool fx_blk = fixed && bbig[j] && T - pe >= oz_min;
+      if (fx_blk && T - se > 0) {
+        if (fix_pending) { GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_fix, 0)); fix_pending = false; }
+        GPK_TRY(launch_oz_slice_fixed(h, h->s_panel, A + (int64_t)se * NB + (int64_t)sb * NB * lda, lda, (T - se) * NB,
+                                      (se - sb) * NB, h->ozSl[j & 1], h->ozFix, (int)np, se * NB, (sb - pb) * 4));
+      }
       if (se < pe) {
         // level-2 update: the block's remaining columns [se, pe), all rows below the sub-block
         const int rows = T - se, cols = pe - se, kw2 = (se - sb) * NB;
         double* P2 = A + (int64_t)se * NB + (int64_t)sb * NB * lda;
         double* C2 = A + (int64_t)se * NB * (1 + lda);
-        if (oz && rows >= oz_min) {
+        if (fx_blk) {
+          GPK_TRY(launch_oz_syrk_buf(h, h->s_panel, fx_sl(j, se, (sb - pb) * 4), h->ozFix + (int64_t)se * NB, (int)np, C2,
+                                     lda, rows * NB, kw2, 0, cols, 0));
+        } else if (oz && rows >= oz_min) {
           GPK_TRY(launch_oz_slice(h, 1, h->s_panel, P2, lda, rows * NB, kw2));
           GPK_TRY(launch_oz_syrk(h, 1, h->s_panel, C2, lda, rows * NB, kw2, 0, cols));
         } else {
@@ -257,13 +313,27 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
       // Panel-chain-bound blocks: the next block's first diagonal tile gets its update on the PANEL stream (four
       // 32-row strips), so the next diagonal kernel starts at once and overlaps the update of the other tiles.
       head_l1 = split && head_l1_on && !bbig[j];
+      if (head_l1 && built_pending) { GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_built, 0)); built_pending = false; }
       if (head_l1) {
         GemmArgs hl{};
         hl.A = Pblk; hl.B = Pblk; hl.C = Ctr;
         hl.lda = lda; hl.ldb = lda; hl.ldc = lda; hl.K = kw; hl.tri = 1; hl.strips = 1;
         GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, hl, 1, 1));
       }
-      if (oz && rem >= oz_min) {
+      if (fixed && rem >= oz_min) {
+        // int8 tensor cores, fixed row scales.  Big blocks: every sub-block was sliced on the panel stream when it was
+        // complete - nothing to do here but the update.  Small (single sub-block) blocks: slice here, without a
+        // row-maximum pass.
+        if (!bbig[j]) {
+          if (fix_pending) { GPK_CK(h, cudaStreamWaitEvent(h->s_main, ev_fix, 0)); }
+          GPK_TRY(launch_oz_slice_fixed(h, h->s_main, Pblk, lda, rem * NB, kw, h->ozSl[j & 1], h->ozFix, (int)np, pe * NB, 0));
+        }
+        const int8_t* sl1 = fx_sl(j, pe, 0);
+        const double* sc1 = h->ozFix + (int64_t)pe * NB;
+        GPK_TRY(launch_oz_syrk_buf(h, h->s_main, sl1, sc1, (int)np, Ctr, lda, rem * NB, kw, 0, first, head_l1 ? 1 : 0));
+        GPK_CK(h, cudaEventRecord(ev_col[j + 1], h->s_main));
+        if (rem > first) GPK_TRY(launch_oz_syrk_buf(h, h->s_main, sl1, sc1, (int)np, Ctr, lda, rem * NB, kw, first, rem, 0));
+      } else if (oz && rem >= oz_min) {
         // int8 tensor-core path (ozaki.cu): slice the panel block once, then the same two launches
         GPK_TRY(launch_oz_slice(h, 0, h->s_main, Pblk, lda, rem * NB, kw));
         GPK_TRY(launch_oz_syrk(h, 0, h->s_main, Ctr, lda, rem * NB, kw, 0, first, head_l1 ? 1 : 0));

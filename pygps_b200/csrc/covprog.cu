@@ -133,8 +133,8 @@ __device__ void prog_backward(const CovProg& P, const double* val, double* adj) 
 // d leaf / d (its own hyper-parameters, in the reference's order), times `w`, accumulated into acc[h0 ...].  The per-dimension
 // ARD derivatives need the pair's coordinates: xi, xj (D doubles each).  diag as in leaf_value (train mode only: the
 // derivative reduction runs over the training matrix).
-__device__ void leaf_grad(const CovProg& P, const ProgNode& nd, const PairGeom& g, bool diag, double w, const double* xi,
-                          const double* xj, double* acc) {
+__device__ void leaf_grad(const CovProg& P, const ProgNode& nd, const PairGeom& g, bool diag, bool train, double w,
+                          const double* xi, const double* xj, double* acc) {
   switch (nd.op) {
     case OP_RBF: {
       const double d2 = g.r2 * nd.p0, k = nd.p1 * exp(-0.5 * d2);
@@ -207,7 +207,7 @@ __device__ void leaf_grad(const CovProg& P, const ProgNode& nd, const PairGeom& 
       acc[nd.h0 + 1] += w * dp * e * sin(dp);
       break;
     }
-    case OP_NOISE: acc[nd.h0] += w * 2.0 * (diag ? nd.p0 : 0.0); break;
+    case OP_NOISE: acc[nd.h0] += w * 2.0 * ((train ? diag : (g.r2 < 1.0e-9)) ? nd.p0 : 0.0); break;
     case OP_CONST: acc[nd.h0] += w * 2.0 * nd.p0; break;
     case OP_LINEAR: acc[nd.h0] += w * 2.0 * nd.p0 * (g.dot + (diag ? 1.0e-16 : 0.0)); break;
     case OP_POLY: {
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) cov_prog_kernel(const CovArgs a) {
         for (int i = 0; i < P.n_nodes; ++i) {
           const ProgNode& nd = P.node[i];
           if (nd.op == OP_SCALE) gacc[nd.h0] += adj[i] * 2.0 * nd.p0 * val[nd.a];   // Core/cov.py:323-325
-          else if (nd.op < OP_SUM) leaf_grad(P, nd, g, diag, adj[i], Fs + tf * D, Ss + j * D, gacc);
+          else if (nd.op < OP_SUM) leaf_grad(P, nd, g, diag, train, adj[i], Fs + tf * D, Ss + j * D, gacc);
         }
         v = gacc[a.prog_der1 - 1];
       }
@@ -317,7 +317,7 @@ __global__ void cov_prog_diag_kernel(const CovProg* __restrict__ prog, const dou
       const ProgNode& nd = P.node[k];
       if (nd.op == OP_SCALE) gacc[nd.h0] += adj[k] * 2.0 * nd.p0 * val[nd.a];
       else if (nd.op == OP_NOISE) { /* self-test derivative of Noise is 0 (Core/cov.py:1286-1288) */ }
-      else if (nd.op < OP_SUM) leaf_grad(P, nd, g, false, adj[k], Z + i * D, Z + i * D, gacc);
+      else if (nd.op < OP_SUM) leaf_grad(P, nd, g, false, true, adj[k], Z + i * D, Z + i * D, gacc);
     }
     v = gacc[der];
   }
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256) dnlz_prog_kernel(const DnlzProgArgs a) {
       for (int k = 0; k < P.n_nodes; ++k) {
         const ProgNode& nd = P.node[k];
         if (nd.op == OP_SCALE) acc[nd.h0] += w * adj[k] * 2.0 * nd.p0 * val[nd.a];
-        else if (nd.op < OP_SUM) leaf_grad(P, nd, g, diag, w * adj[k], Xi + ti * D, Xj + jj * D, acc);
+        else if (nd.op < OP_SUM) leaf_grad(P, nd, g, diag, true, w * adj[k], Xi + ti * D, Xj + jj * D, acc);
       }
       if (diag) acc[nh] += q;
     }

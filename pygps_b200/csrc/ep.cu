@@ -127,10 +127,15 @@ __global__ void ep_set_int_kernel(int* p, int v) { *p = v; }
 __global__ void __launch_bounds__(256) ep_site_blk_kernel(const double* __restrict__ Sig, int64_t ld, int64_t n,
                                                           const int* __restrict__ i0p, int t,
                                                           const double* __restrict__ y,
-                                                          const double* __restrict__ m, double* __restrict__ ttau,
-                                                          double* __restrict__ tnu, double* __restrict__ mu,
+                                                          const double* __restrict__ m,
+                                                          const double* __restrict__ ttau,
+                                                          const double* __restrict__ tnu, double* __restrict__ mu,
                                                           double* __restrict__ S, double* __restrict__ Sc,
-                                                          double* __restrict__ cvec, double* __restrict__ mun) {
+                                                          double* __restrict__ cvec, double* __restrict__ mun,
+                                                          double* __restrict__ ttau_new, double* __restrict__ tnu_new) {
+  // ttau / tnu are READ by every CTA of this launch (each recomputes the site scalars); the new site parameters go to
+  // the staging vectors ttau_new / tnu_new and are committed once per sweep - a CTA scheduled late can therefore never
+  // see the values CTA 0 writes at the end of the same launch.
   const int i = *i0p + t;
   if (i >= n) return;
   const double* mu_in = mun + (i & 1);
@@ -195,8 +200,8 @@ __global__ void __launch_bounds__(256) ep_site_blk_kernel(const double* __restri
     if (r == i + 1) mu_out[0] = munew;           // mu of the NEXT site, read by its launch (two alternating slots)
   }
   if (blockIdx.x == 0 && tid == 0) {
-    ttau[i] = s_tt;
-    tnu[i] = s_tn;
+    ttau_new[i] = s_tt;
+    tnu_new[i] = s_tn;
     cvec[t] = c;
   }
 }
@@ -406,7 +411,8 @@ int gpk_ep_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nh
   b.y = v0; b.m = v0 + np; b.ttau = v0 + 2 * np; b.tnu = v0 + 3 * np; b.mu = v0 + 4 * np; b.sbuf = v0 + 5 * np;
   b.ktnu = v0 + 6 * np; b.v = v0 + 7 * np; b.w = v0 + 8 * np; b.wk = v0 + 9 * np; b.dlz = v0 + 10 * np;
   double* sw = v0 + 11 * np;
-  double* ttau0 = v0 + 12 * np;   // zero vectors kept for resets
+  double* ttau_new = v0 + 12 * np;   // staging of the site parameters of the running sweep (blocked path)
+  double* tnu_new = v0 + 13 * np;
   // res: [0,1] nlZ pieces, [8] nlZ0, [12] scratch, [14] cbuf, [16..) dnlZ results (+ ARD scratch)
   b.parts = v0 + 14 * np; b.res = b.parts + T; b.cbuf = b.res + 14; b.part = b.res + 128 + 4 * D;
   double* cvec = b.part + (int64_t)nsplit * np;   // EPB coefficients of the current block
@@ -449,7 +455,6 @@ int gpk_ep_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nh
     GPK_CK(h, cudaMemcpyAsync(b.Sig, b.K, (size_t)np * np * sizeof(double), cudaMemcpyDeviceToDevice, st));
     nlz = nlZ0;
   }
-  (void)ttau0;
   double nlz_old = INFINITY;
   int sweep = 0;
   const int g64 = (int)((n + 63) / 64);
@@ -482,7 +487,7 @@ int gpk_ep_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nh
         GPK_CK(h, cudaStreamSynchronize(st));
         GPK_CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         for (int t = 0; t < EPB; ++t)
-          ep_site_blk_kernel<<<gsite, 256, 0, st>>>(b.Sig, np, n, i0p, t, b.y, b.m, b.ttau, b.tnu, b.mu, S, Sc, cvec, mun);
+          ep_site_blk_kernel<<<gsite, 256, 0, st>>>(b.Sig, np, n, i0p, t, b.y, b.m, b.ttau, b.tnu, b.mu, S, Sc, cvec, mun, ttau_new, tnu_new);
         GPK_CK(h, cudaStreamEndCapture(st, &g));
         cudaGraphExec_t ge = nullptr;
         GPK_CK(h, cudaGraphInstantiate(&ge, g, 0));
@@ -498,13 +503,16 @@ int gpk_ep_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int nh
           GPK_CK(h, cudaGraphLaunch((cudaGraphExec_t)h->epGraphExec, st));
         } else {
           for (int t = 0; t < bl; ++t)
-            ep_site_blk_kernel<<<gsite, 256, 0, st>>>(b.Sig, np, n, i0p, t, b.y, b.m, b.ttau, b.tnu, b.mu, S, Sc, cvec, mun);
+            ep_site_blk_kernel<<<gsite, 256, 0, st>>>(b.Sig, np, n, i0p, t, b.y, b.m, b.ttau, b.tnu, b.mu, S, Sc, cvec, mun, ttau_new, tnu_new);
         }
         GemmArgs a{};                                 // Sigma0 -= (S diag c) S'  on the lower triangle
         a.A = Sc; a.B = S; a.C = b.Sig; a.lda = np; a.ldb = np; a.ldc = np; a.K = EPB; a.tri = 1;
         GPK_TRY(launch_gemm_nt(h, st, 1, a, T, T));
         h->stats.launches += bl;
       }
+      // every site has been visited once: commit the sweep's site parameters
+      GPK_CK(h, cudaMemcpyAsync(b.ttau, ttau_new, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      GPK_CK(h, cudaMemcpyAsync(b.tnu, tnu_new, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     GPK_CK(h, cudaGetLastError());
     GPK_TRY(ep_compute_params(h, st, b, n, np, &nlz, &info));

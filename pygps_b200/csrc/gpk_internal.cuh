@@ -159,6 +159,7 @@ struct Handle {
   // (two sets: [0] level-1 updates on s_main, [1] level-2 updates on s_panel, which run concurrently)
   int8_t* ozSl[2] = {nullptr, nullptr}; size_t ozCap[2] = {0, 0}; double* ozSc[2] = {nullptr, nullptr}; size_t ozScCap[2] = {0, 0};
   long long* ozDbg = nullptr;
+  double* ozFix = nullptr; size_t ozFixCap = 0;      // fixed row scales of the running factorisation (one per matrix row)
   // fitc state
   bool has_fitc = false; int64_t M = 0, Mp = 0;
   double* dUin = nullptr; double* dUs = nullptr; double* dLpost = nullptr; double* dAlphaU = nullptr;
@@ -254,6 +255,12 @@ int launch_oz_cyclic(Handle* h, int which, cudaStream_t st, double* C, int64_t l
 int launch_oz_gemm_stacked(Handle* h, int which, cudaStream_t st, double* Cab, int64_t ldc, int nb, int na, int kw);
 int launch_oz_syrk(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, int n, int kw, int jb0, int jb1,
                    int skip00 = 0);
+int launch_oz_fixed_scales(Handle* h, cudaStream_t st, const double* A, int64_t lda, int n, double diag_const, double* sc);
+int launch_oz_slice_fixed(Handle* h, cudaStream_t st, const double* P, int64_t lda, int nrows, int kw, int8_t* sl,
+                          double* sc, int srows, int row0, int kstep0);
+int launch_oz_syrk_buf(Handle* h, cudaStream_t st, const int8_t* sl, const double* sc, int srows, double* C, int64_t ldc,
+                       int n, int kw, int jb0, int jb1, int skip00);
+int oz_slices();
 int dist_allreduce_sum(Handle* h, double* buf, size_t count, cudaStream_t st);
 int kind_scale(int kind, int matern_d, const double* hyp, int nhyp, int D, std::vector<double>& scale, int* divide,
                double* premul, double* sf2);

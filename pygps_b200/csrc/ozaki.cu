@@ -100,7 +100,11 @@ __global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict
 // One CTA = 32 panel rows x (a k-range of) the contraction length.  Pass 1: row exponent (from the CTA's own
 // reduction, or from mx when the k-range is split over gridDim.y CTAs); pass 2: digits, written in the tensor core's
 // canonical order so that the CTA's output per k-step (4 row groups x S x 256 B) is contiguous.
-template <int S, int RB>
+// FIXED: the row scales are GIVEN (sc[row], set once per factorisation from the bound |L_ij| <= sqrt(A_ii), see
+// oz_fixed_scale_kernel): no row-maximum pass, and one set of digits serves every update that reads the panel.  An entry
+// that does not fit its row's scale (possible only if the matrix is not positive definite) turns the scale into NaN, so
+// the overflow surfaces as NaN in the updated matrix and as info > 0 at the next pivot - never as silent garbage.
+template <int S, int RB, bool FIXED = false>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ P, int64_t lda, int n, int kw,
                                                         double* __restrict__ sc, int8_t* __restrict__ sl, int row0,
                                                         const unsigned long long* __restrict__ mx) {
@@ -112,13 +116,18 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   const int r = threadIdx.x & 31, kq = threadIdx.x >> 5;
   const double* prow = P + r0 + r;
   double m = 0.0;
-  if (mx == nullptr) {
+  if (FIXED) {
+    if (kq == 0) {
+      const double scv = sc[row0 + r0 + r];
+      sh_e[r] = (scv > 0.0 && scv < 1.0e300) ? ilogb(scv) + RB : 0;      // NaN scale (bad row): digits are irrelevant
+    }
+  } else if (mx == nullptr) {
 #pragma unroll 4
     for (int k = kq; k < kw; k += 8) m = oz_absmax(m, prow[(int64_t)k * lda]);
     red[kq][r] = m;
     __syncthreads();
   }
-  if (kq == 0) {
+  if (!FIXED && kq == 0) {
     if (mx == nullptr) {
 #pragma unroll
       for (int q = 1; q < 8; ++q) m = fmax(m, red[q][r]);
@@ -147,11 +156,15 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   const int wbase = ((r >> 3) * S * 256 + ((4 * kq) >> 4) * 128 + (r & 7) * 16 + ((4 * kq) & 15)) >> 2;
   const int nsteps = kw / 32, per = (nsteps + gridDim.y - 1) / gridDim.y;
   const int ks_b = blockIdx.y * per, ks_e = min(ks_b + per, nsteps);
+  bool ovf = false;
   for (int ks = ks_b; ks < ks_e; ++ks) {
     unsigned long long qq[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      qq[j] = oz_digits<S, RB>(scalbn(prow[(int64_t)(ks * 32 + 4 * kq + j) * lda], -e));   // scaling exact; |x| <= 0.48
+    for (int j = 0; j < 4; ++j) {
+      const double xs = scalbn(prow[(int64_t)(ks * 32 + 4 * kq + j) * lda], -e);            // scaling exact; |x| <= 0.48
+      if (FIXED) ovf |= !(fabs(xs) <= 0.5);                                                  // (also catches NaN/Inf)
+      qq[j] = oz_digits<S, RB>(xs);
+    }
 #pragma unroll
     for (int t = 0; t < S; ++t) {
       const int sh = 8 * (S - 1 - t);
@@ -163,6 +176,28 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     for (int c = threadIdx.x; c < 4 * S * 16; c += 256) dst4[ks * (kstride / 16) + c] = src4[c];
     __syncthreads();
   }
+  if (FIXED && ovf) sc[row0 + r0 + r] = __longlong_as_double(0x7ff8000000000000ll);
+}
+
+// Fixed row scales of a Cholesky factorisation: |L_ij| <= sqrt(A_ii) for a positive definite A, so 2^e_i with
+// sqrt(A_ii) * 2^-e_i <= 0.48 is a valid digit scale for row i in EVERY panel.  diag_const > 0: A_ii is that constant
+// (stationary kernels: sf2/sn2 + 1) and A is not read; else the diagonal of A (pitch lda).  Non-positive or non-finite
+// diagonal entries get a NaN scale.
+template <int RB>
+__global__ void oz_fixed_scale_kernel(const double* __restrict__ A, int64_t lda, int n, double diag_const,
+                                      double* __restrict__ sc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = (diag_const > 0.0) ? diag_const : A[i + (int64_t)i * lda];
+  double out = __longlong_as_double(0x7ff8000000000000ll);
+  if (d > 0.0 && d < 1.0e300) {
+    const double m = sqrt(d) * (1.0 + 1.0e-12);      // rounding head room of the computed factor
+    int e = ilogb(m) + 2;
+    if (scalbn(m, -e) > 0.48) ++e;
+    if (e < -500) e = -500;
+    out = scalbn(1.0, e - RB);
+  }
+  sc[i] = out;
 }
 
 struct OzArgs {
@@ -182,6 +217,8 @@ struct OzArgs {
   int cs, cfirst;     //      global block jb = cfirst + c*cs (relative to the sliced rows); tiles with ti < jb are skipped;
                       //      C columns are the packed local ones (c*128 + ...), slices / scales / masks use jb
   long long* dbg;     // optional per-CTA clock stamps [5] (debug timing), else nullptr
+  int srows;          // rows of the slice BUFFER (k-step stride = srows*S*32 bytes); 0: n.  > n when sl / sc point into a
+                      // larger buffer shared by several updates (fixed row scales, see potrf_device)
 };
 
 // tile index -> (128-row tile ti, 64-column tile tj) over the lower-triangular tile set {jb0 <= jb < jb1, ti >= jb}.
@@ -263,7 +300,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(OzArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = a.kw / 32, nt = a.n / 128;
-  const size_t kstride = (size_t)a.n * S * 32;
+  const size_t kstride = (size_t)(a.srows > 0 ? a.srows : a.n) * S * 32;
   const int tile0 = blockIdx.x * a.tpc;
   const int tile1 = min(tile0 + a.tpc, a.ntiles);
   if (a.skip00) {                                          // (host guarantees tpc == 1 with skip00)
@@ -601,7 +638,59 @@ int launch_oz_cyclic(Handle* h, int which, cudaStream_t st, double* C, int64_t l
   if (ncols <= 0) return 0;
   if (c.tpc != 1 || !c.epi || cs < 1 || cfirst < 0 || cfirst + (ncols - 1) * cs >= nt) return GPK_ERR_ARG;
   if ((size_t)kw * 7 * 16384 >= 2147483648ull) return GPK_ERR_ARG;
-  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, 0, ncols, 2 * nt * ncols, 1, 0, 0, 0, 0, ncols, cs, cfirst, h->ozDbg};
+  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, 0, ncols, 2 * nt * ncols, 1, 0, 0, 0, 0, ncols, cs, cfirst, h->ozDbg, 0};
+  if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
+  return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
+}
+
+// ---- fixed row scales: one slice buffer shared by every update of a factorisation level (potrf_device) ------------
+int launch_oz_fixed_scales(Handle* h, cudaStream_t st, const double* A, int64_t lda, int n, double diag_const, double* sc) {
+  const OzCfg c = oz_cfg();
+  if (c.RB == 7) oz_fixed_scale_kernel<7><<<(n + 255) / 256, 256, 0, st>>>(A, lda, n, diag_const, sc);
+  else oz_fixed_scale_kernel<8><<<(n + 255) / 256, 256, 0, st>>>(A, lda, n, diag_const, sc);
+  h->stats.launches++;
+  GPK_CK(h, cudaGetLastError());
+  return 0;
+}
+
+template <int S, int RB>
+static int oz_slice_fixed_t(cudaStream_t st, const double* P, int64_t lda, int nrows, int kw, int8_t* sl, double* sc,
+                            int srows, int row0, int kstep0) {
+  const int ctas = nrows / 32, nsteps = kw / 32;
+  int ksplit = (ctas >= 1184) ? 1 : (1184 + ctas - 1) / ctas;
+  if (ksplit > nsteps / 4) ksplit = nsteps / 4 > 0 ? nsteps / 4 : 1;
+  int8_t* base = sl + (size_t)kstep0 * srows * S * 32;
+  oz_slice_kernel<S, RB, true><<<dim3(ctas, ksplit), 256, 0, st>>>(P, lda, srows, kw, sc, base, row0, nullptr);
+  return 0;
+}
+
+// rows [row0, row0 + nrows) x k-steps [kstep0, kstep0 + kw/32) of the slice buffer (sl, srows rows) <- P (nrows x kw), with
+// the GIVEN scales sc[row0 ...] (buffer-row indexed)
+int launch_oz_slice_fixed(Handle* h, cudaStream_t st, const double* P, int64_t lda, int nrows, int kw, int8_t* sl,
+                          double* sc, int srows, int row0, int kstep0) {
+  if (nrows % 128 != 0 || kw % 32 != 0 || row0 % 128 != 0 || row0 + nrows > srows) return GPK_ERR_ARG;
+  const OzCfg c = oz_cfg();
+  if (c.RB == 7) { if (c.S == 8) oz_slice_fixed_t<8, 7>(st, P, lda, nrows, kw, sl, sc, srows, row0, kstep0); else oz_slice_fixed_t<7, 7>(st, P, lda, nrows, kw, sl, sc, srows, row0, kstep0); }
+  else { if (c.S == 7) oz_slice_fixed_t<7, 8>(st, P, lda, nrows, kw, sl, sc, srows, row0, kstep0); else oz_slice_fixed_t<6, 8>(st, P, lda, nrows, kw, sl, sc, srows, row0, kstep0); }
+  h->stats.launches++;
+  GPK_CK(h, cudaGetLastError());
+  return 0;
+}
+
+int oz_slices() { return oz_cfg().S; }
+
+// lower(C)(128-column blocks [jb0, jb1)) -= P P' from a shared slice buffer: sl / sc already point at the first row and
+// the first k-step of this update; srows = rows of the whole buffer (the k-step stride)
+int launch_oz_syrk_buf(Handle* h, cudaStream_t st, const int8_t* sl, const double* sc, int srows, double* C, int64_t ldc,
+                       int n, int kw, int jb0, int jb1, int skip00) {
+  const OzCfg c = oz_cfg();
+  const int nt = n / 128;
+  if (jb0 < 0 || jb1 > nt || jb0 >= jb1 || n > srows) return GPK_ERR_ARG;
+  if (skip00 && (c.tpc != 1 || jb0 != 0)) return GPK_ERR_ARG;
+  if ((size_t)kw * 7 * 16384 >= 2147483648ull) return GPK_ERR_ARG;
+  long long nt64 = 0;
+  for (int jb = jb0; jb < jb1; ++jb) nt64 += 2 * (nt - jb);
+  OzArgs a{sl, sc, C, ldc, n, kw, jb0, jb1, (int)nt64, c.tpc, skip00, 0, 0, 0, 0, 0, 0, h->ozDbg, srows};
   if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
   return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
 }
@@ -621,7 +710,7 @@ int launch_oz_ex(Handle* h, int which, cudaStream_t st, double* C, int64_t ldc, 
   long long nt64 = 0;
   for (int jb = jb0; jb < jb1; ++jb) nt64 += 2 * (nt - (jb > ti_min ? jb : ti_min));
   const int ntiles = (int)nt64;
-  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, skip00, ti_min, trap, cmode, 0, 0, 0, h->ozDbg};
+  OzArgs a{h->ozSl[which], h->ozSc[which], C, ldc, n, kw, jb0, jb1, ntiles, c.tpc, skip00, ti_min, trap, cmode, 0, 0, 0, h->ozDbg, 0};
   if (c.RB == 7) return c.S == 8 ? oz_syrk_t<8, 7>(h, st, a) : oz_syrk_t<7, 7>(h, st, a);
   return c.S == 7 ? oz_syrk_t<7, 8>(h, st, a) : oz_syrk_t<6, 8>(h, st, a);
 }
