@@ -230,6 +230,8 @@ __global__ void __launch_bounds__(256, 2) cov_tile_kernel(const CovArgs a) {
 
   const int fa = 2 * lane;                    // this thread's fast indices: fa, fa+1, 64+fa, 64+fa+1
   const double sf2 = a.sf2, scale = a.scale;
+  const bool interior = (f0 + FT <= a.nF) && (gs0 + FT <= a.nS) && (f0 + FT <= a.pF) && (s0 + FT <= a.pS) &&
+                        (a.same_set ? (f0 != gs0) : true) && (a.lower_only ? (f0 > gs0) : true);
 #pragma unroll 1
   for (int q = 0; q < 4; ++q) {
     const int sl = warp * 16 + q * 4;         // slow indices sl .. sl+3 (tile-local)
@@ -253,6 +255,18 @@ __global__ void __launch_bounds__(256, 2) cov_tile_kernel(const CovArgs a) {
           const double df = fv[i] - sv[j];
           acc[i][j] = fma(df, df, acc[i][j]);
         }
+    }
+    if (interior) {
+      // the common case - a whole tile strictly below the diagonal, no padding: no per-entry masks at all
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double* col = a.out + (s0 + sl + j) * a.ld + f0 + fa;
+        *reinterpret_cast<double2*>(col) = make_double2(cov_tile_value<MAT>(acc[0][j], sf2, tab) * scale,
+                                                        cov_tile_value<MAT>(acc[1][j], sf2, tab) * scale);
+        *reinterpret_cast<double2*>(col + 64) = make_double2(cov_tile_value<MAT>(acc[2][j], sf2, tab) * scale,
+                                                             cov_tile_value<MAT>(acc[3][j], sf2, tab) * scale);
+      }
+      continue;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

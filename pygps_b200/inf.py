@@ -196,10 +196,10 @@ class Exact(Inference):
         """Route the evaluation to the sharded path (gpk_exact_eval_dist) when asked to, or when the N x N factor
         (plus the int8 slices of one block) does not fit one GPU of the device list."""
         devs = self._device_list()
+        if self.shard:
+            return True                      # (one device: the sharded code path with world size 1, no NCCL)
         if self.shard is False or len(devs) < 2:
             return False
-        if self.shard:
-            return True
         npad = -(-n // 128) * 128
         need = 8 * npad * npad + 8 * npad * 1152 + (1 << 30)
         try:

@@ -282,12 +282,14 @@ class Optimizer(object):
         except Exception:
             return [0]
 
-    def _worker_for(self, device):
+    def _worker_for(self, device, slot=0):
         """A private copy of the model (and of this optimizer) whose evaluations run on `device`: the restarts of
-        Core/opt.py:301-327 are independent minimisations, so each GPU gets its own copy and its own libgpk handle."""
+        Core/opt.py:301-327 are independent minimisations, so each GPU gets its own copy and its own libgpk handle
+        (a device listed twice gets two copies: two evaluation streams share that GPU)."""
         if not hasattr(self, '_workers'):
             self._workers = {}
-        w = self._workers.get(device)
+        key = (device, slot)
+        w = self._workers.get(key)
         if w is None:
             workers, self._workers = self._workers, {}          # do not copy the copies
             try:
@@ -299,7 +301,7 @@ class Optimizer(object):
             m.inffunc.shard = False
             m.inffunc._engine = None
             m.optimizer.searchConfig = None
-            w = self._workers[device] = m
+            w = self._workers[key] = m
         return w
 
     def _run_trials(self, jobs, numIters):
@@ -324,15 +326,15 @@ class Optimizer(object):
             todo.put((i, job))
         used = set()
 
-        copies = {}
-        for d in devs[:len(jobs)]:                           # model copies are made here, on the calling thread
+        copies = []
+        for slot, d in enumerate(devs[:len(jobs)]):          # model copies are made here, on the calling thread
             try:
-                copies[d] = self._worker_for(d)
+                copies.append(self._worker_for(d, devs[:slot].count(d)))
             except Exception as e:
-                copies[d] = e
+                copies.append(e)
 
-        def work(dev):
-            m = copies[dev]
+        def work(slot, dev):
+            m = copies[slot]
             while True:
                 try:
                     i, (hyp, first) = todo.get_nowait()
@@ -347,7 +349,7 @@ class Optimizer(object):
                     used.add(dev)
                 except Exception as e:
                     out[i] = e
-        threads = [threading.Thread(target=work, args=(d,)) for d in devs[:len(jobs)]]
+        threads = [threading.Thread(target=work, args=(slot, d)) for slot, d in enumerate(devs[:len(jobs)])]
         for t in threads:
             t.start()
         for t in threads:
