@@ -315,6 +315,40 @@ def run_sharded(ctx, args, eng_single):
     out["c3"] = c3
     ctx.barrier()
     del X
+    # ---- C2 data, sharded WITH derivatives and predictions: factor gather + row-slab inverse ----
+    N2, D2 = N_FULL, D_FULL
+    X2, y2 = synth(N2, D2)
+    h2, sn2l = [math.log(2.0), 0.0], math.log(0.1)
+    Xs2 = np.random.default_rng(1).standard_normal((4096, D2))
+    lo, hi = (4096 * ctx.rank) // ctx.world, (4096 * (ctx.rank + 1)) // ctx.world
+    eng.set_data(X2)
+    eng.dist_reserve(2)
+    ts = []
+    for i in range(2):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        nl, al, dc, dl = eng.exact_eval_dist_der(_lib.COV_RBF, 3, h2, sn2l, y2.reshape(-1))
+        ts.append(ctx.max(1e3 * (time.perf_counter() - t0)))
+    ctx.barrier()
+    t0 = time.perf_counter()
+    eng.dist_gather_factor()
+    ka, fs2 = eng.predict(Xs2[lo:hi]) if hi > lo else (np.empty((0, 1)), np.empty((0, 1)))
+    t_pred = ctx.max(1e3 * (time.perf_counter() - t0))
+    e4 = {"workload": "C2 data (N=%d D=%d) sharded over %d GPUs: evaluation WITH derivatives (factor gather, row-slab "
+                      "inverse, one all-reduce) and 4096 predictions split over the ranks" % (N2, D2, ctx.world),
+          "der_eval_ms": min(ts), "predict_ms": t_pred, "nlZ": float(nl)}
+    if ctx.rank == 0:
+        eng_single.set_data(X2)
+        r1 = eng_single.exact_eval(_lib.COV_RBF, 3, h2, sn2l, y2.reshape(-1), True)
+        ka1, fs21 = eng_single.predict(Xs2[lo:hi])
+        rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))
+        e4["rel_err_vs_single_gpu"] = {"nlZ": abs(float(nl) - float(r1[0])) / abs(float(r1[0])), "dcov": rel(dc, r1[2]),
+                                       "dlik": rel(dl, r1[3]), "predict_mean": rel(ka, ka1), "predict_var": rel(fs2, fs21)}
+        if not max(e4["rel_err_vs_single_gpu"].values()) < 1e-8:
+            raise SystemExit("parity gate failed for the sharded derivatives / predictions: %r" % e4)
+    out["sharded_der_predict"] = e4
+    ctx.barrier()
+    del X2
     # ---- C4: GPR_FITC, cov.RBF, N=262144, M=4096 inducing points, data sharded ----------------------------------
     N4, M4 = args.fitc_n, args.fitc_m
     rng = np.random.default_rng(0)
@@ -343,6 +377,35 @@ def run_sharded(ctx, args, eng_single):
     out["c4"] = c4
     ctx.barrier()
     return out
+
+
+def run_concurrent(device, X, ymm, streams, evals):
+    """Throughput of `streams` concurrent evaluation streams on ONE GPU (one libgpk handle + one thread each, independent
+    hyper-parameter vectors): the chain-bound tail of one factorisation overlaps the bulk of another.  Reported beside
+    the headline, which stays the single-stream rate."""
+    import threading
+    from pygps_b200 import _lib
+    from pygps_b200._dist import replica_hyp
+    engs = [_lib.Engine(device) for _ in range(streams)]
+    for e in engs:
+        e.set_data(X)
+        for k in range(2):
+            e.exact_eval(_lib.COV_RBF, 3, *replica_hyp(k, 7), ymm, False)
+    per = max(1, evals // streams)
+
+    def work(i):
+        for k in range(per):
+            h, sn = replica_hyp(50 + k * streams + i, 7)
+            engs[i].exact_eval(_lib.COV_RBF, 3, h, sn, ymm, False)
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(streams)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return {"streams": streams, "evals": per * streams, "value": per * streams / dt, "unit": UNIT,
+            "note": "NOT the headline: `value` above is one evaluation at a time"}
 
 
 # ----------------------------------------------------------------------------- other configs on one GPU (N = 1)
@@ -580,6 +643,13 @@ def run_ours(args):
                  "cholesky_tflops_in_eval": (N ** 3 / 3.0) / (stage["potrf_ms"] / steps * 1e-3) / 1e12,
                  "stage_ms_per_eval": {k: v / steps for k, v in stage.items()},
                  "der_eval_ms": der_ms}
+
+    # ---- several evaluation streams on the one GPU (independent evaluations, as random restarts are) ----------
+    if ctx.rank == 0 and n_gpus == 1 and not args.no_extra:
+        try:
+            extra["concurrent_streams"] = run_concurrent(ctx.local_rank, X, ymm, 2, max(steps, 10))
+        except Exception as e:           # pragma: no cover
+            extra["concurrent_streams"] = {"error": repr(e)}
 
     # ---- one evaluation SHARDED over all GPUs (N > 1): the NCCL paths, with parity ---------------
     sharded = None
