@@ -78,6 +78,10 @@ __global__ void fill_aug_kernel(double* __restrict__ A, int64_t ld, int64_t np, 
   }
 }
 
+// panels per block of the blocked (int8) sharded factorisation: measured on 8 GPUs at N=65536: 4 -> 352 ms, 8 -> 325 ms,
+// 16 -> 319 ms per evaluation (profiles/r2_dist8_c3.md); small problems keep 8 so that the blocked path still applies
+static inline int dist_wd(int T) { return env_int("GPK_DIST_WD", T >= 256 ? 16 : 8); }
+
 constexpr int DT_THREADS = 512;
 constexpr size_t DT_SMEM = size_t(NB) * NB * sizeof(double);
 
@@ -123,6 +127,38 @@ __global__ void __launch_bounds__(NB) bwd_finish_kernel(const double* __restrict
   double o = 0.0;
   for (int r = c; r < NB; ++r) o = fma(Dk[r + c * NB], s[r], o);   // (Dinv^T s)_c = sum_{r>=c} Dinv[r,c] s_r
   xk[c] = o;
+}
+
+// acc[c][j] += sum_r L[k*128 + r, (local column block c) j] * x_k[r]  for the owned column blocks c = 0 .. gridDim.x-1 (all
+// those whose global index is below k): the contribution of the freshly broadcast x_k to every later step of this rank, so
+// that the step of column k-1 has nothing left to do but the 128x128 finish once x_k has arrived.
+__global__ void __launch_bounds__(DT_THREADS, 1) bwd_update_kernel(const double* __restrict__ gA, int64_t ld, int k,
+                                                                   const double* __restrict__ xk,
+                                                                   double* __restrict__ acc) {
+  extern __shared__ __align__(16) double tile[];
+  __shared__ double sx[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x;
+  const double* src = gA + (int64_t)k * NB + (int64_t)c * NB * ld;
+  if (tid < NB) sx[tid] = xk[tid];
+#pragma unroll
+  for (int i = 0; i < (NB * NB / 2) / DT_THREADS; ++i) {
+    const int ch = tid + i * DT_THREADS;
+    const int cc = ch >> 6, r = (ch & 63) * 2;
+    unsigned sa = (unsigned)__cvta_generic_to_shared(tile + r + cc * NB);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + r + (int64_t)cc * ld) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  const double v0 = sx[lane], v1 = sx[lane + 32], v2 = sx[lane + 64], v3 = sx[lane + 96];
+  for (int j = warp; j < NB; j += DT_THREADS / 32) {
+    const double* col = tile + j * NB;
+    double sacc = fma(col[lane], v0, fma(col[lane + 32], v1, fma(col[lane + 64], v2, col[lane + 96] * v3)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+    if (lane == 0) acc[(int64_t)c * NB + j] += sacc;
+  }
 }
 
 // alpha = x/sn2 ; res[0] = r'alpha
@@ -218,7 +254,7 @@ static int dist_reserve(Handle* h, int level) {
     GPK_CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->ev.push_back(e);
   }
-  const int WD = env_int("GPK_DIST_WD", 8);
+  const int WD = dist_wd(T);
   const bool doz = env_int("GPK_DIST_OZAKI", 1) != 0 && env_int("GPK_OZAKI", 1) != 0 && T >= 4 * WD && WD >= 1 && WD <= 16;
   if (doz) {
     GPK_TRY(ensure(h, &h->gBlk, &h->cgBlk, 2 * ld * (int64_t)WD * NB));
@@ -332,7 +368,7 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
   // (full height, pitch ld) in a double-buffered block buffer, and after the block every rank slices it once and
   // applies ONE rank-(WD*128) update on the int8 tensor cores to the columns it owns beyond the block
   // (launch_oz_cyclic) - the column that becomes the next panel first.
-  const int WD = env_int("GPK_DIST_WD", 8);
+  const int WD = dist_wd(T);
   const bool doz = env_int("GPK_DIST_OZAKI", 1) != 0 && env_int("GPK_OZAKI", 1) != 0 && T >= 4 * WD && WD >= 1 && WD <= 16;
   double* PB = nullptr;
   if (doz) {
@@ -442,6 +478,30 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
   GPK_CK(h, cudaEventRecord(h->t2, st));
 
   // ---- backward substitution: x_k = Dinv_k^T (z_k - sum_{i>k} L[i,k]^T x_i), x_k broadcast ------------------------
+  // Right-looking: as soon as x_k has arrived, every rank adds its contribution L[k, c]' x_k to the running sums of ALL
+  // the columns c < k it owns (one launch, one CTA per owned column block), so the dependent chain per block step is
+  // finish (one CTA) -> 1 KiB broadcast -> that one update launch, instead of a launch over the whole column height.
+  // GPK_DIST_BWD=0 selects the round-1 left-looking form (one launch over the column's tiles per step).
+  if (env_int("GPK_DIST_BWD", 1) != 0) {
+    GPK_CK(h, cudaFuncSetAttribute(bwd_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_SMEM));
+    double* acc = partial;                                   // nloc x 128 running sums (the buffer holds T x 128)
+    GPK_CK(h, cudaMemsetAsync(acc, 0, (size_t)(nloc > 0 ? nloc : 1) * NB * sizeof(double), st));
+    for (int k = T - 1; k >= 0; --k) {
+      const int o = k % G, lk = k / G;
+      double* xk = x + (int64_t)k * NB;
+      if (r == o) {
+        const double* Acol = h->gA + (int64_t)lk * NB * ld;
+        bwd_finish_kernel<<<1, NB, 0, st>>>(Acol, ld, np, h->gDinv + (int64_t)lk * NB * NB, acc + (int64_t)lk * NB, 1, xk);
+        h->stats.launches++;
+      }
+      if (G > 1) NCCL_CK(h, g_nccl.bcast(xk, xk, NB, NCCL_F64, o, h->nccl_comm, st));
+      const int ncols = (k > r) ? (k - r + G - 1) / G : 0;   // owned column blocks with global index < k
+      if (ncols > 0) {
+        bwd_update_kernel<<<ncols, DT_THREADS, DT_SMEM, st>>>(h->gA, ld, k, xk, acc);
+        h->stats.launches++;
+      }
+    }
+  } else {
   for (int k = T - 1; k >= 0; --k) {
     const int o = k % G, lk = k / G;
     double* xk = x + (int64_t)k * NB;
@@ -453,6 +513,7 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
       h->stats.launches += 2;
     }
     if (G > 1) NCCL_CK(h, g_nccl.bcast(xk, xk, NB, NCCL_F64, o, h->nccl_comm, st));
+  }
   }
   // log-det parts and info: every entry has exactly one non-zero contributor
   if (G > 1) {
