@@ -390,6 +390,12 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
   // block b therefore runs UNDER the dependent chain (diag -> TRSM -> broadcast -> column update) of block b+1 instead of
   // in front of it - measured before the split: per block 4.1 ms of update + 4.8 ms of chain, strictly one after the other.
   const bool dsplit = env_int("GPK_DIST_SPLIT", 1) != 0;
+  // Stream priorities matter here: the far update is a grid of tens of thousands of CTAs, the chain-side kernels
+  // (copy into the block buffer, immediate rank-128 updates, slicing, near update) must get SMs ahead of it.  s_main has the
+  // LOWEST priority of the handle's streams, s_tail the second highest: in split mode the chain side runs on s_tail and the
+  // far update on s_main (a first version had them the other way round and gained nothing).
+  cudaStream_t su = (doz && dsplit) ? sf : st;     // chain-side updates
+  cudaStream_t sfar = st;                          // far updates (split mode)
   for (int k = 0; k < T; ++k) {
     const int o = k % G, lk = k / G;
     const int rem = T - k;                          // tile rows below the diagonal block, incl. the extra row
@@ -413,9 +419,9 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
       else if (k > 1) GPK_CK(h, cudaStreamWaitEvent(sc, ev_upd[k - 2], 0));  // receive buffer free
       NCCL_CK(h, g_nccl.bcast(pack, pack, (size_t)prow * NB, NCCL_F64, o, h->nccl_comm, sc));
       GPK_CK(h, cudaEventRecord(ev_bcast[k], sc));
-      GPK_CK(h, cudaStreamWaitEvent(st, ev_bcast[k], 0));
+      GPK_CK(h, cudaStreamWaitEvent(su, ev_bcast[k], 0));
     } else {
-      GPK_CK(h, cudaStreamWaitEvent(st, ev_packed[k], 0));
+      GPK_CK(h, cudaStreamWaitEvent(su, ev_packed[k], 0));
     }
     if (doz) {
       const int kb = (k / WD) * WD, ke = (kb + WD < T) ? kb + WD : T;     // the block of panel k: [kb, ke)
@@ -423,7 +429,7 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
       // panel k, full height, into its slot of the block buffer (rows (k+1)*NB .. ld)
       GPK_CK(h, cudaMemcpy2DAsync(blk + (int64_t)(k - kb) * NB * ld + (int64_t)(k + 1) * NB, (size_t)ld * sizeof(double),
                                   pack, (size_t)prow * sizeof(double), (size_t)prow * sizeof(double), NB,
-                                  cudaMemcpyDeviceToDevice, st));
+                                  cudaMemcpyDeviceToDevice, su));
       // immediate updates: owned columns j in (k, ke) only
       const int j0 = k + 1 + (((r - (k + 1)) % G) + G) % G;
       int jstart = j0;
@@ -431,8 +437,8 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
         GemmArgs u{};
         u.A = pack; u.B = pack; u.C = h->gA + (int64_t)(k + 1) * NB + (int64_t)(j0 / G) * NB * ld;
         u.lda = prow; u.ldb = prow; u.ldc = ld; u.K = NB; u.tri = 1; u.ti_off = k + 1; u.tj_off = j0; u.cstride = G;
-        GPK_TRY(launch_gemm_nt(h, st, 1, u, rem, 1));
-        GPK_CK(h, cudaEventRecord(ev_col[k + 1], st));
+        GPK_TRY(launch_gemm_nt(h, su, 1, u, rem, 1));
+        GPK_CK(h, cudaEventRecord(ev_col[k + 1], su));
         jstart = j0 + G;
       }
       if (jstart < ke) {
@@ -441,15 +447,15 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
         u.A = pack; u.B = pack + (int64_t)(jstart - (k + 1)) * NB;
         u.C = h->gA + (int64_t)(k + 1) * NB + (int64_t)(jstart / G) * NB * ld;
         u.lda = prow; u.ldb = prow; u.ldc = ld; u.K = NB; u.tri = 1; u.ti_off = k + 1; u.tj_off = jstart; u.cstride = G;
-        GPK_TRY(launch_gemm_nt(h, st, 1, u, rem, ncols));
+        GPK_TRY(launch_gemm_nt(h, su, 1, u, rem, ncols));
       }
       if (k == ke - 1 && ke < T) {
         // the block is complete: one sliced rank-(ke-kb)*NB update of the owned columns >= ke, rows >= ke*NB
         const int b = k / WD, which = dsplit ? (b & 1) : 0;
         const int nrows = (T + 1 - ke) * NB, kw = (ke - kb) * NB;
         // slice buffer `which` was last read by the far update of block b-2
-        if (dsplit && b >= 2) GPK_CK(h, cudaStreamWaitEvent(st, ev_far[b - 2], 0));
-        GPK_TRY(launch_oz_slice(h, which, st, blk + (int64_t)ke * NB, ld, nrows, kw));
+        if (dsplit && b >= 2) GPK_CK(h, cudaStreamWaitEvent(su, ev_far[b - 2], 0));
+        GPK_TRY(launch_oz_slice(h, which, su, blk + (int64_t)ke * NB, ld, nrows, kw));
         const int jf = ke + (((r - ke) % G) + G) % G;                     // first owned column >= ke
         int nfar = 0, cfar = 0;
         double* Cfar = nullptr;
@@ -464,25 +470,25 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
             Cfar = C + (int64_t)nnear * NB * ld;
             cfar = cfirst + nnear * G;
             // the near columns received the far update of block b-1: it must be complete
-            if (b >= 1 && nnear > 0) GPK_CK(h, cudaStreamWaitEvent(st, ev_far[b - 1], 0));
+            if (b >= 1 && nnear > 0) GPK_CK(h, cudaStreamWaitEvent(su, ev_far[b - 1], 0));
           }
           if (nnear > 0) {
             if (jf == ke) {                                                // this rank owns the next panel: that column first
-              GPK_TRY(launch_oz_cyclic(h, which, st, C, ld, nrows, kw, 1, cfirst, G));
-              GPK_CK(h, cudaEventRecord(ev_col[ke], st));
+              GPK_TRY(launch_oz_cyclic(h, which, su, C, ld, nrows, kw, 1, cfirst, G));
+              GPK_CK(h, cudaEventRecord(ev_col[ke], su));
               C += (int64_t)NB * ld; cfirst += G; --nnear;
             }
-            GPK_TRY(launch_oz_cyclic(h, which, st, C, ld, nrows, kw, nnear, cfirst, G));
+            GPK_TRY(launch_oz_cyclic(h, which, su, C, ld, nrows, kw, nnear, cfirst, G));
           }
         }
         if (dsplit) {
-          GPK_CK(h, cudaEventRecord(ev_sliced, st));
-          GPK_CK(h, cudaStreamWaitEvent(sf, ev_sliced, 0));
-          if (nfar > 0) GPK_TRY(launch_oz_cyclic(h, which, sf, Cfar, ld, nrows, kw, nfar, cfar, G));
-          GPK_CK(h, cudaEventRecord(ev_far[b], sf));
+          GPK_CK(h, cudaEventRecord(ev_sliced, su));
+          GPK_CK(h, cudaStreamWaitEvent(sfar, ev_sliced, 0));
+          if (nfar > 0) GPK_TRY(launch_oz_cyclic(h, which, sfar, Cfar, ld, nrows, kw, nfar, cfar, G));
+          GPK_CK(h, cudaEventRecord(ev_far[b], sfar));
         }
       }
-      GPK_CK(h, cudaEventRecord(ev_upd[k], st));
+      GPK_CK(h, cudaEventRecord(ev_upd[k], su));
       continue;
     }
     // update the owned columns j > k:  C[:, j] -= P[rows >= j] * P[j]^T

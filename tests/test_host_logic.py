@@ -292,3 +292,40 @@ def test_models_with_engines_survive_deepcopy_and_pickle():
     assert m2.inffunc._engine is None and np.array_equal(m2.posterior.L, np.eye(3))
     m3 = pickle.loads(pickle.dumps(m))
     assert m3.inffunc._engine is None and np.array_equal(m3.posterior.L, np.eye(3))
+
+
+def test_covariance_programs_are_emitted_in_post_order_with_the_reference_hyp_layout():
+    """cov.Kernel._device_prog(): nodes in post-order (children before parents, root last), every node's hyp0 the index
+    of its first own entry in the composite's flat hyper-parameter list exactly as the reference concatenates it
+    (Core/cov.py:235, 270, 303-306: cov1.hyp + cov2.hyp; ScaleOfKernel: [scalar] + cov.hyp)."""
+    import pygps_b200 as pg
+    from pygps_b200 import _lib
+    c = pg.cov
+    k = c.RBF(0.1, 0.2) * c.Periodic(0.3, 0.4, 0.5) + c.Noise(0.6)
+    nodes, hyp = k._device_prog()
+    assert hyp == [0.1, 0.2, 0.3, 0.4, 0.5, 0.6] == k.hyp
+    assert nodes == [(_lib.OP_RBF, -1, -1, 0, 0.0), (_lib.OP_PERIODIC, -1, -1, 2, 0.0), (_lib.OP_PROD, 0, 1, -1, 0.0),
+                     (_lib.OP_NOISE, -1, -1, 5, 0.0), (_lib.OP_SUM, 2, 3, -1, 0.0)]
+    # scalar * kernel: the scalar is the node's own hyper-parameter, the child's follow it
+    k = 3.0 * c.Matern(0.7, 5, 0.8) + c.RQard(log_ell_list=[0.1, 0.2], log_sigma=0.3, log_alpha=0.4)
+    nodes, hyp = k._device_prog()
+    assert hyp == [3.0, 0.7, 0.8, 0.1, 0.2, 0.3, 0.4]
+    assert nodes[0] == (_lib.OP_MATERN, -1, -1, 1, 5.0) and nodes[1] == (_lib.OP_SCALE, 0, -1, 0, 0.0)
+    assert nodes[2] == (_lib.OP_RQARD, -1, -1, 3, 0.0) and nodes[3] == (_lib.OP_SUM, 1, 2, -1, 0.0)
+    # setting the composite's hyp propagates into the parts (what the optimizers do every iteration)
+    k.hyp = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0]
+    assert k.cov1.cov.hyp == [2.0, 3.0] and k.cov2.hyp == [4.0, 5.0, 6.0, 7.0] and k._device_prog()[1][0] == 1.0
+    # PiecePoly / Poly carry their integer parameter; precomputed matrices are reported as Pre leaves
+    assert c.PiecePoly(0.1, 3, 0.2)._device_prog()[0][0][4] == 3.0 and c.Poly(0.1, 4, 0.2)._device_prog()[0][0][4] == 4.0
+    pre = c.Pre(np.ones((4, 2)), np.eye(3))
+    kk = pre + c.RBF()
+    assert kk._pre_leaves() == [pre] and kk._device_prog()[0][0][0] == _lib.OP_PRE
+    assert np.array_equal(pre.getCovMatrix(mode='train'), np.eye(3)) and pre.getCovMatrix(mode='cross').shape == (3, 2)
+    assert pre.getCovMatrix(mode='self_test').shape == (2, 1)
+
+    class Mine(c.Kernel):                       # a kernel without a device implementation: no program, no CPU fallback
+        def __init__(self):
+            self.hyp = [0.0]
+    assert (Mine() + c.RBF())._device_prog() is None
+    # the native single kernels keep their dedicated fused build
+    assert c.RBF()._device_spec() is not None and (c.RBF() + c.RBF())._device_spec() is None
