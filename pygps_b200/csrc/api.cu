@@ -438,6 +438,14 @@ static int free_all(Handle* h) {
   h->dFlags = nullptr;
   if (h->epGraphExec) cudaGraphExecDestroy((cudaGraphExec_t)h->epGraphExec);
   h->epGraphExec = nullptr;
+  if (h->ozFix) cudaFree(h->ozFix);
+  h->ozFix = nullptr; h->ozFixCap = 0;
+  if (h->dProg) cudaFree(h->dProg);
+  h->dProg = nullptr;
+  if (h->hProgPinned) cudaFreeHost(h->hProgPinned);
+  h->hProgPinned = nullptr;
+  if (h->dPre) cudaFree(h->dPre);
+  h->dPre = nullptr; h->capPre = 0; h->preN = 0;
   for (int w = 0; w < 2; ++w) {
     if (h->ozSl[w]) cudaFree(h->ozSl[w]);
     if (h->ozSc[w]) cudaFree(h->ozSc[w]);
