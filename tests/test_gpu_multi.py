@@ -84,7 +84,6 @@ def test_evaluation_is_routed_to_the_sharded_path_when_the_factor_does_not_fit(m
     monkeypatch.setattr(_lib, "device_memory", lambda d: (150 << 30, 180 << 30))
     assert not m.inffunc._wants_sharding(16384)
     assert m.inffunc._wants_sharding(150000)
-    free, total = _lib.device_memory.__wrapped__(devs[0]) if hasattr(_lib.device_memory, "__wrapped__") else (1, 1)
     monkeypatch.undo()
     free, total = _lib.device_memory(devs[0])
     assert 0 < free <= total and total > (64 << 30)
