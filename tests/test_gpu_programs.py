@@ -172,3 +172,36 @@ def test_unsupported_kernels_fail_loudly():
     with pytest.raises(Exception) as ei:
         m.getPosterior(x, y)
     assert "no device implementation" in str(ei.value)
+
+
+def test_program_with_a_varying_diagonal_through_the_big_block_int8_path():
+    """N=7424 (58 panels: one level-1 block of 9 panels, sliced sub-block by sub-block with FIXED row scales) and a
+    composite whose diagonal varies from point to point (Linear term): the scales are then read from the diagonal of the
+    built matrix and the panel stream has to wait for them (potrf_device: ev_fix).  Against the CPU oracle."""
+    rng = np.random.default_rng(9)
+    N, D = 7424, 3
+    X = rng.standard_normal((N, D))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    spec = ("sum", ("prod", ("rbf", [0.4, 0.2]), ("const", [0.1])), ("linear", [np.log(0.3)]))
+    m = pg.GPR()
+    m.setPrior(kernel=build(spec))
+    nlZ, post = m.getPosterior(X, y, der=False)
+    rpost, rnlZ = go.exact_evaluate(("zero",), spec, np.log(0.1), X, y, 2)
+    check("varying-diagonal composite N=7424 nlZ", nlZ, rnlZ, 1e-9)
+    check("varying-diagonal composite N=7424 alpha", post.alpha, rpost["alpha"])
+
+
+def test_ragged_size_on_the_int8_path_matches_the_oracle():
+    """N=5003 (np = 5120: 117 identity-padded rows) through the fixed-scale int8 factorisation, native RBF kernel."""
+    rng = np.random.default_rng(10)
+    N, D = 5003, 6
+    X = rng.standard_normal((N, D))
+    y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    m = pg.GPR()
+    m.setPrior(kernel=pg.cov.RBF(np.log(1.8), 0.1))
+    nlZ, dn, post = m.getPosterior(X, y)
+    rpost, rnlZ, rdn = go.exact_evaluate(("zero",), ("rbf", [np.log(1.8), 0.1]), np.log(0.1), X, y, 3)
+    check("ragged N=5003 nlZ", nlZ, rnlZ, 1e-10)
+    check("ragged N=5003 alpha", post.alpha, rpost["alpha"])
+    check("ragged N=5003 dcov", dn.cov, rdn["cov"])
+    check("ragged N=5003 dlik", dn.lik, rdn["lik"])
