@@ -343,10 +343,8 @@ int launch_rowdot(Handle* h, cudaStream_t st, const double* P, int64_t ld, int64
 // Runs the fused reduction; res gets [dcov_0 .. dcov_{nhyp-1}, trace(Q)] (before the 1/2 and sn2 factors).
 static int launch_dnlz_impl(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv,
                             int64_t ld, const double* alpha, const double* sw, double inv_sn2, double sf2, int kind,
-                            int matern_d, double* part, int64_t part_cap, double* res);
-
-static thread_local int64_t t_rect_off = 0, t_rect_rows = 0;
-static thread_local int t_rect = 0;
+                            int matern_d, double* part, int64_t part_cap, double* res, int rect = 0, int64_t rect_off = 0,
+                            int64_t rect_rows = 0);
 
 int launch_dnlz(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
                 const double* alpha, double inv_sn2, double sf2, int kind, int matern_d, double* part,
@@ -357,11 +355,8 @@ int launch_dnlz(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, 
 int launch_dnlz_rect(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv_rows, int64_t ld,
                      int64_t i_off, int64_t rows, const double* alpha, double inv_sn2, double sf2, int kind, int matern_d,
                      double* part, int64_t part_cap, double* res) {
-  t_rect = 1; t_rect_off = i_off; t_rect_rows = rows;
-  const int rc = launch_dnlz_impl(h, st, Xs, n, D, Ainv_rows, ld, alpha, nullptr, inv_sn2, sf2, kind, matern_d, part,
-                                  part_cap, res);
-  t_rect = 0;
-  return rc;
+  return launch_dnlz_impl(h, st, Xs, n, D, Ainv_rows, ld, alpha, nullptr, inv_sn2, sf2, kind, matern_d, part, part_cap,
+                          res, 1, i_off, rows);
 }
 int launch_dnlz_sw(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv, int64_t ld,
                    const double* alpha, const double* sw, double sf2, int kind, int matern_d, double* part,
@@ -371,9 +366,10 @@ int launch_dnlz_sw(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int 
 
 static int launch_dnlz_impl(Handle* h, cudaStream_t st, const double* Xs, int64_t n, int D, const double* Ainv,
                             int64_t ld, const double* alpha, const double* sw, double inv_sn2, double sf2, int kind,
-                            int matern_d, double* part, int64_t part_cap, double* res) {
+                            int matern_d, double* part, int64_t part_cap, double* res, int rect, int64_t rect_off,
+                            int64_t rect_rows) {
   const int64_t g = (n + DT_ - 1) / DT_;
-  const int64_t gi = t_rect ? (t_rect_rows + DT_ - 1) / DT_ : g;     // row tiles (rect mode: the rectangle's rows)
+  const int64_t gi = rect ? (rect_rows + DT_ - 1) / DT_ : g;     // row tiles (rect mode: the rectangle's rows)
   if (g > 65535) return GPK_ERR_ARG;
   const int64_t nctas = gi * g;
   const size_t smem = size_t(2) * DT_ * D * sizeof(double);
@@ -382,7 +378,7 @@ static int launch_dnlz_impl(Handle* h, cudaStream_t st, const double* Xs, int64_
   DnlzArgs a;
   a.Xs = Xs; a.n = n; a.D = D; a.Ainv = Ainv; a.ld = ld; a.alpha = alpha; a.sw = sw; a.inv_sn2 = inv_sn2; a.sf2 = sf2;
   a.kind = kind; a.matern_d = matern_d; a.part = part;
-  a.rect = t_rect; a.i_off = t_rect_off; a.rows = t_rect_rows;
+  a.rect = rect; a.i_off = rect_off; a.rows = rect_rows;
   dim3 grid((unsigned)gi, (unsigned)g);
   if (kind != GPK_COV_RBFARD) {
     a.d_begin = 0; a.nacc = 3;
