@@ -234,7 +234,10 @@ int gpk_bench_copy(gpk_handle h, int64_t bytes, int reps, double* gbs);
  * through the production tile kernel.  mode 0: C=A*B' ; 1: C-=A*B' full;
  * 2: C-=A*B' lower tiles only (M==N); 3: C=A*B' lower tiles, contraction from
  * k = 128*tile_row (upper-triangular operands); 4: A <- A*B' in place (N==K), the
- * panel-TRSM form.  M,N multiples of 128, K of 32.                              */
+ * panel-TRSM form.  M,N multiples of 128, K of 32.
+ * Modes 5-7 run the chain products (sixteen 32x32-block CTAs per 128x128 tile; M = N = 128, K a multiple of 128):
+ * 5: C = A*B' ; 6: C -= A*B' on the blocks on / below the diagonal ; 7 (K = 128): the head pair of the panel chain,
+ * X = A*B' , C -= X*X' (lower), and A is OVERWRITTEN with X.                                                   */
 int gpk_dbg_gemm_nt(gpk_handle h, int mode, int64_t M, int64_t N, int64_t K,
                     const double* A, const double* B, double* C);
 /* debug: factor + invert one 128x128 block (column-major): L and inv(L). */

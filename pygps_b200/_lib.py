@@ -464,8 +464,9 @@ class Engine(object):
         return g.value
 
     def dbg_gemm_nt(self, mode, A, B, C):
-        """Column-major (Fortran-ordered) A (M,K), B (N,K), C (M,N); returns the new C."""
-        A = np.asfortranarray(A, dtype=np.float64)
+        """Column-major (Fortran-ordered) A (M,K), B (N,K), C (M,N); returns the new C (mode 7, the head pair of the
+        panel chain: the new C and the overwritten A)."""
+        A = np.array(A, dtype=np.float64, order="F", copy=True)
         B = np.asfortranarray(B, dtype=np.float64)
         C = np.array(C, dtype=np.float64, order="F", copy=True)
         M, K = A.shape
@@ -473,7 +474,7 @@ class Engine(object):
         rc = self._lib.gpk_dbg_gemm_nt(self._h, mode, M, N, K, A.ctypes.data_as(c_double_p),
                                        B.ctypes.data_as(c_double_p), C.ctypes.data_as(c_double_p))
         self._check(rc, "gpk_dbg_gemm_nt")
-        return C
+        return (C, A) if mode == 7 else C
 
     def dbg_i8_tile(self, A, B, a_tmem=0):
         """int32 C = A (128,K) @ B (N,K)^T through one tcgen05.mma.kind::i8 tile; A, B int8 or uint8 arrays.

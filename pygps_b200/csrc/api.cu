@@ -22,7 +22,9 @@ int ensure(Handle* h, double** p, int64_t* cap, int64_t need) {
 static int ensure_events(Handle* h, size_t count) {
   while (h->ev.size() < count) {
     cudaEvent_t e;
-    GPK_CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // GPK_CHAIN_DUMP (diagnostic): the dependency events carry time stamps so that potrf_device can print the
+    // per-panel timeline of the dependent chain
+    GPK_CK(h, cudaEventCreateWithFlags(&e, getenv("GPK_CHAIN_DUMP") ? cudaEventDefault : cudaEventDisableTiming));
     h->ev.push_back(e);
   }
   return 0;
@@ -131,7 +133,10 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   auto fx_sl = [&](int j, int row_tile, int kstep0) {        // slice-buffer address of (row tile, k-step) of block j
     return h->ozSl[j & 1] + ((size_t)kstep0 * np + (size_t)row_tile * NB) * rowbytes;
   };
-  GPK_TRY(ensure_events(h, 5 * (size_t)T + 5));
+  const bool chain_dump = getenv("GPK_CHAIN_DUMP") != nullptr;
+  GPK_TRY(ensure_events(h, (chain_dump ? 6 : 5) * (size_t)T + 5));
+  cudaEvent_t* ev_dstart = chain_dump ? h->ev.data() + 5 * T + 5 : nullptr;   // [T] the panel stream reaches diag(p)
+  std::vector<char> was_split(T, 0);
   if (h->profile) GPK_TRY(ensure_prof_events(h, 2 * (size_t)T + 2));
   cudaEvent_t* ev_panel = h->ev.data();      // [T]   panel p factored and solved
   cudaEvent_t* ev_col = h->ev.data() + T;    // [T]   columns of level-1 block j up to date
@@ -193,6 +198,11 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   if (split) GPK_CK(h, cudaStreamWaitEvent(h->s_tail, ev_fork, 0));
   if (b_fwd) GPK_CK(h, cudaStreamWaitEvent(h->s_aux, ev_fork, 0));
   const int head_l1_on = env_int("GPK_POTRF_HEADL1", 1);
+  // the two products behind every diagonal block through small_nt_kernel.  0: the pipelined strip kernel of gemm_nt.cu;
+  // 1 / 2: small_nt_kernel in the chain-bound blocks / everywhere, both operands in shared memory; 3 / 4: the same with
+  // the B operand in registers (37 KB of shared memory: the CTAs fit beside a resident trailing-update CTA).
+  // Measured at N=16384 on one B200 (same box, best of 8): 0: 20.45-20.56 ms, 1: 19.75-20.12, 3: 19.78, 4: 19.78.
+  const int headk = env_int("GPK_POTRF_HEADK", 3);
   bool head_l1 = false;                                 // the last hand-over updated the next diagonal tile itself
   for (int j = 0; j < nblk; ++j) {
     const int pb = bstart[j], pe = bstart[j + 1];      // the level-1 block: panels [pb, pe)
@@ -204,6 +214,9 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
       else GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_col[j], 0));
     }
     const int w2 = bsub[j];
+    // the products on the dependent chain through small_nt_kernel: 1 = in the chain-bound (small) blocks, 2 = everywhere
+    // (3 / 4: as 1 / 2 with the B operand in registers, see small_nt_kernel)
+    const bool small_heads = headk == 2 || headk == 4 || ((headk == 1 || headk == 3) && !bbig[j]);
     for (int sb = pb; sb < pe; sb += w2) {
       const int se = (sb + w2 < pe) ? sb + w2 : pe;    // the level-2 sub-block: panels [sb, se)
       for (int p = sb; p < se; ++p) {
@@ -212,6 +225,7 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
         const int rem = T - p - 1;                     // tile rows below panel p
         const int inner = se - p - 1;                  // remaining columns of this sub-block
         if (split && p >= sb + 2) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_tail[p - 2], 0));
+        if (chain_dump) GPK_CK(h, cudaEventRecord(ev_dstart[p], h->s_panel));
         GPK_TRY(launch_diag(h, h->s_panel, App, lda, Dp, logdet_parts + p, info, p * NB));
         if (col_pending) {
           GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_col[j], 0));
@@ -237,16 +251,31 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
           if (split) GPK_CK(h, cudaEventRecord(ev_tail[p], h->s_panel));   // nothing of panel p is left for s_tail
         } else {
           GPK_CK(h, cudaEventRecord(ev_diag[p], h->s_panel));
+          was_split[p] = 1;
           // head (panel stream): tile (p+1,p) <- tile * Dinv_p', then tile (p+1,p+1) -= L(p+1,p) L(p+1,p)'
           if (p > sb) GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_tail[p - 1], 0));
           GemmArgs t{};
           t.A = App + NB; t.B = Dp; t.C = App + NB;
           t.lda = lda; t.ldb = NB; t.ldc = lda; t.K = NB; t.tri = 0;
-          GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, 1, 1));
-          GemmArgs hs{};
-          hs.A = App + NB; hs.B = App + NB; hs.C = A + (int64_t)(p + 1) * NB * (1 + lda);
-          hs.lda = lda; hs.ldb = lda; hs.ldc = lda; hs.K = NB; hs.tri = 1; hs.strips = 1;
-          GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, hs, 1, 1));
+          if (small_heads) {
+            // sixteen 32x32-block CTAs per product, whole operands requested at once (small_nt_kernel): the solved
+            // tile goes to the scratch tile, the update reads it from there and copies it home
+            SmallArgs s1{};
+            s1.A = App + NB; s1.lda = lda; s1.B = Dp; s1.ldb = NB; s1.C = h->dHead; s1.ldc = NB; s1.K = NB; s1.mode = 0;
+            s1.breg = headk >= 3;
+            GPK_TRY(launch_small_nt(h, h->s_panel, s1));
+            SmallArgs s2{};
+            s2.A = h->dHead; s2.lda = NB; s2.B = h->dHead; s2.ldb = NB; s2.C = A + (int64_t)(p + 1) * NB * (1 + lda);
+            s2.ldc = lda; s2.K = NB; s2.mode = 1; s2.tri = 1; s2.copy_dst = App + NB; s2.ld_copy = lda;
+            s2.breg = headk >= 3;
+            GPK_TRY(launch_small_nt(h, h->s_panel, s2));
+          } else {
+            GPK_TRY(launch_gemm_nt(h, h->s_panel, 0, t, 1, 1));
+            GemmArgs hs{};
+            hs.A = App + NB; hs.B = App + NB; hs.C = A + (int64_t)(p + 1) * NB * (1 + lda);
+            hs.lda = lda; hs.ldb = lda; hs.ldc = lda; hs.K = NB; hs.tri = 1; hs.strips = 1;
+            GPK_TRY(launch_gemm_nt(h, h->s_panel, 1, hs, 1, 1));
+          }
           GPK_CK(h, cudaEventRecord(ev_head[p], h->s_panel));
           // tail (s_tail): TRSM of rows p+2.., then column p+1 below its diagonal tile, then columns p+2..se-1
           GPK_CK(h, cudaStreamWaitEvent(h->s_tail, ev_diag[p], 0));
@@ -314,7 +343,11 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
       // 32-row strips), so the next diagonal kernel starts at once and overlaps the update of the other tiles.
       head_l1 = split && head_l1_on && !bbig[j];
       if (head_l1 && built_pending) { GPK_CK(h, cudaStreamWaitEvent(h->s_panel, ev_built, 0)); built_pending = false; }
-      if (head_l1) {
+      if (head_l1 && small_heads) {
+        SmallArgs hl{};
+        hl.A = Pblk; hl.lda = lda; hl.B = Pblk; hl.ldb = lda; hl.C = Ctr; hl.ldc = lda; hl.K = kw; hl.mode = 1; hl.tri = 1;
+        GPK_TRY(launch_small_nt(h, h->s_panel, hl));
+      } else if (head_l1) {
         GemmArgs hl{};
         hl.A = Pblk; hl.B = Pblk; hl.C = Ctr;
         hl.lda = lda; hl.ldb = lda; hl.ldc = lda; hl.K = kw; hl.tri = 1; hl.strips = 1;
@@ -374,6 +407,31 @@ int potrf_device(Handle* h, double* A, int64_t np, double* Dinv, double* logdet_
   if (b_fwd) {
     GPK_CK(h, cudaEventRecord(ev_aux, h->s_aux));
     GPK_CK(h, cudaStreamWaitEvent(h->s_main, ev_aux, 0));
+  }
+  if (chain_dump && h->profile) {
+    // per-panel timeline in microseconds since the fork: when the panel stream reached diag(p), diag done, head done,
+    // panel solved (ev_panel), tail done; per level-1 block: its columns up to date (ev_col), update start / end
+    GPK_CK(h, cudaStreamSynchronize(h->s_main));
+    auto us = [&](cudaEvent_t e) {
+      float ms = 0.f;
+      return cudaEventElapsedTime(&ms, ev_fork, e) == cudaSuccess ? (double)ms * 1e3 : -1.0;
+    };
+    (void)cudaGetLastError();
+    int pairs = 0;
+    for (int j = 0; j < nblk; ++j) {
+      const int pe = bstart[j + 1];
+      fprintf(stderr, "block %d panels [%d,%d) big=%d col_ready %.1f", j, bstart[j], pe, bbig[j], j > 0 ? us(ev_col[j]) : 0.0);
+      if (T - pe > 0 && h->profile && 2 * pairs + 1 < (int)h->prof_ev.size()) {
+        fprintf(stderr, " update [%.1f, %.1f]", us(h->prof_ev[2 * pairs]), us(h->prof_ev[2 * pairs + 1]));
+        ++pairs;
+      }
+      fprintf(stderr, "\n");
+      for (int p = bstart[j]; p < pe; ++p)
+        fprintf(stderr, "  p %3d dstart %9.1f diag %9.1f head %9.1f panel %9.1f tail %9.1f\n", p, us(ev_dstart[p]),
+                was_split[p] ? us(ev_diag[p]) : -1.0, was_split[p] ? us(ev_head[p]) : -1.0, us(ev_panel[p]),
+                split ? us(ev_tail[p]) : -1.0);
+    }
+    (void)cudaGetLastError();
   }
   return 0;
 }
@@ -714,6 +772,7 @@ int gpk_create(int device, gpk_handle* out) {
   for (auto e : te)
     if (cudaEventCreate(e) != cudaSuccess) return fail(GPK_ERR_CUDA);
   if (cudaMallocHost((void**)&h->hPinned, 4096 * sizeof(double)) != cudaSuccess) return fail(GPK_ERR_CUDA);
+  if (cudaMalloc((void**)&h->dHead, (size_t)NB * NB * sizeof(double)) != cudaSuccess) return fail(GPK_ERR_NOMEM);
   int rc = gemm_init(h);
   if (rc == 0) rc = diag_init(h);
   if (rc != 0) return fail(rc);
@@ -734,6 +793,7 @@ int gpk_destroy(gpk_handle hh) {
   for (auto e : te)
     if (e) cudaEventDestroy(e);
   if (h->hPinned) cudaFreeHost(h->hPinned);
+  if (h->dHead) cudaFree(h->dHead);
   if (h->s_main) cudaStreamDestroy(h->s_main);
   if (h->s_panel) cudaStreamDestroy(h->s_panel);
   if (h->s_aux) cudaStreamDestroy(h->s_aux);
@@ -1366,7 +1426,9 @@ int gpk_dbg_gemm_nt(gpk_handle hh, int mode, int64_t M, int64_t N, int64_t K, co
                     double* C) {
   Handle* h;
   GPK_TRY(check_handle(hh, &h));
-  if (!A || !B || !C || M % NB || N % NB || K % 32 || mode < 0 || mode > 4) return GPK_ERR_ARG;
+  if (!A || !B || !C || M % NB || N % NB || K % 32 || mode < 0 || mode > 7) return GPK_ERR_ARG;
+  if (mode >= 5 && (M != NB || N != NB || K % NB)) return GPK_ERR_ARG;
+  if (mode == 7 && K != NB) return GPK_ERR_ARG;
   if ((mode == 2 || mode == 3) && M != N) return GPK_ERR_ARG;
   if (mode == 4 && N != K) return GPK_ERR_ARG;
   cudaStream_t st = h->s_main;
@@ -1381,7 +1443,25 @@ int gpk_dbg_gemm_nt(gpk_handle hh, int mode, int64_t M, int64_t N, int64_t K, co
   u.A = dA; u.B = dB; u.C = dC; u.lda = M; u.ldb = N; u.ldc = M; u.K = (int)K;
   u.tri = (mode == 2) ? 1 : (mode == 3 ? 2 : 0);
   if (mode == 4) u.C = dA;   // in place over A, as the panel TRSM runs
-  int rc = launch_gemm_nt(h, st, (mode == 0 || mode >= 3) ? 0 : 1, u, (int)(M / NB), (int)(N / NB));
+  int rc = 0;
+  if (mode >= 5) {
+    // the chain products (small_nt_kernel).  5: C = A B' ; 6: C -= A B', blocks on / below the diagonal ;
+    // 7: the head pair of the panel chain: X = A B' into the scratch tile, C -= X X' (lower), A <- X
+    SmallArgs s1{};
+    s1.A = dA; s1.lda = M; s1.B = dB; s1.ldb = N; s1.C = (mode == 7) ? h->dHead : dC; s1.ldc = NB; s1.K = (int)K;
+    s1.mode = (mode == 6) ? 1 : 0; s1.tri = (mode == 6) ? 1 : 0;
+    s1.breg = env_int("GPK_SMALL_BREG", 0);
+    rc = launch_small_nt(h, st, s1);
+    if (rc == 0 && mode == 7) {
+      SmallArgs s2{};
+      s2.A = h->dHead; s2.lda = NB; s2.B = h->dHead; s2.ldb = NB; s2.C = dC; s2.ldc = NB; s2.K = NB; s2.mode = 1; s2.tri = 1;
+      s2.copy_dst = dA; s2.ld_copy = M; s2.breg = s1.breg;
+      rc = launch_small_nt(h, st, s2);
+      cudaMemcpyAsync(const_cast<double*>(A), dA, (size_t)M * K * 8, cudaMemcpyDeviceToHost, st);
+    }
+  } else {
+    rc = launch_gemm_nt(h, st, (mode == 0 || mode >= 3) ? 0 : 1, u, (int)(M / NB), (int)(N / NB));
+  }
   cudaMemcpyAsync(C, (mode == 4) ? dA : dC, (size_t)M * N * 8, cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(dA); cudaFree(dB); cudaFree(dC);

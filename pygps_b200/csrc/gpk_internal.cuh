@@ -46,6 +46,18 @@ struct GemmArgs {
                     // B rows advance by cstride*NB per tc while C columns stay packed.  0/1 = contiguous.
 };
 
+// one 128x128 tile of C (op)= A(128 x K) * B(128 x K)' by sixteen 32x32-block CTAs (potrf_diag.cu: small_nt_kernel)
+struct SmallArgs {
+  const double* A; const double* B; double* C;
+  int64_t lda, ldb, ldc;
+  int K;               // multiple of 128
+  int mode;            // 0: C = A B' ; 1: C -= A B'
+  int tri;             // only blocks on / below the diagonal; diagonal blocks store row >= col
+  double* copy_dst;    // K == 128 only: block column 0 also stores its 32 x 128 strip of A here (pitch ld_copy)
+  int64_t ld_copy;
+  int breg;            // K == 128 only: B goes global -> registers, 37 KB of shared memory per CTA instead of 74 KB
+};
+
 enum CovEpi { EPI_COV = 0, EPI_DER_ELL = 1, EPI_DER_SF = 2, EPI_DER_ARD = 3 };
 
 // ---- covariance programs: composite kernels evaluated on the device (covprog.cu) ---------------------------------
@@ -127,6 +139,7 @@ struct Handle {
   void* epGraphExec = nullptr; const void* epGraphSig[8] = {};   // the EP block's site launches as a CUDA graph (ep.cu)
   int* dFlags = nullptr; int flag_epoch = 0;   // epoch-stamped ready flags of the persistent backward substitution
   double* hPinned = nullptr; // small pinned staging
+  double* dHead = nullptr;   // (128,128) scratch tile of the panel chain: the solved head tile between its two products
   // posterior state
   bool has_post = false; int kind = 0, matern_d = 3, nhyp = 0; double sn2 = 1.0, sf2 = 1.0;
   std::vector<double> hyp;
@@ -243,6 +256,7 @@ int launch_fill_random(Handle* h, cudaStream_t st, double* p, int64_t n, unsigne
 int bench_dmma(Handle* h, int shape, int warps, int iters, double* tflops, double* ms_out);
 int gemm_init(Handle* h);
 int diag_init(Handle* h);
+int launch_small_nt(Handle* h, cudaStream_t st, const SmallArgs& a);
 
 int ensure(Handle* h, double** p, int64_t* cap, int64_t need_elems);
 int oz_ensure(Handle* h, int which, int64_t n, int kw);

@@ -346,6 +346,473 @@ potrf_diag_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ D
 }
 
 // ---------------------------------------------------------------------------
+// potrf_diag_ovl_kernel: the same factorisation with the block inverse taken OFF the end of the kernel.
+// The phase clocks of potrf_diag_kernel (scripts/diag_clk.py, B200): load 3.3k | 4 x (LDL' of a 32x32 block by ONE warp
+// 6.7-8.0k, sub-panel solve + trailing update 5.0-6.9k) | 32x32 inverses 4.0k | block inverse 18.3k | store 4.1k
+// = 75.7k clk; while warp 0 factors a 32x32 block the other seven warps idle, and the whole inverse (22.3k) waits for
+// the last block.  Here the inverse is built by ROW blocks, W[i,j] = -W_ii * Z[i,j], Z[i,j] = sum_{k=j}^{i-1} L[i,k] W[k,j],
+// and row block i only needs rows <= i of L: warps 1-7 compute W_(i-1,i-1), row i-1 of the inverse and Z[i,.] in the
+// shadow of LDL'(i) on warp 0 (named barrier 1 among themselves).  After the last block only W_33 and three 32x32
+// products remain.  The strictly-upper 32x32 blocks of S are unused by the factorisation: block (j,i) of S holds W[i,j].
+// ---------------------------------------------------------------------------
+constexpr size_t DIAG_OVL_SMEM = DIAG_SMEM + size_t(3) * IB * LDT * sizeof(double);
+
+template <int NT>
+__device__ __forceinline__ void frag_store(double (&acc)[2][NT][4], double* C, int ldc, int lane, double alpha) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+      double* p = C + (mi * 16 + g) + (ni * 8 + 2 * t) * ldc;
+      p[0] = alpha * acc[mi][ni][0];
+      p[ldc] = alpha * acc[mi][ni][1];
+      p[8] = alpha * acc[mi][ni][2];
+      p[8 + ldc] = alpha * acc[mi][ni][3];
+    }
+}
+
+// one warp: T[b] = W = inv(L_bb).  Lane r solves x L_bb' = e_r by the right-looking substitution of the sub-panel solve
+// (the factor is read down its columns with broadcast 16-byte loads; one DMUL + one DFMA on the chain per column):
+// x = row r of L_bb^-T = column r of W.  The left-looking form of potrf_diag_kernel's phase 2 needs a 8-byte shared
+// load per DFMA: 4.0k clk against 1.6k here.
+__device__ __forceinline__ void inv32_warp(const double* S, double* T, const double* rdiag, int b, int lane) {
+  const int j0 = b * IB;
+  double x[IB];
+#pragma unroll
+  for (int c = 0; c < IB; ++c) x[c] = (c == lane) ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 0; k < IB; ++k) {
+    const double xk = x[k] * rdiag[j0 + k];
+    x[k] = xk;
+    const double* colk = &S_(j0, j0 + k);
+    if (((k + 1) & 1) && k + 1 < IB) x[k + 1] = fma(-xk, colk[k + 1], x[k + 1]);
+#pragma unroll
+    for (int c = (k + 2) & ~1; c < IB; c += 2) {
+      const double2 lc = *reinterpret_cast<const double2*>(colk + c);
+      x[c] = fma(-xk, lc.x, x[c]);
+      x[c + 1] = fma(-xk, lc.y, x[c + 1]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < IB; ++c) T_(b, c, lane) = x[c];
+}
+
+// rows [32*rb0, 32*rb1) of the block inverse to global (dense 128x128, pitch 128): diagonal blocks from T, block
+// (bi > bj) from S block (bj, bi), zeros above; `nthr` threads with index `t`
+__device__ __forceinline__ void inv_rows_to_global(const double* S, const double* T, double* __restrict__ Dinv, int rb0,
+                                                   int rb1, int t, int nthr) {
+  const int hr = (rb1 - rb0) * IB / 2;               // 16-byte pieces per column
+  for (int idx = t; idx < hr * DB; idx += nthr) {
+    const int r = rb0 * IB + (idx % hr) * 2, c = idx / hr;
+    const int bi = r / IB, bj = c / IB, ri = r % IB, ci = c % IB;
+    double2 v = make_double2(0.0, 0.0);
+    if (bi == bj) v = *reinterpret_cast<const double2*>(&T_(bi, ri, ci));
+    else if (bi > bj) v = *reinterpret_cast<const double2*>(&S_(bj * IB + ri, bi * IB + ci));
+    *reinterpret_cast<double2*>(Dinv + r + c * DB) = v;
+  }
+}
+
+// shared -> global through the TMA engine (async proxy, bulk_group completion): the store neither occupies the
+// load/store pipe of the issuing warp nor stalls later shared-memory instructions behind a queue of global stores
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// ASYNC_ST = false: L and the inverse leave through ordinary 16-byte stores after the factorisation (the L tile by warps
+// 4-7 beside W_33, the inverse by everybody at the end).  One SM drains about 32 bytes per clock: the 2 x 128 KB cost
+// 8k clk, and shared-memory instructions issued behind them wait (measured: the 1.5k-clk last row block took 12.7k clk
+// behind 224 KB of stores).  ASYNC_ST = true: every piece leaves by cp.async.bulk the moment it is final - block column
+// jb of L after its sub-panel solve, row block i-1 of the inverse after step S2 of iteration i, the zero blocks above
+// the diagonal right at the start - and only the last row block of the inverse is still to go when the arithmetic ends.
+template <bool ASYNC_ST>
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
+potrf_diag_ovl_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ Dinv,
+                      double* __restrict__ logdet_slot, int* __restrict__ info, int gidx0, long long* dbg_clk) {
+  extern __shared__ __align__(16) double dsm[];
+  int dbg_i = 0;
+#define DBG_T() do { if (dbg_clk && threadIdx.x == 0) dbg_clk[dbg_i++] = clock64(); } while (0)
+#define SIDE_BAR() asm volatile("bar.sync 1, 224;\n" ::: "memory")
+  DBG_T();
+  double* S = dsm;                    // DB x LDS_
+  double* T = dsm + DB * LDS_;        // 4 x (IB x LDT): W_jj
+  double* rdiag = T + 4 * IB * LDT;   // DB reciprocals of the diagonal of L
+  double* Zs = rdiag + DB;            // 3 x (IB x LDT): Z[i, 0..2] of the row block in progress
+  __shared__ double s_logdet;
+  __shared__ int s_info;
+  __shared__ __align__(16) double zcol[IB];   // ASYNC_ST: source of the zero blocks
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+#pragma unroll 8
+  for (int idx = tid; idx < DB * DB / 2; idx += DIAG_THREADS) {
+    const int r = (idx % (DB / 2)) * 2, c = idx / (DB / 2);
+    double2 v = make_double2(0.0, 0.0);
+    if (r + 1 >= c) v = *reinterpret_cast<const double2*>(Ablk + r + (int64_t)c * lda);
+    if (r < c) v.x = 0.0;
+    *reinterpret_cast<double2*>(&S_(r, c)) = v;
+  }
+  if (tid == 0) { s_logdet = 0.0; s_info = 0; }
+  if (ASYNC_ST) {
+    if (tid < IB) zcol[tid] = 0.0;
+    fence_async_smem();
+  }
+  __syncthreads();
+  DBG_T();
+  if (ASYNC_ST && warp >= 1 && warp <= 6) {
+    // the six 32x32 blocks above the block diagonal, of the L tile and of the inverse: zeros (lane = column)
+    const int ub = warp - 1;                         // (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    const int bj = (ub < 3) ? ub + 1 : (ub < 5 ? ub - 1 : 3), bi = (ub < 3) ? 0 : (ub < 5 ? 1 : 2);
+    fence_async_smem();
+    bulk_store(Ablk + bi * IB + (int64_t)(bj * IB + lane) * lda, zcol, IB * sizeof(double));
+    bulk_store(Dinv + bi * IB + (bj * IB + lane) * DB, zcol, IB * sizeof(double));
+    bulk_commit();
+  }
+
+  for (int jb = 0; jb < DB / IB; ++jb) {
+    const int j0 = jb * IB;
+    if (warp == 0) {
+      // 32x32 diagonal block by ONE warp, square-root-free (see potrf_diag_kernel)
+      double a[IB];
+#pragma unroll
+      for (int c = 0; c < IB; ++c) a[c] = S_(j0 + lane, j0 + c);
+      __syncwarp();
+      double dmine = 1.0;
+      int bad = 0;
+#pragma unroll
+      for (int j = 0; j < IB; ++j) {
+        const double aj = (lane >= j) ? a[j] : 0.0;
+        double* colj = &S_(j0, j0 + j);
+        colj[lane] = aj;
+        __syncwarp();
+        const double d = colj[j];
+        if (!(d > 0.0) && bad == 0) bad = j + 1;
+        if (lane == j) dmine = d;
+        double x0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(d));
+        const double e = fma(-d, x0, 1.0);
+        const double inv = fma(x0, fma(e, e, e), x0);
+        const double w = -aj * inv;
+        if (((j + 1) & 1) && j + 1 < IB) a[j + 1] = fma(w, colj[j + 1], a[j + 1]);
+#pragma unroll
+        for (int c = (j + 2) & ~1; c < IB; c += 2) {
+          const double2 lc = *reinterpret_cast<const double2*>(colj + c);
+          a[c] = fma(w, lc.x, a[c]);
+          a[c + 1] = fma(w, lc.y, a[c + 1]);
+        }
+      }
+      const double rs = rsqrt(dmine);
+      double lg = 0.5 * log(dmine);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(FULL, lg, o);
+      rdiag[j0 + lane] = rs;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < IB; c += 2) {
+        const double2 rc = *reinterpret_cast<const double2*>(rdiag + j0 + c);
+        const double v0 = (lane == c) ? dmine * rs : S_(j0 + lane, j0 + c) * rc.x;
+        const double v1 = (lane == c + 1) ? dmine * rs : S_(j0 + lane, j0 + c + 1) * rc.y;
+        S_(j0 + lane, j0 + c) = v0;
+        S_(j0 + lane, j0 + c + 1) = v1;
+      }
+      if (lane == 0) {
+        s_logdet += lg;
+        if (bad != 0 && s_info == 0) s_info = gidx0 + j0 + bad;
+      }
+    } else if (jb >= 1) {
+      // ---- in the shadow of LDL'(jb): the inverse up to row block jb-1, and Z of row block jb ----
+      const int i = jb, sw = warp - 1;               // sw = 0..6
+      const int j = sw >> 1, half = sw & 1;
+      if (sw == 0) inv32_warp(S, T, rdiag, i - 1, lane);
+      if (ASYNC_ST) fence_async_smem();
+      SIDE_BAR();
+      if (j < i - 1) {                               // W[i-1, j] = -W_(i-1,i-1) * Z[i-1, j]  ->  S block (j, i-1)
+        double acc[2][2][4];
+        frag_zero<2>(acc);
+        warp_mma32<2>(acc, &T_(i - 1, 0, 0), LDT, Zs + j * IB * LDT + half * 16 * LDT, LDT, 1, IB, lane);
+        frag_store<2>(acc, &S_(j * IB, (i - 1) * IB + half * 16), LDS_, lane, -1.0);
+      }
+      if (ASYNC_ST) fence_async_smem();
+      SIDE_BAR();
+      if (ASYNC_ST && sw == 6) {
+        // row block i-1 of the inverse is final: W[i-1, j] from S block (j, i-1), W_(i-1,i-1) from T (lane = column)
+        fence_async_smem();
+        for (int jj = 0; jj < i - 1; ++jj)
+          bulk_store(Dinv + (i - 1) * IB + (jj * IB + lane) * DB, &S_(jj * IB, (i - 1) * IB + lane), IB * sizeof(double));
+        bulk_store(Dinv + (i - 1) * IB + ((i - 1) * IB + lane) * DB, &T_(i - 1, 0, lane), IB * sizeof(double));
+        bulk_commit();
+      }
+      if (j < i) {                                   // Z[i, j] = sum_{k=j}^{i-1} L[i,k] W[k,j]  ->  Zs[j]
+        double acc[2][2][4];
+        frag_zero<2>(acc);
+        warp_mma32<2>(acc, &S_(i * IB, j * IB), LDS_, &T_(j, 0, half * 16), LDT, 1, IB, lane);
+        for (int k = j + 1; k < i; ++k)
+          warp_mma32<2>(acc, &S_(i * IB, k * IB), LDS_, &S_(j * IB, k * IB + half * 16), LDS_, 1, IB, lane);
+        frag_store<2>(acc, Zs + j * IB * LDT + half * 16 * LDT, LDT, lane, 1.0);
+      }
+    }
+    if (ASYNC_ST) fence_async_smem();
+    __syncthreads();
+    DBG_T();
+    const int nrb = DB / IB - 1 - jb;
+    if (nrb > 0) {
+      if (tid < nrb * IB) {
+        const int r = j0 + IB + tid;
+        double x[IB];
+#pragma unroll
+        for (int c = 0; c < IB; ++c) x[c] = S_(r, j0 + c);
+#pragma unroll
+        for (int k = 0; k < IB; ++k) {
+          const double xk = x[k] * rdiag[j0 + k];
+          x[k] = xk;
+          const double* colk = &S_(j0, j0 + k);
+          if (((k + 1) & 1) && k + 1 < IB) x[k + 1] = fma(-xk, colk[k + 1], x[k + 1]);
+#pragma unroll
+          for (int c = (k + 2) & ~1; c < IB; c += 2) {
+            const double2 lc = *reinterpret_cast<const double2*>(colk + c);
+            x[c] = fma(-xk, lc.x, x[c]);
+            x[c + 1] = fma(-xk, lc.y, x[c + 1]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < IB; ++c) S_(r, j0 + c) = x[c];
+      }
+      if (ASYNC_ST) fence_async_smem();
+      __syncthreads();
+    }
+    if (ASYNC_ST && warp == DW - 1) {
+      // block column jb of L is final (rows from its diagonal block down; zeros above the diagonal inside that block
+      // were stored by the LDL' warp): one bulk store per column, issued by the warp the trailing update leaves idle
+      fence_async_smem();
+      bulk_store(Ablk + j0 + (int64_t)(j0 + lane) * lda, &S_(j0, j0 + lane), (DB - j0) * sizeof(double));
+      bulk_commit();
+    }
+    if (nrb > 0) {
+      const int npair = nrb * (nrb + 1) / 2;
+      for (int pr = warp; pr < npair; pr += DW) {
+        int ib = 0, cb = 0;
+        {
+          int q = pr;
+          while (q > ib) { q -= (ib + 1); ++ib; }
+          cb = q;
+        }
+        double acc[2][4][4];
+        frag_zero<4>(acc);
+        const int rr = j0 + IB + ib * IB, cc = j0 + IB + cb * IB;
+        warp_mma32<4>(acc, &S_(rr, j0), LDS_, &S_(cc, j0), 1, LDS_, IB, lane);
+        frag_apply<4>(acc, &S_(rr, cc), lane, -1.0, 1.0);
+      }
+      __syncthreads();
+    }
+    DBG_T();
+  }
+
+  // ---- W_33 (warp 0) || ordinary stores only: L back to global (warps 4-7) ----
+  if (warp == 0) {
+    inv32_warp(S, T, rdiag, DB / IB - 1, lane);
+  } else if (!ASYNC_ST && warp >= 4) {
+    for (int idx = tid - 4 * 32; idx < DB * DB / 2; idx += DIAG_THREADS - 4 * 32) {
+      const int r = (idx % (DB / 2)) * 2, c = idx / (DB / 2);
+      double2 v = *reinterpret_cast<const double2*>(&S_(r, c));
+      if (r < c) v.x = 0.0;
+      if (r + 1 < c) v.y = 0.0;
+      *reinterpret_cast<double2*>(Ablk + r + (int64_t)c * lda) = v;
+    }
+  }
+  if (tid == 0) {
+    *logdet_slot = s_logdet;
+    if (s_info != 0) info_min(info, s_info);
+  }
+  __syncthreads();
+  DBG_T();
+  // ---- last row block of the inverse: W[3, j] = -W_33 * Z[3, j] -> S block (j, 3); twelve 32x8 tasks over 8 warps ----
+  for (int task = warp; task < 3 * 4; task += DW) {
+    const int j = task >> 2, q = task & 3;
+    double acc[2][1][4];
+    frag_zero<1>(acc);
+    warp_mma32<1>(acc, &T_(DB / IB - 1, 0, 0), LDT, Zs + j * IB * LDT + q * 8 * LDT, LDT, 1, IB, lane);
+    frag_store<1>(acc, &S_(j * IB, (DB / IB - 1) * IB + q * 8), LDS_, lane, -1.0);
+  }
+  if (ASYNC_ST) fence_async_smem();
+  __syncthreads();
+  DBG_T();
+  if (ASYNC_ST) {
+    // ---- last row block of the inverse: warp j < 3 sends W[3, j], warp 3 sends W_33; then every thread that issued
+    //      bulk stores waits until the engine has read its shared-memory sources ----
+    if (warp < DB / IB) {
+      fence_async_smem();
+      const double* src = (warp < DB / IB - 1) ? &S_(warp * IB, (DB / IB - 1) * IB + lane) : &T_(DB / IB - 1, 0, lane);
+      bulk_store(Dinv + (DB / IB - 1) * IB + (warp * IB + lane) * DB, src, IB * sizeof(double));
+      bulk_commit();
+    }
+    bulk_wait_read_all();
+  } else {
+    inv_rows_to_global(S, T, Dinv, 0, DB / IB, tid, DIAG_THREADS);
+  }
+  __syncthreads();
+  DBG_T();
+#undef DBG_T
+#undef SIDE_BAR
+}
+
+// ---------------------------------------------------------------------------
+// small_nt_kernel: the products ON the dependent chain, where the operands are one or two 128-row tiles and the time is
+// launch + memory latency, not arithmetic:  C(32x32 block bi,bj) (op)= A(rows 32bi..) * B(rows 32bj..)'  over K.
+// The chain timeline (GPK_CHAIN_DUMP) showed the two "head" products after every diagonal block - tile (p+1,p) times
+// Dinv_p', then the rank-128 update of tile (p+1,p+1) - at 10-13 us EACH through the pipelined tile kernel of
+// gemm_nt.cu (four 32-row-strip CTAs, a 4-stage ring of 16-column slabs: eight dependent slab round trips for K=128).
+// Here a 128x128 tile is cut into sixteen 32x32 blocks, one CTA of four warps each; a CTA requests its WHOLE operand
+// chunk (32 rows x 128 columns of A and of B) at once, waits once, and runs 16 DMMA k-steps per warp from shared
+// memory.  K > 128 (the rank-512 update of the next diagonal tile at a level-1 hand-over) walks chunks of 128 through
+// two stages.  Sixteen CTAs cannot work in place (a sibling would overwrite columns still being read), so the
+// solved tile goes to a scratch tile and the CTAs of block column 0 of the FOLLOWING update copy it home
+// (copy_dst) - the update reads the scratch tile as both operands anyway.
+//   mode 0: C = A B'      mode 1: C -= A B'
+//   tri   : only blocks bi >= bj, diagonal blocks store row >= col
+// Replaces (on the chain-bound part of the factorisation) the same reference lines as launch_gemm_nt:
+// LAPACK dpotrf called at /root/reference/pyGPs/Core/tools.py:61.
+// ---------------------------------------------------------------------------
+constexpr int SN_P = 36;                        // shared-memory pitch of a 32-row operand block: == 4 mod 16, see LDT
+constexpr int SN_KC = 128;                      // contraction chunk
+constexpr int SN_STAGE = 2 * SN_KC * SN_P;      // doubles per stage: A block, then B block
+constexpr int SN_THREADS = 128;
+constexpr size_t SN_SMEM1 = size_t(SN_STAGE) * sizeof(double);       // K == 128
+constexpr size_t SN_SMEM2 = 2 * SN_SMEM1;                            // K  > 128
+
+// 32 rows x 128 columns of a column-major matrix -> shared memory (pitch SN_P): 16 pieces of 16 bytes per column
+__device__ __forceinline__ void sn_load(double* dst, const double* __restrict__ src, int64_t ld, int tid) {
+#pragma unroll
+  for (int i = 0; i < (32 * SN_KC / 2) / SN_THREADS; ++i) {
+    const int piece = tid + i * SN_THREADS;
+    const int c = piece >> 4, r = (piece & 15) * 2;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r + c * SN_P);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + r + (int64_t)c * ld) : "memory");
+  }
+}
+
+// BREG (K == 128 only): the B operand never touches shared memory.  A warp needs just 8 rows of B (its 8 output columns),
+// 32 doubles per lane for the whole contraction, fetched straight into the DMMA fragment registers while the A block
+// arrives by cp.async.  Shared memory per CTA drops from 74 KB to 37 KB, which is what lets these CTAs start BESIDE a
+// resident trailing-update CTA (172 KB of the SM's 227 KB): with 74 KB the chain timeline showed the head products
+// waiting up to 20 us for the first wave of a freshly launched update to retire.
+template <bool BREG>
+__global__ void __launch_bounds__(SN_THREADS) small_nt_kernel(SmallArgs a) {
+  extern __shared__ __align__(16) double sn_sm[];
+  const int bi = blockIdx.x, bj = blockIdx.y;
+  if (a.tri && bj > bi) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const double* Ag = a.A + 32 * bi;
+  const double* Bg = a.B + 32 * bj;
+  const int nch = BREG ? 1 : a.K / SN_KC;
+  const int nst = nch > 1 ? 2 : 1;
+  double breg[BREG ? 2 * (SN_KC / 8) : 1];
+  if (BREG) {
+    sn_load(sn_sm, Ag, a.lda, tid);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const double* Bw = Bg + 8 * warp + g;           // row 8*warp + g of this block of B
+#pragma unroll
+    for (int ks = 0; ks < SN_KC / 8; ++ks) {
+      breg[2 * ks] = Bw[(int64_t)(8 * ks + t) * a.ldb];
+      breg[2 * ks + 1] = Bw[(int64_t)(8 * ks + t + 4) * a.ldb];
+    }
+  } else {
+    for (int s = 0; s < nst; ++s) {
+      double* stg = sn_sm + s * SN_STAGE;
+      sn_load(stg, Ag + (int64_t)s * SN_KC * a.lda, a.lda, tid);
+      sn_load(stg + SN_KC * SN_P, Bg + (int64_t)s * SN_KC * a.ldb, a.ldb, tid);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+  }
+  // this thread's entries of the 32x32 block: rows mi*16+g (+8), columns 8*warp + 2t (+1)
+  double* Cb = a.C + 32 * bi + (int64_t)(32 * bj + 8 * warp + 2 * t) * a.ldc;
+  double cold[2][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    cold[mi][0] = cold[mi][1] = cold[mi][2] = cold[mi][3] = 0.0;
+    if (a.mode == 1) {                            // requested while the operands are in flight
+      const int r0 = mi * 16 + g;
+      cold[mi][0] = Cb[r0]; cold[mi][1] = Cb[r0 + a.ldc];
+      cold[mi][2] = Cb[r0 + 8]; cold[mi][3] = Cb[r0 + 8 + a.ldc];
+    }
+  }
+  double acc[2][1][4];
+  frag_zero<1>(acc);
+  if (BREG) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < SN_KC / 8; ++ks) {
+      const int k0 = 8 * ks;
+      double af[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        af[mi][0] = sn_sm[(mi * 16 + g) + (k0 + t) * SN_P];
+        af[mi][1] = sn_sm[(mi * 16 + g + 8) + (k0 + t) * SN_P];
+        af[mi][2] = sn_sm[(mi * 16 + g) + (k0 + t + 4) * SN_P];
+        af[mi][3] = sn_sm[(mi * 16 + g + 8) + (k0 + t + 4) * SN_P];
+      }
+      dmma8(acc[0][0], af[0], breg[2 * ks], breg[2 * ks + 1]);
+      dmma8(acc[1][0], af[1], breg[2 * ks], breg[2 * ks + 1]);
+    }
+  }
+  for (int c = 0; !BREG && c < nch; ++c) {
+    if (c + 1 < nch) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    const double* stg = sn_sm + (c & 1) * SN_STAGE;
+    warp_mma32<1>(acc, stg, SN_P, stg + SN_KC * SN_P + 8 * warp, 1, SN_P, SN_KC, lane);
+    if (c + 2 < nch) {
+      __syncthreads();                            // every warp is done with this stage
+      double* nxt = sn_sm + (c & 1) * SN_STAGE;
+      sn_load(nxt, Ag + (int64_t)(c + 2) * SN_KC * a.lda, a.lda, tid);
+      sn_load(nxt + SN_KC * SN_P, Bg + (int64_t)(c + 2) * SN_KC * a.ldb, a.ldb, tid);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+  }
+  const bool diag_blk = a.tri && bi == bj;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    const int r0 = mi * 16 + g, r1 = r0 + 8, c0 = 8 * warp + 2 * t, c1 = c0 + 1;
+    const double v0 = (a.mode == 1) ? cold[mi][0] - acc[mi][0][0] : acc[mi][0][0];
+    const double v1 = (a.mode == 1) ? cold[mi][1] - acc[mi][0][1] : acc[mi][0][1];
+    const double v2 = (a.mode == 1) ? cold[mi][2] - acc[mi][0][2] : acc[mi][0][2];
+    const double v3 = (a.mode == 1) ? cold[mi][3] - acc[mi][0][3] : acc[mi][0][3];
+    if (!diag_blk || r0 >= c0) Cb[r0] = v0;
+    if (!diag_blk || r0 >= c1) Cb[r0 + a.ldc] = v1;
+    if (!diag_blk || r1 >= c0) Cb[r1] = v2;
+    if (!diag_blk || r1 >= c1) Cb[r1 + a.ldc] = v3;
+  }
+  if (a.copy_dst && bj == 0) {
+    // K == 128 (checked by the launcher): stage 0 still holds this CTA's 32 x 128 strip of A
+    double* dst = a.copy_dst + 32 * bi;
+#pragma unroll
+    for (int i = 0; i < (32 * SN_KC / 2) / SN_THREADS; ++i) {
+      const int piece = tid + i * SN_THREADS;
+      const int c = piece >> 4, r = (piece & 15) * 2;
+      *reinterpret_cast<double2*>(dst + r + (int64_t)c * a.ld_copy) = *reinterpret_cast<const double2*>(sn_sm + r + c * SN_P);
+    }
+  }
+}
+
+// one 128x128 tile of C: sixteen (tri: ten working) CTAs
+int launch_small_nt(Handle* h, cudaStream_t st, const SmallArgs& a) {
+  if (a.K <= 0 || a.K % SN_KC != 0 || (a.mode != 0 && a.mode != 1)) return GPK_ERR_ARG;
+  if (a.copy_dst && a.K != SN_KC) return GPK_ERR_ARG;
+  if (a.breg && a.K == SN_KC)
+    small_nt_kernel<true><<<dim3(NB / 32, NB / 32), SN_THREADS, SN_SMEM1 / 2, st>>>(a);
+  else
+    small_nt_kernel<false><<<dim3(NB / 32, NB / 32), SN_THREADS, a.K > SN_KC ? SN_SMEM2 : SN_SMEM1, st>>>(a);
+  h->stats.launches++;
+  GPK_CK(h, cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // single right-hand-side substitution steps.  512 threads; each 128x128 tile is pulled into shared
 // memory with cp.async (all 128 KB in flight at once - these steps are pure latency), then reduced there.
 // ---------------------------------------------------------------------------
@@ -596,15 +1063,24 @@ int launch_trsv_bwd_all(Handle* h, cudaStream_t st, const double* A, int64_t lda
 int diag_init(Handle* h) {
   GPK_CK(h, cudaFuncSetAttribute(potrf_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
   GPK_CK(h, cudaFuncSetAttribute(potrf_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+  GPK_CK(h, cudaFuncSetAttribute(potrf_diag_ovl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_OVL_SMEM));
+  GPK_CK(h, cudaFuncSetAttribute(potrf_diag_ovl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_OVL_SMEM));
   GPK_CK(h, cudaFuncSetAttribute(trsv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM));
   GPK_CK(h, cudaFuncSetAttribute(trsv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSV_SMEM));
   GPK_CK(h, cudaFuncSetAttribute(trsv_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SMEM));
+  GPK_CK(h, cudaFuncSetAttribute(small_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SN_SMEM2));
   return 0;
 }
 
 int launch_diag(Handle* h, cudaStream_t st, double* Ablk, int64_t lda, double* Dinv, double* logdet_slot, int* info,
                 int gidx0, long long* dbg_clk) {
-  potrf_diag_kernel<false><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
+  const int ovl = env_int("GPK_DIAG_OVL", 1);             // 0: the inverse after the factorisation (A/B runs)
+  if (ovl >= 2)       // 2: every finished piece leaves at once by cp.async.bulk
+    potrf_diag_ovl_kernel<true><<<1, DIAG_THREADS, DIAG_OVL_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
+  else if (ovl == 1)  // 1: the inverse by row blocks in the shadow of the 32x32 factorisations, ordinary stores
+    potrf_diag_ovl_kernel<false><<<1, DIAG_THREADS, DIAG_OVL_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
+  else
+    potrf_diag_kernel<false><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
   h->stats.launches++;
   GPK_CK(h, cudaGetLastError());
   return 0;

@@ -64,6 +64,39 @@ def test_gemm_nt_in_place_is_race_free(eng):
         assert np.allclose(got, A @ B.T, rtol=1e-12, atol=1e-11), _report("in-place A*B^T", got, A @ B.T)
 
 
+@pytest.mark.parametrize("breg", ["0", "1"])
+@pytest.mark.parametrize("K", [128, 256, 512, 1024])
+def test_chain_products_match_numpy(eng, monkeypatch, K, breg):
+    """small_nt_kernel (sixteen 32x32-block CTAs per tile): C = A B' and the lower-block C -= A B'; for K = 128 with
+    both operands in shared memory and with the B operand in registers."""
+    monkeypatch.setenv("GPK_SMALL_BREG", breg)
+    rng = np.random.default_rng(K)
+    A = rng.standard_normal((128, K)); B = rng.standard_normal((128, K)); C = rng.standard_normal((128, 128))
+    got = eng.dbg_gemm_nt(5, A, B, C)
+    assert np.allclose(got, A @ B.T, rtol=1e-12, atol=1e-11), _report("chain product, set", got, A @ B.T)
+    got = eng.dbg_gemm_nt(6, A, B, C)
+    ref = C - A @ B.T
+    lo = np.tril(np.ones((128, 128), bool))
+    assert np.allclose(got[lo], ref[lo], rtol=1e-12, atol=1e-11), _report("chain product, update", np.where(lo, got, 0), np.where(lo, ref, 0))
+    assert np.array_equal(got[~lo], C[~lo]), "strict upper triangle was written"
+
+
+@pytest.mark.parametrize("breg", ["0", "1"])
+def test_chain_head_pair_solves_updates_and_copies_home(eng, monkeypatch, breg):
+    """The two products behind every diagonal block: X = A W' (W lower triangular), C -= X X' (lower), A <- X."""
+    monkeypatch.setenv("GPK_SMALL_BREG", breg)
+    rng = np.random.default_rng(77)
+    A = rng.standard_normal((128, 128)); W = np.tril(rng.standard_normal((128, 128))); C = rng.standard_normal((128, 128))
+    for _ in range(3):
+        gotC, gotA = eng.dbg_gemm_nt(7, A, W, C)
+        X = A @ W.T
+        ref = C - X @ X.T
+        lo = np.tril(np.ones((128, 128), bool))
+        assert np.allclose(gotA, X, rtol=1e-12, atol=1e-11), _report("head tile", gotA, X)
+        assert np.allclose(gotC[lo], ref[lo], rtol=1e-12, atol=1e-10), _report("head update", np.where(lo, gotC, 0), np.where(lo, ref, 0))
+        assert np.array_equal(gotC[~lo], C[~lo]), "strict upper triangle was written"
+
+
 def _spd128(seed):
     rng = np.random.default_rng(seed)
     X = rng.standard_normal((128, 3))
@@ -71,7 +104,11 @@ def _spd128(seed):
     return np.exp(-0.5 * d / 4.0) / 0.01 + np.eye(128)
 
 
-def test_diag_block_factor_and_inverse(eng):
+@pytest.mark.parametrize("ovl", ["0", "1", "2"])
+def test_diag_block_factor_and_inverse(eng, monkeypatch, ovl):
+    """ovl 0: inverse after the factorisation; 1: inverse by row blocks under the 32x32 factorisations; 2: as 1, every
+    finished piece stored at once by cp.async.bulk."""
+    monkeypatch.setenv("GPK_DIAG_OVL", ovl)
     A = _spd128(1)
     L, Li, ld, info = eng.dbg_diag(A)
     Lref = np.linalg.cholesky(A)
@@ -82,7 +119,9 @@ def test_diag_block_factor_and_inverse(eng):
     assert abs(ld - np.log(np.diag(Lref)).sum()) < 1e-10 * abs(ld)
 
 
-def test_diag_block_flags_first_bad_pivot(eng):
+@pytest.mark.parametrize("ovl", ["0", "1", "2"])
+def test_diag_block_flags_first_bad_pivot(eng, monkeypatch, ovl):
+    monkeypatch.setenv("GPK_DIAG_OVL", ovl)
     A = _spd128(2)
     A[70, 70] = -3.0
     _, _, _, info = eng.dbg_diag(A)
@@ -142,6 +181,25 @@ def test_potrf_potrs_match_lapack(eng, n):
     Xs = eng.potrs(B)
     ref = sla.cho_solve((Rref, False), B)
     assert np.allclose(Xs, ref, rtol=1e-7, atol=1e-9), _report("potrs n=%d" % n, Xs, ref)
+
+
+@pytest.mark.parametrize("headk,ovl", [("0", "0"), ("1", "1"), ("2", "1"), ("3", "2"), ("4", "2")])
+def test_chain_variants_give_the_same_factor(eng, monkeypatch, headk, ovl):
+    """The dependent chain of the blocked factorisation through every combination of its kernels (GPK_POTRF_HEADK:
+    strip kernel / small_nt_kernel with B in shared memory / in registers, in the small blocks / everywhere;
+    GPK_DIAG_OVL: the three diagonal-block kernels): same factor as LAPACK, N large enough for split panels."""
+    n = 1500
+    rng = np.random.default_rng(15)
+    X = rng.standard_normal((n, 3))
+    d = ((X[:, None] - X[None]) ** 2).sum(-1)
+    A = np.exp(-0.5 * d / 2.0) / 0.04 + np.eye(n)
+    monkeypatch.setenv("GPK_POTRF_HEADK", headk)
+    monkeypatch.setenv("GPK_DIAG_OVL", ovl)
+    R, ld = eng.potrf(A)
+    Rref = np.linalg.cholesky(A).T
+    assert np.all(np.tril(R, -1) == 0)
+    assert np.allclose(R, Rref, rtol=1e-9, atol=1e-9), _report("potrf headk=%s ovl=%s" % (headk, ovl), R, Rref)
+    assert abs(ld - np.log(np.diag(Rref)).sum()) < 1e-10 * abs(ld)
 
 
 def test_potrf_not_positive_definite_raises(eng):
