@@ -19,6 +19,17 @@ int ensure(Handle* h, double** p, int64_t* cap, int64_t need) {
   return 0;
 }
 
+// ensure() for the buffers that hold inverses of diagonal blocks: a fresh allocation is zero-filled, because the
+// factorisation's diagonal kernel does not store the zero blocks above the block diagonal of an inverse (GPK_DIAG_SKIPZ)
+// while every consumer multiplies by the whole 128x128 block.
+int ensure_zero(Handle* h, double** p, int64_t* cap, int64_t need) {
+  if (*cap >= need && *p) return 0;
+  GPK_TRY(ensure(h, p, cap, need));
+  GPK_CK(h, cudaMemset(*p, 0, (size_t)need * sizeof(double)));
+  GPK_CK(h, cudaStreamSynchronize(0));
+  return 0;
+}
+
 static int ensure_events(Handle* h, size_t count) {
   while (h->ev.size() < count) {
     cudaEvent_t e;
@@ -530,6 +541,8 @@ static int alloc_problem(Handle* h, int64_t n, int D) {
     GPK_CK(h, cudaMalloc((void**)&h->dXs, (size_t)np * D * sizeof(double)));
     GPK_CK(h, cudaMalloc((void**)&h->dScale, (size_t)(D + 8) * sizeof(double)));
     GPK_CK(h, cudaMalloc((void**)&h->dDinv, (size_t)np * NB * sizeof(double)));
+    GPK_CK(h, cudaMemset(h->dDinv, 0, (size_t)np * NB * sizeof(double)));     // see ensure_zero
+    GPK_CK(h, cudaStreamSynchronize(0));
     GPK_CK(h, cudaMalloc((void**)&h->dB, (size_t)np * sizeof(double)));
     GPK_CK(h, cudaMalloc((void**)&h->dZ, (size_t)np * sizeof(double)));
     GPK_CK(h, cudaMalloc((void**)&h->dAlpha, (size_t)np * sizeof(double)));
@@ -1481,7 +1494,14 @@ int gpk_dbg_diag(gpk_handle hh, const double* A128, double* L128, double* Linv12
   GPK_CK(h, cudaMalloc((void**)&dI, NB * NB * 8));
   GPK_CK(h, cudaMalloc((void**)&dS, 64 * 8));
   GPK_CK(h, cudaMalloc((void**)&dInfo, 16));
-  cudaMemcpyAsync(dA, A128, NB * NB * 8, cudaMemcpyHostToDevice, st);
+  // only the lower triangle goes up (the kernel reads nothing else), and the inverse starts from zeros (see ensure_zero):
+  // with GPK_DIAG_SKIPZ the kernel leaves the blocks above the block diagonal of both tiles as it finds them
+  std::vector<double> lower((size_t)NB * NB, 0.0);
+  for (int c = 0; c < NB; ++c)
+    for (int r = c; r < NB; ++r) lower[r + (size_t)c * NB] = A128[r + (size_t)c * NB];
+  cudaMemsetAsync(dI, 0, NB * NB * 8, st);
+  cudaMemcpyAsync(dA, lower.data(), NB * NB * 8, cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);                     // `lower` is pageable: the copy has left the host buffer after this
   cudaMemsetAsync(dInfo, 0, 16, st);
   cudaMemsetAsync(dS, 0, 64 * 8, st);
   int rc = launch_diag(h, st, dA, NB, dI, dS, dInfo, 0, reinterpret_cast<long long*>(dS + 8));

@@ -247,7 +247,7 @@ static int dist_reserve(Handle* h, int level) {
   const int nloc = (T > r) ? (T - 1 - r) / G + 1 : 0;
   const int64_t ncl = (int64_t)(nloc > 0 ? nloc : 1) * NB;
   GPK_TRY(ensure(h, &h->gA, &h->cgA, ld * ncl));
-  GPK_TRY(ensure(h, &h->gDinv, &h->cgDinv, ncl * NB));
+  GPK_TRY(ensure_zero(h, &h->gDinv, &h->cgDinv, ncl * NB));
   GPK_TRY(ensure(h, &h->gVec, &h->cgVec, np + T + 16 + (int64_t)T * NB + NB));
   GPK_TRY(ensure(h, &h->gPack, &h->cgPack, 2 * ld * NB));
   while (h->ev.size() < 5 * (size_t)T + 8) {
@@ -310,7 +310,7 @@ static int exact_eval_dist_impl(gpk_handle hh, int kind, int matern_d, const dou
 
   const int64_t ncl = (int64_t)(nloc > 0 ? nloc : 1) * NB;
   GPK_TRY(ensure(h, &h->gA, &h->cgA, ld * ncl));
-  GPK_TRY(ensure(h, &h->gDinv, &h->cgDinv, ncl * NB));
+  GPK_TRY(ensure_zero(h, &h->gDinv, &h->cgDinv, ncl * NB));
   // vectors: x (np) | parts (T) | res (16) | partial (T*NB) | xk staging (NB)
   GPK_TRY(ensure(h, &h->gVec, &h->cgVec, np + T + 16 + (int64_t)T * NB + NB));
   double* x = h->gVec;

@@ -267,9 +267,9 @@ int gpk_fitc_eval(gpk_handle hh, int kind, int matern_d, const double* hyp, int 
   GPK_TRY(ensure(h, &h->dUin, &h->capUin, M * D));
   GPK_TRY(ensure(h, &h->dUs, &h->capUs, Mp * D));
   GPK_TRY(ensure(h, &h->fKuu, &h->cKuu, Mp * Mp));
-  GPK_TRY(ensure(h, &h->fDinvU, &h->cDinvU, Mp * NB));
+  GPK_TRY(ensure_zero(h, &h->fDinvU, &h->cDinvU, Mp * NB));
   GPK_TRY(ensure(h, &h->fA2, &h->cA2, Mp * Mp));
-  GPK_TRY(ensure(h, &h->fDinv2, &h->cDinv2, Mp * NB));
+  GPK_TRY(ensure_zero(h, &h->fDinv2, &h->cDinv2, Mp * NB));
   GPK_TRY(ensure(h, &h->fVt, &h->cVt, np * Mp));
   GPK_TRY(ensure(h, &h->fVs, &h->cVs, np * Mp));
   GPK_TRY(ensure(h, &h->dAlphaU, &h->capAlphaU, Mp));

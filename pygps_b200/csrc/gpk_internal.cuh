@@ -259,6 +259,7 @@ int diag_init(Handle* h);
 int launch_small_nt(Handle* h, cudaStream_t st, const SmallArgs& a);
 
 int ensure(Handle* h, double** p, int64_t* cap, int64_t need_elems);
+int ensure_zero(Handle* h, double** p, int64_t* cap, int64_t need_elems);   // zero-filled when (re)allocated
 int oz_ensure(Handle* h, int which, int64_t n, int kw);
 int launch_oz_slice(Handle* h, int which, cudaStream_t st, const double* P, int64_t lda, int n, int kw, int row0 = 0,
                     int ntot = 0);

@@ -401,11 +401,12 @@ __device__ __forceinline__ void inv32_warp(const double* S, double* T, const dou
 // rows [32*rb0, 32*rb1) of the block inverse to global (dense 128x128, pitch 128): diagonal blocks from T, block
 // (bi > bj) from S block (bj, bi), zeros above; `nthr` threads with index `t`
 __device__ __forceinline__ void inv_rows_to_global(const double* S, const double* T, double* __restrict__ Dinv, int rb0,
-                                                   int rb1, int t, int nthr) {
+                                                   int rb1, int t, int nthr, int skipz) {
   const int hr = (rb1 - rb0) * IB / 2;               // 16-byte pieces per column
   for (int idx = t; idx < hr * DB; idx += nthr) {
     const int r = rb0 * IB + (idx % hr) * 2, c = idx / hr;
     const int bi = r / IB, bj = c / IB, ri = r % IB, ci = c % IB;
+    if (skipz && bi < bj) continue;                   // a zero block the (zero-filled) buffer already holds
     double2 v = make_double2(0.0, 0.0);
     if (bi == bj) v = *reinterpret_cast<const double2*>(&T_(bi, ri, ci));
     else if (bi > bj) v = *reinterpret_cast<const double2*>(&S_(bj * IB + ri, bi * IB + ci));
@@ -432,7 +433,11 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <bool ASYNC_ST>
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_ovl_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ Dinv,
-                      double* __restrict__ logdet_slot, int* __restrict__ info, int gidx0, long long* dbg_clk) {
+                      double* __restrict__ logdet_slot, int* __restrict__ info, int gidx0, long long* dbg_clk, int skipz) {
+  // skipz: the six 32x32 blocks above the block diagonal are not stored - 48 KB of zeros of the inverse (its buffer is
+  // zero-filled when allocated, ensure_zero) and 48 KB of the L tile (nobody reads a diagonal tile above its diagonal: the
+  // diagonal blocks enter every later product through their inverses).  The kernel ends with the drain of its own stores
+  // through one SM (profiles/r2_diag_clk.md); this takes 96 of the 256 KB away.
   extern __shared__ __align__(16) double dsm[];
   int dbg_i = 0;
 #define DBG_T() do { if (dbg_clk && threadIdx.x == 0) dbg_clk[dbg_i++] = clock64(); } while (0)
@@ -463,7 +468,7 @@ potrf_diag_ovl_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict
   }
   __syncthreads();
   DBG_T();
-  if (ASYNC_ST && warp >= 1 && warp <= 6) {
+  if (ASYNC_ST && !skipz && warp >= 1 && warp <= 6) {
     // the six 32x32 blocks above the block diagonal, of the L tile and of the inverse: zeros (lane = column)
     const int ub = warp - 1;                         // (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
     const int bj = (ub < 3) ? ub + 1 : (ub < 5 ? ub - 1 : 3), bi = (ub < 3) ? 0 : (ub < 5 ? 1 : 2);
@@ -617,6 +622,7 @@ potrf_diag_ovl_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict
   } else if (!ASYNC_ST && warp >= 4) {
     for (int idx = tid - 4 * 32; idx < DB * DB / 2; idx += DIAG_THREADS - 4 * 32) {
       const int r = (idx % (DB / 2)) * 2, c = idx / (DB / 2);
+      if (skipz && r / IB < c / IB) continue;
       double2 v = *reinterpret_cast<const double2*>(&S_(r, c));
       if (r < c) v.x = 0.0;
       if (r + 1 < c) v.y = 0.0;
@@ -651,7 +657,7 @@ potrf_diag_ovl_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict
     }
     bulk_wait_read_all();
   } else {
-    inv_rows_to_global(S, T, Dinv, 0, DB / IB, tid, DIAG_THREADS);
+    inv_rows_to_global(S, T, Dinv, 0, DB / IB, tid, DIAG_THREADS, skipz);
   }
   __syncthreads();
   DBG_T();
@@ -1075,10 +1081,11 @@ int diag_init(Handle* h) {
 int launch_diag(Handle* h, cudaStream_t st, double* Ablk, int64_t lda, double* Dinv, double* logdet_slot, int* info,
                 int gidx0, long long* dbg_clk) {
   const int ovl = env_int("GPK_DIAG_OVL", 1);             // 0: the inverse after the factorisation (A/B runs)
+  const int skipz = env_int("GPK_DIAG_SKIPZ", 0);        // 1: the zero blocks above the block diagonal are not stored
   if (ovl >= 2)       // 2: every finished piece leaves at once by cp.async.bulk
-    potrf_diag_ovl_kernel<true><<<1, DIAG_THREADS, DIAG_OVL_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
+    potrf_diag_ovl_kernel<true><<<1, DIAG_THREADS, DIAG_OVL_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk, skipz);
   else if (ovl == 1)  // 1: the inverse by row blocks in the shadow of the 32x32 factorisations, ordinary stores
-    potrf_diag_ovl_kernel<false><<<1, DIAG_THREADS, DIAG_OVL_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
+    potrf_diag_ovl_kernel<false><<<1, DIAG_THREADS, DIAG_OVL_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk, skipz);
   else
     potrf_diag_kernel<false><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(Ablk, lda, Dinv, logdet_slot, info, gidx0, dbg_clk);
   h->stats.launches++;
