@@ -113,6 +113,109 @@ def diag_block(Ablk):
     return L, S.copy(order="F"), logdet, info
 
 
+def diag_block_ovl(Ablk):
+    """potrf_diag_ovl_kernel: the same factorisation with the block inverse built by ROW blocks in the shadow of the
+    32x32 factorisations.  `S` is the kernel's shared-memory tile: its strictly-upper 32x32 blocks, unused by the
+    factorisation, hold the inverse - block (j, i) of S is W[i, j] - and `Zs` holds Z[i, j] = sum_{k=j}^{i-1} L[i,k] W[k,j]
+    of the row block in progress; W[i, j] = -W_ii Z[i, j].  Steps S1-S3 are what warps 1-7 do while warp 0 factors
+    diagonal block i.  Returns (L, inv(L), sum log diag, info)."""
+    S = np.tril(Ablk).copy(order="F")
+    nblk = NB // IB
+    T = [None] * nblk
+    Zs = [None] * (nblk - 1)
+    logdet = 0.0
+    info = 0
+
+    def blk(bi, bj):
+        return S[bi * IB:(bi + 1) * IB, bj * IB:(bj + 1) * IB]
+
+    def inv32(b):                       # inv32_warp: lane r solves x L' = e_r, right-looking; x = column r of W
+        Lb = np.tril(blk(b, b))
+        W = np.zeros((IB, IB))
+        for r in range(IB):
+            x = np.zeros(IB)
+            x[r] = 1.0
+            for k in range(IB):
+                x[k] = x[k] * (1.0 / Lb[k, k])
+                x[k + 1:] -= x[k] * Lb[k + 1:, k]
+            W[:, r] = x
+        return W
+
+    for jb in range(nblk):
+        j0 = jb * IB
+        # warp 0: LDL' of diagonal block jb
+        a, lg, bad = ldl_block(blk(jb, jb).copy())
+        # warps 1-7, meanwhile (jb >= 1): nothing below touches block (jb, jb)
+        if jb >= 1:
+            i = jb
+            T[i - 1] = inv32(i - 1)                                     # S1
+            for j in range(i - 1):                                      # S2: row block i-1 of the inverse
+                blk(j, i - 1)[...] = -(T[i - 1] @ Zs[j])
+            for j in range(i):                                          # S3: Z of row block i
+                z = blk(i, j) @ T[j]
+                for k in range(j + 1, i):
+                    z = z + blk(i, k) @ blk(j, k)
+                Zs[j] = z
+        logdet += lg
+        if bad and info == 0:
+            info = j0 + bad
+        blk(jb, jb)[...] = np.tril(a)
+        if jb < nblk - 1:
+            r0 = j0 + IB
+            Ljj = np.tril(blk(jb, jb))
+            S[r0:, j0:j0 + IB] = np.linalg.solve(Ljj, S[r0:, j0:j0 + IB].T).T      # sub-panel solve X Ljj' = Y
+            P = S[r0:, j0:j0 + IB]
+            upd = P @ P.T
+            nrb = nblk - 1 - jb
+            for ib in range(nrb):
+                for cb in range(ib + 1):
+                    S[r0 + ib * IB:r0 + (ib + 1) * IB, r0 + cb * IB:r0 + (cb + 1) * IB] -= \
+                        upd[ib * IB:(ib + 1) * IB, cb * IB:(cb + 1) * IB]
+    L = np.tril(S).copy(order="F")
+    last = nblk - 1
+    T[last] = inv32(last)
+    for j in range(last):
+        blk(j, last)[...] = -(T[last] @ Zs[j])
+    Dinv = np.zeros((NB, NB), order="F")
+    for bi in range(nblk):
+        for bj in range(bi + 1):
+            Dinv[bi * IB:(bi + 1) * IB, bj * IB:(bj + 1) * IB] = T[bi] if bi == bj else blk(bj, bi)
+    return L, Dinv, logdet, info
+
+
+def small_nt(C, A, B, K, mode, tri=False, copy_dst=None):
+    """small_nt_kernel: one 128x128 tile of C (op)= A(128 x K) B(128 x K)' as sixteen independent 32x32 blocks, each
+    walking the contraction in chunks of 128; with copy_dst the CTAs of block column 0 also store their 32 x 128 strip
+    of A there (K == 128).  Every block reads ONLY A, B and its own block of C - asserted by working on snapshots."""
+    A0, B0, C0 = A.copy(), B.copy(), C.copy()
+    for bj in range(4):
+        for bi in range(4):
+            if tri and bj > bi:
+                continue
+            acc = np.zeros((32, 32))
+            for c0 in range(0, K, 128):
+                acc += A0[32 * bi:32 * bi + 32, c0:c0 + 128] @ B0[32 * bj:32 * bj + 32, c0:c0 + 128].T
+            new = acc if mode == 0 else C0[32 * bi:32 * bi + 32, 32 * bj:32 * bj + 32] - acc
+            cb = C[32 * bi:32 * bi + 32, 32 * bj:32 * bj + 32]
+            if tri and bi == bj:
+                m = np.tril(np.ones((32, 32), dtype=bool))
+                cb[m] = new[m]
+            else:
+                cb[...] = new
+            if copy_dst is not None and bj == 0:
+                assert K == 128
+                copy_dst[32 * bi:32 * bi + 32, :] = A0[32 * bi:32 * bi + 32, :128]
+
+
+def chain_head_pair(tile_p1p, Dinv_p, tile_p1p1):
+    """The two products behind diag(p) on the panel stream (api.cu, small_heads): the solved head tile goes to a
+    scratch tile (sixteen CTAs cannot work in place), the update of the next diagonal tile reads the scratch tile as
+    both operands and copies it home."""
+    scratch = np.zeros((NB, NB), order="F")
+    small_nt(scratch, tile_p1p, Dinv_p, NB, mode=0)
+    small_nt(tile_p1p1, scratch, scratch, NB, mode=1, tri=True, copy_dst=tile_p1p)
+
+
 def trsv_fwd(A, Dinv, b, z, k, T):
     zk = Dinv[k] @ b[k * NB:(k + 1) * NB]
     z[k * NB:(k + 1) * NB] = zk

@@ -238,3 +238,47 @@ def test_fixed_row_scales_with_shared_slices_specification(n, W, W1):
     Lref = np.linalg.cholesky(A0)
     assert np.max(np.abs(np.tril(A[:n, :n]) - Lref)) <= 1e-11 * np.max(np.abs(Lref))
     assert abs(parts.sum() - np.log(np.diag(Lref)).sum()) <= 1e-10 * abs(parts.sum())
+
+
+def test_overlapped_diag_block_builds_the_same_inverse_by_row_blocks():
+    """Specification of potrf_diag_ovl_kernel: W[i,j] = -W_ii sum_k L[i,k] W[k,j], row block by row block, with the
+    inverse parked in the strictly-upper 32x32 blocks of the tile the factorisation works in."""
+    A = _spd(128, seed=4)
+    L, Li, ld, info = br.diag_block_ovl(np.asfortranarray(A))
+    L0, Li0, ld0, info0 = br.diag_block(np.asfortranarray(A))
+    Lref = np.linalg.cholesky(A)
+    assert info == 0 and info0 == 0
+    assert np.allclose(L, Lref, rtol=1e-12, atol=1e-12)
+    assert np.all(np.triu(L, 1) == 0) and np.all(np.triu(Li, 1) == 0)
+    assert np.allclose(Li @ Lref, np.eye(128), atol=1e-10)
+    assert np.allclose(Li, Li0, rtol=1e-9, atol=1e-12)
+    assert abs(ld - ld0) < 1e-12 * abs(ld0)
+    B = A.copy()
+    B[70, 70] = -3.0
+    assert br.diag_block_ovl(np.asfortranarray(B))[3] == 71
+
+
+@pytest.mark.parametrize("K", [128, 512])
+def test_chain_products_as_sixteen_independent_blocks(K):
+    rng = np.random.default_rng(K)
+    A = np.asfortranarray(rng.standard_normal((128, K))); B = np.asfortranarray(rng.standard_normal((128, K)))
+    C = np.asfortranarray(rng.standard_normal((128, 128)))
+    got = C.copy(order="F")
+    br.small_nt(got, A, B, K, mode=1, tri=True)
+    lo = np.tril(np.ones((128, 128), bool))
+    assert np.allclose(got[lo], (C - A @ B.T)[lo], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(got[~lo], C[~lo])
+
+
+def test_chain_head_pair_through_the_scratch_tile():
+    """X = A W' -> scratch; C -= X X' (lower) from the scratch tile; X copied home by block column 0 of the update."""
+    rng = np.random.default_rng(3)
+    A = np.asfortranarray(rng.standard_normal((128, 128))); W = np.asfortranarray(np.tril(rng.standard_normal((128, 128))))
+    C = np.asfortranarray(rng.standard_normal((128, 128)))
+    a, c = A.copy(order="F"), C.copy(order="F")
+    br.chain_head_pair(a, W, c)
+    X = A @ W.T
+    lo = np.tril(np.ones((128, 128), bool))
+    assert np.allclose(a, X, rtol=1e-12, atol=1e-12)
+    assert np.allclose(c[lo], (C - X @ X.T)[lo], rtol=1e-12, atol=1e-11)
+    assert np.array_equal(c[~lo], C[~lo])
