@@ -337,7 +337,7 @@ def oz_update_from_digits(C, dr, dc, sr, sc_, S=7, RB=8, lower=True):
         C -= upd
 
 
-def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=None, fixed_scale=False):
+def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=None, fixed_scale=False, headk=0, ovl=False):
     """api.cu potrf_device (stream order flattened): three-level blocking - level-1 blocks of W1 panels (W1=0: same as
     the sub-blocks), sub-blocks of W panels, single panels.  oz: trailing updates through oz_syrk.
     fixed_scale (with oz; NOT on the device yet - the executable specification of DESIGN section 8 item 2): row i is
@@ -411,7 +411,7 @@ def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=No
             se = min(sb + w2, pe)
             for p in range(sb, se):
                 s = slice(p * NB, (p + 1) * NB)
-                L, Li, ld, inf_p = diag_block(A[s, s])
+                L, Li, ld, inf_p = (diag_block_ovl if ovl else diag_block)(A[s, s])
                 A[s, s] = L
                 Dinv[p], parts[p] = Li, ld
                 if inf_p and not info:
@@ -428,8 +428,11 @@ def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=No
                 else:
                     # head (panel stream): tile (p+1,p) solved, tile (p+1,p+1) updated
                     h = slice((p + 1) * NB, (p + 2) * NB)
-                    gemm_nt(0, A[h, s], A[h, s].copy(), Li, NB, 1, 1)
-                    gemm_nt(1, A[h, h], A[h, s], A[h, s], NB, 1, 1, tri=1)
+                    if headk == 2 or (headk == 1 and not bbig[j]):
+                        chain_head_pair(A[h, s], Li, A[h, h])          # small_nt_kernel x 2 through the scratch tile
+                    else:
+                        gemm_nt(0, A[h, s], A[h, s].copy(), Li, NB, 1, 1)
+                        gemm_nt(1, A[h, h], A[h, s], A[h, s], NB, 1, 1, tri=1)
                     # tail (s_tail): rows p+2.. solved; column p+1 below its diagonal tile; columns p+2..se-1
                     t0 = (p + 2) * NB
                     pan = A[t0:, s]
@@ -451,7 +454,10 @@ def potrf_device(A, b=None, W=2, W1=0, w1_minrem=0, oz=False, split=True, W2B=No
                 h = slice(pe * NB, (pe + 1) * NB)
                 pan0 = A[h, pb * NB:pe * NB]
                 saved = A[h, h].copy()
-                gemm_nt(1, A[h, h], pan0, pan0, (pe - pb) * NB, 1, 1, tri=1)
+                if headk:
+                    small_nt(A[h, h], pan0, pan0, (pe - pb) * NB, mode=1, tri=True)
+                else:
+                    gemm_nt(1, A[h, h], pan0, pan0, (pe - pb) * NB, 1, 1, tri=1)
                 mine = A[h, h].copy()
                 A[h, h] = saved
                 update(pe, T, pb, pe)

@@ -282,3 +282,19 @@ def test_chain_head_pair_through_the_scratch_tile():
     assert np.allclose(a, X, rtol=1e-12, atol=1e-12)
     assert np.allclose(c[lo], (C - X @ X.T)[lo], rtol=1e-12, atol=1e-11)
     assert np.array_equal(c[~lo], C[~lo])
+
+
+@pytest.mark.parametrize("n,W,W1,W2B,headk", [(1100, 2, 0, None, 2), (1500, 3, 6, 4, 1), (1500, 3, 6, 4, 2), (900, 2, 4, 3, 1)])
+def test_chain_through_small_products_and_overlapped_diag_gives_the_same_factor(n, W, W1, W2B, headk):
+    """api.cu with GPK_POTRF_HEADK / GPK_DIAG_OVL: head products through the scratch tile, the hand-over tile in 32x32
+    blocks, the diagonal kernel with the row-block inverse - same factor, same forward solve."""
+    A0 = _spd(n, seed=n + headk)
+    rng = np.random.default_rng(n)
+    b0 = rng.standard_normal(n)
+    A, b = br.pad_spd(A0), np.concatenate([b0, np.zeros(-n % 128)])
+    Dinv, parts, info, z = br.potrf_device(A, b.copy(), W=W, W1=W1, w1_minrem=2, W2B=W2B, headk=headk, ovl=True)
+    Lref = np.linalg.cholesky(A0)
+    assert info == 0
+    assert np.allclose(np.tril(A)[:n, :n], Lref, rtol=1e-10, atol=1e-10)
+    assert np.allclose(z[:n], sla.solve_triangular(Lref, b0, lower=True), rtol=1e-9, atol=1e-9)
+    assert abs(parts.sum() - np.log(np.diag(Lref)).sum()) < 1e-10 * abs(parts.sum())
