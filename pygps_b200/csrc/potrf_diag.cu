@@ -1,23 +1,23 @@
-// potrf_diag.cu - the latency-critical panel kernels of the blocked Cholesky.
+// potrf_diag.cu - the latency-critical kernels of the blocked Cholesky: everything that sits ON the dependent panel chain.
 //
-//  potrf_diag_kernel : factor one 128x128 diagonal block (lower Cholesky) AND
-//                      invert the factor, in shared memory, one CTA.
-//     - 32x32 diagonal sub-blocks are factored by ONE WARP holding one matrix
-//       row per lane in registers; pivots and multipliers travel by warp
-//       shuffle (no shared-memory round trips, no block barriers).
-//     - the sub-block inverse is a per-lane forward substitution (lane c owns
-//       column c of the inverse), again in registers.
-//     - sub-panel solves / trailing updates / the block inverse are small
-//       shared-memory GEMMs by all 8 warps.
-//    The inverse turns the panel TRSM and every later triangular solve with
-//    this block into the tensor-pipe GEMM of gemm_nt.cu.
-//    Replaces the unblocked part of LAPACK dpotrf called at
-//    /root/reference/pyGPs/Core/tools.py:61; emits sum(log(diag L)) for
-//    Core/inf.py:370 and a LAPACK-style info for Core/tools.py:62-77.
+//  potrf_diag_ovl_kernel : factor one 128x128 diagonal block (lower Cholesky) AND invert the factor, in shared memory,
+//                          one CTA.  Warp 0 factors the 32x32 diagonal sub-blocks (square-root-free LDL', one matrix row
+//                          per lane, columns travelling through shared memory); the sub-panel solves and trailing updates
+//                          are small shared-memory GEMMs by all 8 warps (DMMA); the inverse is built by ROW blocks by
+//                          warps 1-7 while warp 0 factors the next sub-block.  The default (GPK_DIAG_OVL=1).
+//  potrf_diag_kernel     : the round-1 form of the same (inverse after the factorisation, GPK_DIAG_OVL=0), and with
+//                          INV_ONLY the inverses + log-determinant shares of an UPLOADED factor, all blocks in one launch
+//                          (gpk_set_factor).
+//    The inverse turns the panel TRSM and every later triangular solve with this block into a tensor-pipe GEMM.
+//    Replaces the unblocked part of LAPACK dpotrf called at /root/reference/pyGPs/Core/tools.py:61; emits
+//    sum(log(diag L)) for Core/inf.py:370 and a LAPACK-style info for Core/tools.py:62-77.
 //
-//  trsv_fwd_step / trsv_bwd_step : one block step of the forward / backward
-//    substitution with a single right-hand side (solve_chol with B=(n,1),
-//    Core/tools.py:96, as used at Core/inf.py:363).
+//  small_nt_kernel       : the two products behind every diagonal block (tile (p+1,p) times Dinv_p', rank-128 update of
+//                          tile (p+1,p+1)) and the rank-512 update of the next diagonal tile at a level-1 hand-over, as
+//                          sixteen 32x32-block CTAs per 128x128 tile.
+//
+//  trsv_fwd_kernel / trsv_bwd_kernel / trsv_bwd_persistent_kernel : the forward / backward substitution with a single
+//    right-hand side (solve_chol with B=(n,1), Core/tools.py:96, as used at Core/inf.py:363).
 #include "gpk_internal.cuh"
 
 namespace gpk {
